@@ -1,0 +1,193 @@
+/* pk_anchor.h — C ABI of libpkanchor.so, the B200-native pan-kmer anchoring engine.
+ *
+ * This is the drop-in boundary for the `panagram index` anchoring path. Each
+ * entry point names the reference interface it replaces (paths relative to the
+ * kjenike/panagram tree). Plain pointers and sizes only; no C++ or torch types;
+ * no exceptions cross the boundary. All functions return PK_OK (0) or a negative
+ * pk_status; pk_last_error() gives a thread-local message for the last failure.
+ *
+ * Semantics, bit-exact to the reference:
+ *   row[p] bit g = 1  iff  canon(seq[p:p+k]) is in K_g
+ *   canon(x) = min(x, revcomp(x)) as a 2k-bit integer, A=0 C=1 G=2 T=3, first base
+ *   most significant (kmer_api.h:373-386); only ACGTacgt are symbols
+ *   (kmer_api.h:264-275): a window containing any other byte gives an all-zero row
+ *   (kmc_file.cpp:972-993). Genome g lives in byte g/8, bit g%8 of a row
+ *   (cpp/anchor.cpp:155-159). k <= 32.
+ *
+ * Threading: an engine is bound to one CUDA device; calls on one engine must be
+ * serialised by the caller. Multi-GPU = one engine (one process) per GPU, each
+ * owning a contiguous genome shard [genome_begin, genome_end).
+ */
+#ifndef PK_ANCHOR_H
+#define PK_ANCHOR_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+typedef enum pk_status {
+    PK_OK = 0,
+    PK_EINVAL = -1,       /* bad argument */
+    PK_EIO = -2,          /* file missing / bad KMC marker (OpenForRA returning false, kmc_file.cpp:30-39) */
+    PK_ECUDA = -3,        /* CUDA runtime error */
+    PK_ENOMEM = -4,       /* host or device allocation failed / table full */
+    PK_EUNSUPPORTED = -5, /* k > 32, Quake-mode DB, non-canonical DB */
+    PK_ESTATE = -6        /* call out of order (e.g. probe before finalize) */
+} pk_status;
+
+int pk_abi_version(void);
+const char *pk_last_error(void);
+/* number of CUDA devices visible; 0 when none (never an error) */
+int pk_device_count(void);
+
+/* ---- KMC database reader -------------------------------------------------
+ * Replaces CKMCFile::OpenForRA + ReadParamsFrom_prefix_file_buf
+ * (KMC/kmc_api/kmc_file.cpp:25-53,178-325; bound as KMCFile.OpenForRA /
+ * KMCFile.Info in KMC/py_kmc_api/py_kmc_api.cpp:85,98). Host only. Accepts both
+ * KMC1 (kmc_tools output: .onehot, bitvec{i}) and KMC2 (kmc output: .count). */
+typedef struct pk_kmcdb pk_kmcdb;
+typedef struct pk_kmcdb_info {
+    uint32_t kmer_length, mode, counter_size, lut_prefix_length, signature_len;
+    uint32_t kmc_version;       /* 0 = KMC1, 0x200 = KMC2 */
+    uint32_t both_strands;
+    uint32_t _pad;
+    uint64_t min_count, max_count, total_kmers;
+} pk_kmcdb_info;
+int pk_kmcdb_open(const char *prefix, pk_kmcdb **out);
+int pk_kmcdb_info_get(const pk_kmcdb *db, pk_kmcdb_info *info);
+void pk_kmcdb_close(pk_kmcdb *db);
+
+/* ---- engine ---------------------------------------------------------------
+ * Replaces KMCdb::KMCdb (cpp/anchor.cpp:21-35) / Genome._load_kmc
+ * (panagram/index.py:847-863): instead of ceil(N/32) merged "bitvec" databases
+ * searched by LUT + binary search, the engine keeps one bucketed hash table per
+ * genome in HBM. */
+typedef struct pk_engine pk_engine;
+typedef struct pk_config {
+    uint32_t k;              /* k-mer length, 1..32 */
+    uint32_t n_genomes;      /* N: total genomes = bit columns of a full row */
+    uint32_t genome_begin;   /* this engine's shard [genome_begin, genome_end) ... */
+    uint32_t genome_end;     /* ... multiples of 8 unless genome_end == n_genomes */
+    int32_t device;          /* CUDA ordinal */
+    uint32_t lowres_step;    /* 100 (cpp/anchor.cpp:170; index.py lowres_step) */
+    uint32_t max_bin_len;    /* 200000 (cpp/anchor.cpp:114; max_bin_kbp*1000) */
+    uint32_t min_bin_count;  /* 100 (cpp/anchor.cpp:116; min_bin_count) */
+    float load_factor;       /* table fill target, 0 < f <= 0.9; 0 selects the default 0.5 */
+    uint32_t chunk_positions;/* positions per pipelined chunk in pk_anchor_chrom; 0 = default */
+} pk_config;
+int pk_engine_create(const pk_config *cfg, pk_engine **out);
+void pk_engine_destroy(pk_engine *e);
+
+/* Table construction. genome ids are GLOBAL (0..N-1); ids outside this engine's
+ * shard are accepted and ignored (so every rank can run the same loop).
+ *
+ * pk_engine_reserve: size genome g's table for up to max_keys distinct k-mers.
+ * pk_engine_add_kmc: all k-mers of a per-genome KMC database with
+ *   min_count <= counter <= max_count (the filter of kmc_file.cpp:1396), i.e. the
+ *   set K_g that rule kmc_count produces (workflow/Snakefile:81-110). Reserves
+ *   automatically.
+ * pk_engine_add_bitvec: a merged bitvec database (rule kmc_bitvec,
+ *   workflow/Snakefile:54-69): counter bit j set => k-mer belongs to genome
+ *   first_genome + j (index.py:407-415). Reserves automatically.
+ * pk_engine_add_keys: canonical k-mer integers from host memory.
+ * pk_engine_add_sequence: every canonical k-mer of an ASCII sequence (what
+ *   `kmc -ci1 -fm` would count for a FASTA record; kmc_core/splitter.cpp:44-47).
+ *   Needs a prior pk_engine_reserve. */
+int pk_engine_reserve(pk_engine *e, uint32_t genome, uint64_t max_keys);
+int pk_engine_add_kmc(pk_engine *e, uint32_t genome, const char *kmc_prefix);
+int pk_engine_add_bitvec(pk_engine *e, uint32_t first_genome, const char *kmc_prefix);
+int pk_engine_add_keys(pk_engine *e, uint32_t genome, const uint64_t *canon_kmers, uint64_t n);
+int pk_engine_add_sequence(pk_engine *e, uint32_t genome, const char *ascii, uint64_t len);
+/* as pk_engine_add_sequence, from ASCII already resident in device memory */
+int pk_engine_add_sequence_device(pk_engine *e, uint32_t genome, const void *d_ascii, uint64_t len);
+int pk_engine_finalize(pk_engine *e);
+
+typedef struct pk_table_stats {
+    uint64_t n_keys;        /* distinct k-mers stored */
+    uint64_t n_buckets;     /* 32-byte buckets (4 x uint64 slots) */
+    uint64_t n_overflow;    /* keys not in their home bucket */
+    uint64_t bytes;         /* device bytes */
+} pk_table_stats;
+int pk_engine_table_stats(const pk_engine *e, uint32_t genome, pk_table_stats *out);
+
+/* ---- the hot path, host buffers ---------------------------------------------
+ * pk_bin_len: the bin-length rule of KMCdb::write_bits (cpp/anchor.cpp:114-118) /
+ *   Genome.bin_bitsum (index.py:1169-1172). 0 when nkmers < min_bin_count.
+ * pk_anchor_chrom: replaces KMCdb::write_bits (cpp/anchor.cpp:112-195) and
+ *   Genome._write_bitmap + the per-chromosome reductions of Genome.run_anchor
+ *   (index.py:949-969,1044-1051) for ONE chromosome, with the
+ *   CKMCFile::GetCountersForRead calls (kmc_file.cpp:873-1027) inside it.
+ *   H2D, pack, probe, reduce and D2H are pipelined over chunks.
+ *     ascii      [len]                          chromosome bytes, any case
+ *     bitmap1    [nkmers * row_bytes]           step-1 rows, nkmers = len-k+1
+ *     bitmap_low [ceil(nkmers/step) * row_bytes] rows with p % lowres_step == 0
+ *     bin_hist   [nbins * (N_local+1)]          per-bin histogram of popcount(row),
+ *                                               nbins = ceil(nkmers/binlen)
+ *     col_sums   [N_local]  (+=)                per-genome set-bit counts (index.py:1051)
+ *   row_bytes = ceil(N_local/8) where N_local = genome_end - genome_begin.
+ *   Any output pointer may be NULL to skip it. len < k: returns PK_OK with
+ *   *nkmers_out = 0 and writes nothing (GetCountersForRead clears and returns
+ *   false, kmc_file.cpp:878-882). nkmers < min_bin_count (binlen 0, a division
+ *   by zero in the reference, cpp/anchor.cpp:116-120): bitmaps and col_sums are
+ *   produced, bin_hist must be NULL or PK_EINVAL is returned. */
+uint64_t pk_bin_len(const pk_config *cfg, uint64_t nkmers);
+int pk_anchor_chrom(pk_engine *e, const char *ascii, uint64_t len,
+                    uint8_t *bitmap1, uint8_t *bitmap_low,
+                    uint64_t *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out);
+
+/* Replaces CKMCFile::GetCountersForRead as the anchoring path calls it on
+ * bitvec database `dbi` (cpp/anchor.cpp:148; index.py:932-938):
+ * counters[p] bit j = presence in genome 32*dbi + j. Returns PK_OK and
+ * *n_out = len-k+1, or *n_out = 0 when len < k. Genomes outside this engine's
+ * shard read as 0. */
+int pk_get_counters_for_read(pk_engine *e, uint32_t dbi, const char *read, uint64_t len,
+                             uint32_t *counters, uint64_t *n_out);
+
+/* pinned host memory for the buffers above (optional; pageable memory works,
+ * but copies then do not overlap with kernels) */
+int pk_host_alloc(void **out, size_t bytes);
+int pk_host_free(void *p);
+
+/* ---- the hot path, device buffers (building blocks for multi-GPU hosts) ------
+ * All pointers are device pointers on the engine's device; `stream` is a
+ * cudaStream_t passed as void* (NULL = the engine's own stream). Nothing
+ * synchronises; the caller orders work on `stream`.
+ *
+ * pk_pack_device:   ASCII -> 2-bit words (32 bases per uint64, first base in the
+ *                   two most significant bits) + invalid-base mask (1 bit per base,
+ *                   LSB first, uint32 per 32 bases). d_words/d_mask need
+ *                   pk_packed_words(len) uint64 / uint32 elements.
+ * pk_probe_device:  rows for positions [p0, p0+n) of the packed sequence into
+ *                   d_rows + (p - p0) * row_stride + col_offset, writing
+ *                   ceil(N_local/8) bytes per row.
+ * pk_reduce_device: per-bin popcount histogram (+=, N_cols+1 uint64 per bin,
+ *                   bin = (p_first + i) / binlen), per-column sums (+=) and the
+ *                   low-res rows (rows with p = p_first+i, p % step == 0, written at
+ *                   index p/step - ceil(p_first/step)) of n full rows.
+ * pk_interleave_device: [R][n][w] column planes (an all-gather of per-rank rows)
+ *                   -> [n][row_stride] rows, plane r at byte offset r*w. */
+uint64_t pk_packed_words(uint64_t len);
+int pk_pack_device(pk_engine *e, const void *d_ascii, uint64_t len, void *d_words, void *d_mask, void *stream);
+int pk_probe_device(pk_engine *e, const void *d_words, const void *d_mask, uint64_t p0, uint64_t n,
+                    void *d_rows, uint32_t row_stride, uint32_t col_offset, void *stream);
+int pk_reduce_device(pk_engine *e, const void *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first,
+                     uint64_t n, uint64_t binlen, void *d_bin_hist, void *d_col_sums,
+                     void *d_rows_low, uint32_t lowres_step, void *stream);
+int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w,
+                         void *d_rows, uint32_t row_stride, void *stream);
+
+/* timing / accounting of the last pk_anchor_chrom or pk_get_counters_for_read */
+typedef struct pk_stats {
+    float h2d_ms, pack_ms, probe_ms, reduce_ms, d2h_ms, total_ms;
+    uint64_t positions, probes, probe_launches, kernel_launches;
+} pk_stats;
+int pk_engine_stats(const pk_engine *e, pk_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,95 @@
+"""`anchor_fasta`: one anchor genome -> its ``anchor/<name>/`` directory.
+
+Host-side mirror of ``KMCdb::anchor_fasta`` (``cpp/anchor.cpp:37-109``) and of
+``Genome.run_anchor`` (``panagram/index.py:1012-1097``): parse the FASTA, run every
+chromosome through the engine (GPU), stream the rows into BGZF, and emit
+``chrs.tsv``, ``bitsum.bins.tsv`` and ``total_paircounts.csv``.
+"""
+from __future__ import annotations
+
+import gzip
+import os
+from pathlib import Path
+
+import numpy as np
+
+from . import layout
+from .engine import Engine
+
+
+def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
+    """[(name, uint8 sequence)] with the C++ reference's rules (cpp/anchor.cpp:74-100):
+    the record name is the header up to the first space, sequence lines are
+    concatenated verbatim (a trailing \\r stays in the sequence unless strip_cr,
+    which gives Biopython's behaviour, index.py:922-930). gzip-aware like
+    Genome.iter_fasta."""
+    path = str(path)
+    if path.endswith(".gz") or path.endswith(".bgz"):
+        with gzip.open(path, "rb") as fh:
+            raw = fh.read()
+    else:
+        raw = Path(path).read_bytes()
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    nl = np.flatnonzero(buf == 10)
+    starts = np.concatenate(([0], nl + 1))
+    ends = np.concatenate((nl, [buf.size]))
+    if starts.size and starts[-1] >= buf.size:          # file ends with \n: no empty last line
+        starts, ends = starts[:-1], ends[:-1]
+    if strip_cr:
+        cr = (ends > starts) & (buf[np.maximum(ends - 1, 0)] == 13)
+        ends = ends - cr
+    is_hdr = (ends > starts) & (buf[np.minimum(starts, buf.size - 1)] == ord(">")) if buf.size else np.zeros(0, bool)
+    hdr_idx = np.flatnonzero(is_hdr)
+    recs = []
+    keep = np.ones(buf.size, dtype=bool)
+    keep[nl] = False
+    if strip_cr:
+        keep[np.flatnonzero(buf == 13)] = False
+    for j, hi in enumerate(hdr_idx):
+        name = raw[starts[hi] + 1:ends[hi]].split(b" ")[0].decode()
+        if strip_cr:
+            name = name.split()[0] if name.split() else ""
+        lo = ends[hi] + 1
+        up = starts[hdr_idx[j + 1]] if j + 1 < hdr_idx.size else buf.size
+        lo = min(lo, up)
+        seg = buf[lo:up]
+        recs.append((name, np.ascontiguousarray(seg[keep[lo:up]])))
+    return recs
+
+
+def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[str] | None = None,
+                 bgzf_level: int = 6, threads: int | None = None, strip_cr: bool = False) -> dict:
+    """Anchor one genome and write its directory. Returns summary numbers.
+
+    The engine must hold all N genomes (single-GPU layout). Chromosomes shorter
+    than k + min_bin_count - 1 have no defined bins in the reference
+    (cpp/anchor.cpp:116-120 divides by zero): they raise ValueError here.
+    """
+    outdir = Path(outdir)
+    outdir.mkdir(parents=True, exist_ok=True)
+    threads = threads or min(32, os.cpu_count() or 1)
+    step = engine.lowres_step
+    w1 = layout.BgzfWriter(outdir / "bitmap.1.gz", bgzf_level, threads)
+    wl = layout.BgzfWriter(outdir / f"bitmap.{step}.gz", bgzf_level, threads)
+    chroms, bins = [], []
+    col = np.zeros(engine.n_local, dtype=np.uint64)
+    positions = 0
+    for cname, seq in parse_fasta(fasta, strip_cr=strip_cr):
+        nk = seq.size - engine.k + 1
+        if nk < 1 or engine.bin_len(nk) == 0:
+            raise ValueError(f"{fasta}: chromosome {cname!r} has {max(nk, 0)} k-mers; the reference "
+                             "needs at least min_bin_count (cpp/anchor.cpp:116-120)")
+        r = engine.anchor_chrom(seq)
+        w1.write(r["bitmap1"])
+        wl.write(r["low"])
+        chroms.append((cname, nk))
+        bins.append((r["binlen"], r["bin_hist"]))
+        col += r["col_sums"]
+        positions += nk
+    w1.close(outdir / "bitmap.1.gzi")
+    wl.close(outdir / f"bitmap.{step}.gzi")
+    (outdir / "chrs.tsv").write_text(layout.chrs_tsv(chroms))
+    (outdir / "bitsum.bins.tsv").write_text(layout.bins_tsv(engine.n_local, bins))
+    if genome_names is not None and name in genome_names:
+        (outdir / "total_paircounts.csv").write_text(layout.paircounts_csv(genome_names, col, name))
+    return {"positions": positions, "chroms": len(chroms), "col_sums": col}

@@ -1,0 +1,74 @@
+// Internal declarations shared by the translation units of libpkanchor.so.
+#ifndef PK_INTERNAL_H
+#define PK_INTERNAL_H
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pk_anchor.h"
+
+void pk_set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+
+// ---- host KMC reader (pk_kmcdb.cpp) ----
+struct pk_kmcdb {
+    std::string prefix;
+    pk_kmcdb_info info;
+    uint64_t single_lut = 0;        // 4^lut_prefix_length
+    std::vector<uint64_t> lut;      // flattened LUT(s) + guard = total_kmers
+    uint32_t suf_size = 0, rec_size = 0;
+    FILE *suf = nullptr;
+};
+int pk_kmcdb_open_impl(const char *prefix, pk_kmcdb **out);
+bool pk_kmcdb_read_records(pk_kmcdb *db, uint64_t first, uint64_t count, uint8_t *dst);
+void pk_kmcdb_close_impl(pk_kmcdb *db);
+
+// ---- device-side table descriptor ----
+// One bucketed open-addressing table per genome: n_buckets buckets of 4 x uint64
+// slots (32 B = one DRAM sector). Empty slot = ~0 (never a canonical k-mer for
+// k <= 32: T^k canonicalises to A^k = 0).
+struct PkTable {
+    unsigned long long *slots;
+    uint32_t n_buckets;
+    uint32_t _pad;
+};
+
+#define PK_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+// ---- kernel launchers (pk_kernels.cu); all asynchronous on `stream` ----
+typedef struct CUstream_st *pk_stream_t;
+void pk_launch_fill_empty(unsigned long long *slots, uint64_t n_slots, pk_stream_t s);
+void pk_launch_pack(const uint8_t *d_ascii, uint64_t len, uint64_t n_words, uint64_t *d_words, uint32_t *d_mask, pk_stream_t s);
+// insert every valid canonical k-mer of positions [0, n) of a packed sequence into table t
+void pk_launch_insert_seq(const uint64_t *d_words, const uint32_t *d_mask, uint64_t n, uint32_t k, PkTable t,
+                          unsigned long long *d_counters /*[3]: inserted, overflow, fail*/, pk_stream_t s);
+void pk_launch_insert_keys(const uint64_t *d_keys, uint64_t n, PkTable t, unsigned long long *d_counters, pk_stream_t s);
+// decode KMC suffix records [rec0, rec0+n) and insert. tables: one PkTable* array on device
+// (local genomes); mode 0: all into tables[local_genome]; mode 1 (bitvec): counter bit j ->
+// global genome first_genome + j, inserted when inside [gbegin, gend).
+struct PkDecodeArgs {
+    const uint8_t *d_recs;      // n records, rec_size bytes each
+    uint64_t rec0, n;
+    const uint64_t *d_lut;      // n_lut_slots + 1 entries
+    uint64_t n_lut_slots, single_lut;
+    uint32_t suf_size, counter_size, rec_size;
+    uint64_t min_count, max_count;
+    int bitvec;
+    uint32_t first_genome, gbegin, gend;
+    const PkTable *d_tables;    // indexed by local genome
+    uint32_t local_genome;      // mode 0
+    unsigned long long *d_counters;   // [3 * n_local]: inserted, overflow, fail per local genome
+};
+void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s);
+void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
+                     const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
+                     uint32_t col_offset, pk_stream_t s);
+void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
+                      uint64_t binlen, unsigned long long *d_bin_hist, unsigned long long *d_col_sums,
+                      uint8_t *d_rows_low, uint32_t step, pk_stream_t s);
+void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,
+                          uint32_t row_stride, pk_stream_t s);
+void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
+                           uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
+void pk_launch_table_overflow_count(PkTable t, unsigned long long *d_out, pk_stream_t s);
+#endif

@@ -1,0 +1,433 @@
+// sm_100a kernels of the anchoring path. Integer/byte work bounded by HBM; no tensor cores.
+//
+//   pack      ASCII -> 2-bit words + invalid mask         (replaces CKmerAPI::num_codes mapping, kmer_api.h:264-275)
+//   insert    canonical k-mers -> per-genome bucket table  (replaces the sorted suffix arrays of a KMC DB)
+//   decode    KMC suffix records -> k-mers -> insert       (replaces CKMCFile record decoding, kmc_file.cpp:421-490)
+//   probe     sliding canonical k-mer + membership probe   (replaces GetCountersForRead_kmc1_both_strands +
+//                                                           count_for_kmer_kmc1 + BinarySearch, kmc_file.cpp:905-1027,1321-1399)
+//   reduce    popcount histograms, column sums, low-res    (replaces cpp/anchor.cpp:160,169-190; index.py:1048-1051)
+//   interleave all-gathered column planes -> rows          (byte interleave of cpp/anchor.cpp:154-165 across ranks)
+#include <cuda_runtime.h>
+
+#include "pk_internal.h"
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t pk_hash32(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0x9E3779B97F4A7C15ull;
+    x ^= x >> 29;
+    x *= 0xBF58476D1CE4E5B9ull;
+    return (uint32_t)(x >> 32);
+}
+
+// reverse complement of a right-aligned 2k-bit k-mer (A=0 C=1 G=2 T=3: complement = 3-c = ~c)
+__device__ __forceinline__ uint64_t pk_revcomp(uint64_t fwd, uint32_t k) {
+    uint64_t x = __brevll(~fwd);
+    x = ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+    return x >> (64 - 2 * k);
+}
+
+// canonical k-mer of the window starting at base p; false if the window holds a non-ACGT byte.
+// words: 32 bases per uint64, first base in the top two bits. mask64: 1 bit per base, LSB first.
+__device__ __forceinline__ bool pk_window(const uint64_t *__restrict__ words, const uint64_t *__restrict__ mask64,
+                                          uint64_t p, uint32_t k, uint64_t &canon) {
+    const uint64_t m0 = mask64[p >> 6], m1 = mask64[(p >> 6) + 1];
+    const uint32_t t = (uint32_t)p & 63;
+    const uint64_t win = (m0 >> t) | ((m1 << 1) << (63 - t));
+    const uint64_t kmask = k == 64 ? ~0ull : ((1ull << k) - 1);
+    if (win & kmask) return false;
+    const uint64_t w0 = words[p >> 5], w1 = words[(p >> 5) + 1];
+    const uint32_t s = 2 * ((uint32_t)p & 31);
+    const uint64_t x = (w0 << s) | ((w1 >> 1) >> (63 - s));
+    const uint64_t fwd = x >> (64 - 2 * k);
+    const uint64_t rc = pk_revcomp(fwd, k);
+    canon = fwd < rc ? fwd : rc;     // kmer < kmer_rev ? kmer : kmer_rev  (kmc_file.cpp:998-1001)
+    return true;
+}
+
+struct u64x4 { unsigned long long a, b, c, d; };
+// one 32-byte bucket in one instruction (LDG.E.256, sm_100+)
+__device__ __forceinline__ u64x4 pk_ld_bucket(const unsigned long long *p) {
+    u64x4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------ fill / pack
+__global__ void __launch_bounds__(256) fill_empty_kernel(ulonglong2 *slots2, uint64_t n2) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n2; i += stride)
+        slots2[i] = make_ulonglong2(PK_EMPTY, PK_EMPTY);
+}
+void pk_launch_fill_empty(unsigned long long *slots, uint64_t n_slots, pk_stream_t s) {
+    const uint64_t n2 = n_slots / 2;   // n_slots is a multiple of 4
+    const unsigned grid = (unsigned)(n2 / 256 + 1 < 148u * 16 ? n2 / 256 + 1 : 148u * 16);
+    fill_empty_kernel<<<grid, 256, 0, s>>>((ulonglong2 *)slots, n2);
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ ascii, uint64_t len, uint64_t n_words,
+                                                   uint64_t *__restrict__ words, uint32_t *__restrict__ mask) {
+    const uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const uint64_t base = w * 32;
+    uint64_t bits = 0;
+    uint32_t inv = 0;
+    uint32_t chunk[8];
+    if (base + 32 <= len && (((uintptr_t)ascii) & 15) == 0) {
+        const uint4 a = *(const uint4 *)(ascii + base), b = *(const uint4 *)(ascii + base + 16);
+        chunk[0] = a.x; chunk[1] = a.y; chunk[2] = a.z; chunk[3] = a.w;
+        chunk[4] = b.x; chunk[5] = b.y; chunk[6] = b.z; chunk[7] = b.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint64_t i = base + 4 * q + b;
+                v |= (uint32_t)(i < len ? ascii[i] : (uint8_t)'N') << (8 * b);
+            }
+            chunk[q] = v;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t c = (chunk[q] >> (8 * b)) & 0xff;
+            const uint32_t code = ((c >> 1) ^ (c >> 2)) & 3;          // A,a->0 C,c->1 G,g->2 T,t->3
+            const uint32_t u = c | 0x20;
+            const bool ok = (u == 'a') | (u == 'c') | (u == 'g') | (u == 't');
+            const int i = 4 * q + b;
+            bits |= (uint64_t)(ok ? code : 0) << (62 - 2 * i);
+            inv |= (ok ? 0u : 1u) << i;
+        }
+    }
+    words[w] = bits;
+    mask[w] = inv;
+}
+void pk_launch_pack(const uint8_t *d_ascii, uint64_t len, uint64_t n_words, uint64_t *d_words, uint32_t *d_mask, pk_stream_t s) {
+    if (!n_words) return;
+    pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, s>>>(d_ascii, len, n_words, d_words, d_mask);
+}
+
+// ------------------------------------------------------------------ insert
+// Bucket-granular linear probing: a key lives in the first bucket, starting at its home bucket,
+// that had a free slot when it was inserted. Slots only ever go EMPTY -> key, so a lookup that
+// sees an EMPTY slot in a bucket knows the key is in no later bucket.
+// returns 0 = already present, 1 = inserted in home bucket, 2 = inserted in a later bucket, 3 = table full
+__device__ __forceinline__ int pk_table_insert(const PkTable t, unsigned long long key) {
+    const uint32_t home = __umulhi(pk_hash32(key), t.n_buckets);
+    uint32_t b = home;
+    for (uint32_t tries = 0; tries < t.n_buckets; ++tries) {
+        volatile unsigned long long *slot = t.slots + 4ull * b;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned long long cur = slot[i];
+            if (cur == key) return 0;
+            if (cur == PK_EMPTY) {
+                const unsigned long long old = atomicCAS((unsigned long long *)slot + i, PK_EMPTY, key);
+                if (old == PK_EMPTY) return b == home ? 1 : 2;
+                if (old == key) return 0;
+            }
+        }
+        b = b + 1 == t.n_buckets ? 0 : b + 1;
+    }
+    return 3;
+}
+
+__device__ __forceinline__ void pk_flush_counts(unsigned long long *counters, uint32_t ins, uint32_t ovf, uint32_t fail) {
+    ins = __reduce_add_sync(0xffffffffu, ins);
+    ovf = __reduce_add_sync(0xffffffffu, ovf);
+    fail = __reduce_add_sync(0xffffffffu, fail);
+    if ((threadIdx.x & 31) == 0) {
+        if (ins) atomicAdd(counters, (unsigned long long)ins);
+        if (ovf) atomicAdd(counters + 1, (unsigned long long)ovf);
+        if (fail) atomicAdd(counters + 2, (unsigned long long)fail);
+    }
+}
+
+__global__ void __launch_bounds__(256) insert_seq_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ mask64,
+                                                         uint64_t n, uint32_t k, PkTable t, unsigned long long *counters) {
+    uint32_t ins = 0, ovf = 0, fail = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += stride) {
+        uint64_t canon;
+        if (!pk_window(words, mask64, p, k, canon)) continue;
+        const int r = pk_table_insert(t, canon);
+        ins += r == 1 || r == 2; ovf += r == 2; fail += r == 3;
+    }
+    pk_flush_counts(counters, ins, ovf, fail);
+}
+static unsigned grid_for(uint64_t n, unsigned per_block = 256, unsigned cap = 148u * 32) {
+    const uint64_t g = (n + per_block - 1) / per_block;
+    return (unsigned)(g < 1 ? 1 : g > cap ? cap : g);
+}
+void pk_launch_insert_seq(const uint64_t *d_words, const uint32_t *d_mask, uint64_t n, uint32_t k, PkTable t,
+                          unsigned long long *d_counters, pk_stream_t s) {
+    if (!n) return;
+    insert_seq_kernel<<<grid_for(n), 256, 0, s>>>(d_words, (const uint64_t *)d_mask, n, k, t, d_counters);
+}
+
+__global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t *__restrict__ keys, uint64_t n, PkTable t,
+                                                          unsigned long long *counters) {
+    uint32_t ins = 0, ovf = 0, fail = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int r = pk_table_insert(t, keys[i]);
+        ins += r == 1 || r == 2; ovf += r == 2; fail += r == 3;
+    }
+    pk_flush_counts(counters, ins, ovf, fail);
+}
+void pk_launch_insert_keys(const uint64_t *d_keys, uint64_t n, PkTable t, unsigned long long *d_counters, pk_stream_t s) {
+    if (!n) return;
+    insert_keys_kernel<<<grid_for(n), 256, 0, s>>>(d_keys, n, t, d_counters);
+}
+
+// KMC record r (global index) belongs to LUT slot j iff lut[j] <= r < lut[j+1]; its prefix is
+// j mod 4^lut (KMC2 keeps one LUT per signature bin); k-mer = prefix << 8*suf_size | suffix
+// (suffix bytes most significant first), counter little-endian (kmc_file.cpp:421-490).
+__global__ void __launch_bounds__(256) decode_insert_kernel(PkDecodeArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const uint64_t r = a.rec0 + i;
+        uint64_t lo = 0, hi = a.n_lut_slots;        // lut[lo] <= r < lut[hi]
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (a.d_lut[mid] <= r) lo = mid; else hi = mid;
+        }
+        const uint64_t prefix = lo % a.single_lut;
+        const uint8_t *rec = a.d_recs + i * a.rec_size;
+        uint64_t suf = 0;
+        for (uint32_t b = 0; b < a.suf_size; b++) suf = (suf << 8) | rec[b];
+        const uint32_t sbits = 8 * a.suf_size;
+        const uint64_t key = (sbits >= 64 ? 0 : prefix << sbits) | suf;
+        uint64_t cnt = 1;
+        if (a.counter_size) {
+            cnt = 0;
+            for (uint32_t b = 0; b < a.counter_size; b++) cnt |= (uint64_t)rec[a.suf_size + b] << (8 * b);
+            if (cnt < a.min_count || cnt > a.max_count) continue;   // kmc_file.cpp:487 / :1396
+        }
+        if (!a.bitvec) {
+            const int rr = pk_table_insert(a.d_tables[a.local_genome], key);
+            unsigned long long *c = a.d_counters + 3 * a.local_genome;
+            if (rr == 1 || rr == 2) atomicAdd(c, 1ull);
+            if (rr == 2) atomicAdd(c + 1, 1ull);
+            if (rr == 3) atomicAdd(c + 2, 1ull);
+        } else {
+            uint32_t bits = (uint32_t)cnt;
+            while (bits) {
+                const uint32_t j = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t g = a.first_genome + j;
+                if (g < a.gbegin || g >= a.gend) continue;
+                const int rr = pk_table_insert(a.d_tables[g - a.gbegin], key);
+                unsigned long long *c = a.d_counters + 3 * (g - a.gbegin);
+                if (rr == 1 || rr == 2) atomicAdd(c, 1ull);
+                if (rr == 2) atomicAdd(c + 1, 1ull);
+                if (rr == 3) atomicAdd(c + 2, 1ull);
+            }
+        }
+    }
+}
+void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s) {
+    if (!a.n) return;
+    decode_insert_kernel<<<grid_for(a.n), 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) overflow_count_kernel(PkTable t, unsigned long long *out) {
+    uint32_t ovf = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n = 4ull * t.n_buckets;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = t.slots[i];
+        if (key != PK_EMPTY && __umulhi(pk_hash32(key), t.n_buckets) != (uint32_t)(i >> 2)) ovf++;
+    }
+    ovf = __reduce_add_sync(0xffffffffu, ovf);
+    if ((threadIdx.x & 31) == 0 && ovf) atomicAdd(out, (unsigned long long)ovf);
+}
+void pk_launch_table_overflow_count(PkTable t, unsigned long long *d_out, pk_stream_t s) {
+    overflow_count_kernel<<<grid_for(4ull * t.n_buckets), 256, 0, s>>>(t, d_out);
+}
+
+// ------------------------------------------------------------------ probe (direct)
+__device__ __noinline__ bool pk_probe_slow(const PkTable t, unsigned long long key, uint32_t b) {
+    // the home bucket was full and did not hold the key: walk on until a hit or a free slot
+    for (uint32_t tries = 1; tries < t.n_buckets; ++tries) {
+        b = b + 1 == t.n_buckets ? 0 : b + 1;
+        const u64x4 v = pk_ld_bucket(t.slots + 4ull * b);
+        if (v.a == key || v.b == key || v.c == key || v.d == key) return true;
+        if (v.a == PK_EMPTY || v.b == PK_EMPTY || v.c == PK_EMPTY || v.d == PK_EMPTY) return false;
+    }
+    return false;
+}
+
+// One thread per position; for each local genome one 32 B bucket load (LDG.256), U loads in
+// flight per thread. Row bits accumulate in a register and are stored once per 32 genomes.
+template <int U>
+__global__ void __launch_bounds__(256) probe_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ mask64,
+                                                    uint64_t p0, uint64_t n, uint32_t k,
+                                                    const PkTable *__restrict__ tables, uint32_t n_local,
+                                                    uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t col_offset) {
+    const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
+    if (i >= n) return;
+    uint64_t canon = 0;
+    const bool valid = pk_window(words, mask64, p0 + i, k, canon);
+    const uint32_t h = pk_hash32(canon);
+    const uint32_t nbl = (n_local + 7) / 8;
+    uint8_t *dst = rows + i * row_stride + col_offset;
+    const bool al4 = ((row_stride | col_offset) & 3) == 0;
+    for (uint32_t g0 = 0; g0 < n_local; g0 += 32) {
+        uint32_t bits = 0;
+        const uint32_t ng = n_local - g0 < 32 ? n_local - g0 : 32;
+        if (valid) {
+            for (uint32_t j0 = 0; j0 < ng; j0 += U) {
+                u64x4 v[U];
+                uint32_t b[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (j0 + u < ng) {
+                        const PkTable t = tables[g0 + j0 + u];
+                        b[u] = __umulhi(h, t.n_buckets);
+                        v[u] = pk_ld_bucket(t.slots + 4ull * b[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (j0 + u < ng) {
+                        bool hit = v[u].a == canon || v[u].b == canon || v[u].c == canon || v[u].d == canon;
+                        if (!hit && v[u].a != PK_EMPTY && v[u].b != PK_EMPTY && v[u].c != PK_EMPTY && v[u].d != PK_EMPTY)
+                            hit = pk_probe_slow(tables[g0 + j0 + u], canon, b[u]);
+                        bits |= (uint32_t)hit << (j0 + u);
+                    }
+                }
+            }
+        }
+        const uint32_t nb = nbl - g0 / 8 < 4 ? nbl - g0 / 8 : 4;
+        if (nb == 4 && al4) {
+            *(uint32_t *)(dst + g0 / 8) = bits;
+        } else {
+            for (uint32_t q = 0; q < nb; q++) dst[g0 / 8 + q] = (uint8_t)(bits >> (8 * q));
+        }
+    }
+}
+void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
+                     const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
+                     uint32_t col_offset, pk_stream_t s) {
+    if (!n) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (n_local <= 4)
+        probe_kernel<4><<<grid, 256, 0, s>>>(d_words, (const uint64_t *)d_mask, p0, n, k, d_tables, n_local, d_rows, row_stride, col_offset);
+    else
+        probe_kernel<8><<<grid, 256, 0, s>>>(d_words, (const uint64_t *)d_mask, p0, n, k, d_tables, n_local, d_rows, row_stride, col_offset);
+}
+
+// ------------------------------------------------------------------ reduce
+// rows: n full rows (n_cols bit columns, ceil(n_cols/8) bytes used of row_stride). For chromosome
+// position p = p_first + i:  hist[(p / binlen) * (n_cols+1) + popcount(row)]++ ; col_sums[g] += bit g ;
+// rows_low[(p/step - ceil(p_first/step))] = row  when p % step == 0.
+#define PK_RED_ITEMS 8
+__global__ void __launch_bounds__(256) reduce_kernel(const uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t n_cols,
+                                                     uint64_t p_first, uint64_t n, uint64_t binlen,
+                                                     unsigned long long *__restrict__ hist, unsigned long long *__restrict__ col_sums,
+                                                     uint8_t *__restrict__ rows_low, uint32_t step) {
+    extern __shared__ unsigned int sh[];
+    const uint32_t n_words = (n_cols + 31) / 32, nbytes = (n_cols + 7) / 8;
+    unsigned int *sh_hist = sh;                    // [n_cols + 1]
+    unsigned int *sh_col = sh + n_cols + 1;        // [n_words * 32]
+    for (uint32_t q = threadIdx.x; q < n_cols + 1 + n_words * 32; q += blockDim.x) sh[q] = 0;
+    __syncthreads();
+    const uint64_t base = blockIdx.x * (uint64_t)(256 * PK_RED_ITEMS);
+    const uint64_t bin0 = binlen ? (p_first + base) / binlen : 0;
+    const uint64_t low0 = step ? (p_first + step - 1) / step : 0;
+    const uint32_t lane = threadIdx.x & 31;
+    for (int it = 0; it < PK_RED_ITEMS; it++) {
+        const uint64_t i = base + (uint64_t)it * 256 + threadIdx.x;
+        if (base + (uint64_t)it * 256 + (threadIdx.x & ~31u) >= n) break;   // whole warp out of range (warp-uniform)
+        const bool active = i < n;
+        const uint64_t p = p_first + i;
+        const uint8_t *row = rows + i * row_stride;
+        uint32_t pc = 0;
+        for (uint32_t wd = 0; wd < n_words; wd++) {
+            uint32_t w = 0;
+            if (active) {
+                for (uint32_t b = 0; b < 4 && 4 * wd + b < nbytes; b++) w |= (uint32_t)row[4 * wd + b] << (8 * b);
+                if (wd == n_words - 1 && (n_cols & 31)) w &= (1u << (n_cols & 31)) - 1;
+            }
+            pc += __popc(w);
+            if (col_sums) {
+                uint32_t mine = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, (w >> j) & 1);
+                    if (lane == j) mine = __popc(m);
+                }
+                if (mine) atomicAdd(&sh_col[wd * 32 + lane], mine);
+            }
+        }
+        if (hist && binlen) {
+            const uint64_t bin = p / binlen;
+            const uint32_t key = active ? (uint32_t)((bin - bin0) << 16 | pc) : 0xffffffffu;   // a block spans <= 2048 positions, so bin - bin0 < 2^16
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            if (active && lane == (uint32_t)(__ffs(peers) - 1)) {
+                const uint32_t cnt = __popc(peers);
+                if (bin == bin0) atomicAdd(&sh_hist[pc], cnt);
+                else atomicAdd(&hist[bin * (n_cols + 1) + pc], (unsigned long long)cnt);
+            }
+        }
+        if (rows_low && active && p % step == 0) {
+            uint8_t *d = rows_low + (p / step - low0) * row_stride;
+            for (uint32_t b = 0; b < nbytes; b++) d[b] = row[b];
+        }
+    }
+    __syncthreads();
+    if (hist && binlen)
+        for (uint32_t q = threadIdx.x; q < n_cols + 1; q += blockDim.x)
+            if (sh_hist[q]) atomicAdd(&hist[bin0 * (n_cols + 1) + q], (unsigned long long)sh_hist[q]);
+    if (col_sums)
+        for (uint32_t q = threadIdx.x; q < n_cols; q += blockDim.x)
+            if (sh_col[q]) atomicAdd(&col_sums[q], (unsigned long long)sh_col[q]);
+}
+void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
+                      uint64_t binlen, unsigned long long *d_bin_hist, unsigned long long *d_col_sums,
+                      uint8_t *d_rows_low, uint32_t step, pk_stream_t s) {
+    if (!n) return;
+    const uint32_t n_words = (n_cols + 31) / 32;
+    const size_t shmem = (size_t)(n_cols + 1 + n_words * 32) * sizeof(unsigned int);
+    const unsigned grid = (unsigned)((n + 256 * PK_RED_ITEMS - 1) / (256 * PK_RED_ITEMS));
+    reduce_kernel<<<grid, 256, shmem, s>>>(d_rows, row_stride, n_cols, p_first, n, binlen, d_bin_hist, d_col_sums, d_rows_low, step);
+}
+
+// ------------------------------------------------------------------ interleave / unpack
+__global__ void __launch_bounds__(256) interleave_kernel(const uint8_t *__restrict__ planes, uint32_t n_ranks, uint64_t n, uint32_t w,
+                                                         uint8_t *__restrict__ rows, uint32_t row_stride) {
+    const uint64_t total = n * n_ranks;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < total; q += stride) {
+        const uint64_t i = q / n_ranks;
+        const uint32_t r = (uint32_t)(q % n_ranks);
+        const uint8_t *src = planes + ((uint64_t)r * n + i) * w;
+        uint8_t *dst = rows + i * row_stride + (uint64_t)r * w;
+        for (uint32_t b = 0; b < w; b++) dst[b] = src[b];
+    }
+}
+void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,
+                          uint32_t row_stride, pk_stream_t s) {
+    if (!n || !n_ranks) return;
+    interleave_kernel<<<grid_for(n * n_ranks), 256, 0, s>>>(d_planes, n_ranks, n, w, d_rows, row_stride);
+}
+
+__global__ void __launch_bounds__(256) rows_to_u32_kernel(const uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t byte_off,
+                                                          uint32_t n_bytes, uint32_t bit_mask, uint64_t n, uint32_t *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t v = 0;
+        for (uint32_t b = 0; b < n_bytes; b++) v |= (uint32_t)rows[i * row_stride + byte_off + b] << (8 * b);
+        out[i] = v & bit_mask;
+    }
+}
+void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
+                           uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s) {
+    if (!n) return;
+    rows_to_u32_kernel<<<grid_for(n), 256, 0, s>>>(d_rows, row_stride, byte_off, n_bytes, bit_mask, n, d_out);
+}

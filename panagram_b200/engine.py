@@ -1,0 +1,179 @@
+"""Python host side of the anchoring engine: a thin object layer over the C ABI
+(include/pk_anchor.h). Mirrors the roles of ``KMCdb`` in ``cpp/anchor.cpp:16-35``
+(open the k-mer sets once, anchor many FASTAs) and of ``Genome._load_kmc`` /
+``Genome._write_bitmap`` in ``panagram/index.py:847-863,949-969``.
+
+All compute happens in libpkanchor.so on the GPU; this module only moves
+buffers. numpy is used for host arrays, torch (optional) only to hand device
+pointers of tensors to the device-level entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import PkConfig, PkStats, PkTableStats, check
+
+
+def _u8(seq) -> np.ndarray:
+    if isinstance(seq, np.ndarray):
+        if seq.dtype != np.uint8:
+            raise TypeError("sequence arrays must be uint8")
+        return np.ascontiguousarray(seq)
+    if isinstance(seq, str):
+        seq = seq.encode()
+    return np.frombuffer(seq, dtype=np.uint8)
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array over page-locked host memory (pk_host_alloc)."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(_lib.lib().pk_host_alloc(C.byref(p), max(nbytes, 1)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    weakref.finalize(buf, _lib.lib().pk_host_free, p)
+    return arr
+
+
+class Engine:
+    """Per-genome k-mer tables resident in HBM + the anchoring calls."""
+
+    def __init__(self, k: int, n_genomes: int, genome_begin: int = 0, genome_end: int | None = None,
+                 device: int = 0, lowres_step: int = 100, max_bin_kbp: int = 200,
+                 min_bin_count: int = 100, load_factor: float = 0.5, chunk_positions: int = 0):
+        self._L = _lib.lib()
+        genome_end = n_genomes if genome_end is None else genome_end
+        self.cfg = PkConfig(k, n_genomes, genome_begin, genome_end, device, lowres_step,
+                            max_bin_kbp * 1000, min_bin_count, load_factor, chunk_positions)
+        self.k, self.n_genomes = k, n_genomes
+        self.genome_begin, self.genome_end = genome_begin, genome_end
+        self.n_local = genome_end - genome_begin
+        self.row_bytes = (self.n_local + 7) // 8
+        self.lowres_step = lowres_step
+        h = C.c_void_p()
+        check(self._L.pk_engine_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, self._L.pk_engine_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    # ---- table construction -------------------------------------------------
+    def reserve(self, genome: int, max_keys: int):
+        check(self._L.pk_engine_reserve(self._h, genome, max_keys))
+
+    def add_kmc(self, genome: int, prefix):
+        """K_g from a per-genome KMC database (kmc/{s}.count or .onehot)."""
+        check(self._L.pk_engine_add_kmc(self._h, genome, str(prefix).encode()))
+
+    def add_bitvec(self, first_genome: int, prefix):
+        """A merged bitvec database (kmc/bitvec{i}): counter bit j -> genome first+j."""
+        check(self._L.pk_engine_add_bitvec(self._h, first_genome, str(prefix).encode()))
+
+    def add_keys(self, genome: int, canon_kmers):
+        a = np.ascontiguousarray(canon_kmers, dtype=np.uint64)
+        check(self._L.pk_engine_add_keys(self._h, genome, a.ctypes.data, a.size))
+
+    def add_sequence(self, genome: int, seq):
+        a = _u8(seq)
+        check(self._L.pk_engine_add_sequence(self._h, genome, a.ctypes.data, a.size))
+
+    def add_sequence_device(self, genome: int, d_ptr: int, length: int):
+        check(self._L.pk_engine_add_sequence_device(self._h, genome, d_ptr, length))
+
+    def finalize(self):
+        check(self._L.pk_engine_finalize(self._h))
+
+    def table_stats(self, genome: int) -> dict:
+        s = PkTableStats()
+        check(self._L.pk_engine_table_stats(self._h, genome, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    # ---- hot path, host buffers --------------------------------------------
+    def bin_len(self, nkmers: int) -> int:
+        return int(self._L.pk_bin_len(C.byref(self.cfg), nkmers))
+
+    def anchor_chrom(self, seq, bitmap1=True, low=True, hist=True, colsums=True, out=None) -> dict:
+        """One chromosome -> rows / low-res rows / per-bin popcount histogram / column sums.
+
+        `out` may carry preallocated (e.g. pinned) arrays under the keys
+        'bitmap1' and 'low'. Returns a dict with nkmers and the requested arrays.
+        """
+        a = _u8(seq)
+        nk = max(a.size - self.k + 1, 0)
+        rb, step = self.row_bytes, self.lowres_step
+        out = dict(out or {})
+        res = {"nkmers": nk}
+        if nk == 0:
+            return res
+        binlen = self.bin_len(nk)
+        b1 = lo = hi = cs = None
+        if bitmap1:
+            b1 = out.get("bitmap1")
+            if b1 is None:
+                b1 = np.empty((nk, rb), dtype=np.uint8)
+        if low:
+            nlow = (nk + step - 1) // step
+            lo = out.get("low")
+            if lo is None:
+                lo = np.empty((nlow, rb), dtype=np.uint8)
+        if hist and binlen > 0:
+            nbins = (nk + binlen - 1) // binlen
+            hi = np.zeros((nbins, self.n_local + 1), dtype=np.uint64)
+        if colsums:
+            cs = np.zeros(self.n_local, dtype=np.uint64)
+        nko = C.c_uint64(0)
+        check(self._L.pk_anchor_chrom(self._h, a.ctypes.data, a.size,
+                                      None if b1 is None else b1.ctypes.data,
+                                      None if lo is None else lo.ctypes.data,
+                                      None if hi is None else hi.ctypes.data,
+                                      None if cs is None else cs.ctypes.data, C.byref(nko)))
+        assert nko.value == nk
+        res.update(bitmap1=None if b1 is None else b1[:nk], low=lo, bin_hist=hi, col_sums=cs,
+                   binlen=binlen)
+        return res
+
+    def get_counters_for_read(self, dbi: int, read) -> np.ndarray | None:
+        """uint32 counters of bitvec database `dbi` for every k-mer of `read`
+        (CKMCFile::GetCountersForRead); None when len(read) < k."""
+        a = _u8(read)
+        if a.size < self.k:
+            return None
+        outv = np.empty(a.size - self.k + 1, dtype=np.uint32)
+        n = C.c_uint64(0)
+        check(self._L.pk_get_counters_for_read(self._h, dbi, a.ctypes.data, a.size, outv.ctypes.data,
+                                               C.byref(n)))
+        return outv[:n.value]
+
+    def stats(self) -> dict:
+        s = PkStats()
+        check(self._L.pk_engine_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    # ---- hot path, device pointers (ints; e.g. torch.Tensor.data_ptr()) ------
+    def packed_words(self, length: int) -> int:
+        return int(self._L.pk_packed_words(length))
+
+    def pack_device(self, d_ascii: int, length: int, d_words: int, d_mask: int, stream: int = 0):
+        check(self._L.pk_pack_device(self._h, d_ascii, length, d_words, d_mask, stream or None))
+
+    def probe_device(self, d_words: int, d_mask: int, p0: int, n: int, d_rows: int, row_stride: int,
+                     col_offset: int = 0, stream: int = 0):
+        check(self._L.pk_probe_device(self._h, d_words, d_mask, p0, n, d_rows, row_stride, col_offset,
+                                      stream or None))
+
+    def reduce_device(self, d_rows: int, row_stride: int, n_cols: int, p_first: int, n: int, binlen: int,
+                      d_hist: int = 0, d_colsums: int = 0, d_low: int = 0, stream: int = 0):
+        check(self._L.pk_reduce_device(self._h, d_rows, row_stride, n_cols, p_first, n, binlen,
+                                       d_hist or None, d_colsums or None, d_low or None,
+                                       self.lowres_step, stream or None))
+
+    def interleave_device(self, d_planes: int, n_ranks: int, n: int, w: int, d_rows: int, row_stride: int,
+                          stream: int = 0):
+        check(self._L.pk_interleave_device(self._h, d_planes, n_ranks, n, w, d_rows, row_stride,
+                                           stream or None))

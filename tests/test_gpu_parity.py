@@ -1,0 +1,233 @@
+"""GPU: the CUDA path, called through the C ABI, against the reference's golden outputs and the
+oracle. Bit-exact throughout (integer/byte work)."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from panagram_b200 import _lib, anchor, kmc_api, layout
+from panagram_b200.engine import Engine, pinned_empty
+
+pytestmark = pytest.mark.gpu
+
+
+def anchor_outputs(eng, fasta, n_genomes):
+    """What cpp/anchor.cpp writes for one anchor, assembled from Engine.anchor_chrom."""
+    b1, lo, chroms, bins = [], [], [], []
+    col = np.zeros(eng.n_local, dtype=np.uint64)
+    for name, seq in anchor.parse_fasta(fasta):
+        r = eng.anchor_chrom(seq)
+        b1.append(r["bitmap1"].tobytes()); lo.append(r["low"].tobytes())
+        chroms.append((name, r["nkmers"])); bins.append((r["binlen"], r["bin_hist"]))
+        col += r["col_sums"]
+    return {"bitmap.1": b"".join(b1), "bitmap.100": b"".join(lo), "chrs.tsv": layout.chrs_tsv(chroms),
+            "bitsum.bins.tsv": layout.bins_tsv(n_genomes, bins), "col_sums": col}
+
+
+def check_against_golden(eng, pan):
+    for a in pan["anchors"]:
+        got = anchor_outputs(eng, pan["fasta"][a], pan["n_genomes"])
+        for key, want in pan["expected"][a].items():
+            assert got[key] == want, f"{a}/{key}"
+        rows = np.frombuffer(got["bitmap.1"], dtype=np.uint8).reshape(-1, eng.row_bytes)
+        bits = np.unpackbits(rows, axis=1, bitorder="little")[:, :pan["n_genomes"]]
+        assert (bits.sum(axis=0) == got["col_sums"]).all()       # index.py:1051 paircount sums
+
+
+@pytest.mark.parametrize("which", ["pan3", "pan35"])
+@pytest.mark.parametrize("chunk", [0, 777])
+def test_bitvec_db_engine_equals_reference(which, chunk, request):
+    pan = request.getfixturevalue(which)
+    eng = Engine(pan["k"], pan["n_genomes"], chunk_positions=chunk)
+    for i in range(pan["ndb"]):
+        eng.add_bitvec(32 * i, pan["dir"] / "kmc" / f"bitvec{i}")
+    eng.finalize()
+    check_against_golden(eng, pan)
+    bk, bc = oracle.OracleDB.open(pan["dir"] / "kmc" / "bitvec0").list()
+    for g in range(min(3, pan["n_genomes"])):
+        assert eng.table_stats(g)["n_keys"] == int(((bc >> g) & 1).sum())
+
+
+@pytest.mark.parametrize("kind", ["count", "onehot"])
+def test_per_genome_kmc_dbs_equal_reference(pan3, kind):
+    """K_g ingested from kmc/{s}.count (KMC2, written by kmc) or .onehot (KMC1, kmc_tools)."""
+    eng = Engine(pan3["k"], 3, load_factor=0.85)
+    for g, name in enumerate(pan3["names"]):
+        eng.add_kmc(g, pan3["dir"] / "kmc" / f"{name}.{kind}")
+    eng.finalize()
+    check_against_golden(eng, pan3)
+
+
+def test_tables_built_from_fasta_equal_reference(pan3):
+    """On-GPU k-mer set construction straight from the sequences == kmc -ci1 (FASTA input)."""
+    eng = Engine(pan3["k"], 3)
+    for g, name in enumerate(pan3["names"]):
+        recs = anchor.parse_fasta(pan3["fasta"][name])
+        eng.reserve(g, sum(max(s.size - pan3["k"] + 1, 0) for _, s in recs))
+        for _, s in recs:
+            eng.add_sequence(g, s)
+    eng.finalize()
+    check_against_golden(eng, pan3)
+    km, _ = oracle.OracleDB.open(pan3["dir"] / "kmc" / "g1.count").list()
+    assert eng.table_stats(1)["n_keys"] == km.size
+
+
+def test_kmcfile_dropin_known_answer(kat):
+    """test_py_kmc_file.py::test_get_counters_for_read through the py_kmc_api mirror."""
+    for name in ("kmc_db", "kmc_db_sorted"):
+        f = kmc_api.KMCFile()
+        assert f.OpenForRA(str(kat["dir"] / name))
+        assert not f.OpenForRA(str(kat["dir"] / name))
+        assert f.KmerLength() == 17 and f.Info().total_kmers > 0
+        v = kmc_api.CountVec()
+        assert f.GetCountersForRead(kat["query"], v)
+        assert v.value == kat["counters"]
+        assert np.array(v, dtype="uint32").tolist() == kat["counters"]
+        assert not f.GetCountersForRead("ACGTACGT", v) and v.value == []
+        assert f.Close() and not f.Close()
+
+
+def random_case(rng, n_genomes, k, length, p_member=0.6):
+    seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=length)
+    for _ in range(3):
+        o = int(rng.integers(0, max(length - 40, 1)))
+        seq[o:o + int(rng.integers(1, 40))] = ord("N")
+    seq[rng.integers(0, length, size=5)] = np.frombuffer(b"acgtn", dtype=np.uint8)
+    sb = seq.tobytes()
+    canon = sorted(oracle.kmer_set([sb], k))
+    ints = np.array([oracle.kmer_int(s) for s in canon], dtype=np.uint64)
+    extra = rng.integers(0, 1 << min(2 * k, 62), size=len(ints) // 2 + 1, dtype=np.uint64)
+    member = rng.random((len(ints), n_genomes)) < p_member
+    return sb, ints, member, extra
+
+
+@pytest.mark.parametrize("n_genomes,k,load", [(1, 21, 0.5), (2, 5, 0.5), (8, 31, 0.9), (9, 32, 0.75), (33, 21, 0.9),
+                                              (64, 17, 0.5), (70, 1, 0.5)])
+def test_random_sets_vs_oracle(n_genomes, k, load):
+    rng = np.random.default_rng(1000 * n_genomes + k)
+    sb, ints, member, extra = random_case(rng, n_genomes, k, 6000)
+    eng = Engine(k, n_genomes, load_factor=load, chunk_positions=1500)
+    dbs = []
+    for d in range((n_genomes + 31) // 32):
+        cnt = np.zeros(len(ints), dtype=np.uint32)
+        for g in range(32 * d, min(32 * d + 32, n_genomes)):
+            cnt |= member[:, g].astype(np.uint32) << np.uint32(g - 32 * d)
+        keep = cnt != 0
+        dbs.append(oracle.OracleDB.from_kmers(k, ints[keep], cnt[keep]))
+    for g in range(n_genomes):
+        keys = ints[member[:, g]]
+        eng.add_keys(g, keys)
+        eng.add_keys(g, keys[: len(keys) // 3])       # duplicates are absorbed
+    eng.finalize()
+    for g in range(n_genomes):
+        st = eng.table_stats(g)
+        assert st["n_keys"] == int(member[:, g].sum())
+    want = oracle.anchor_chrom(dbs, n_genomes, sb)
+    got = eng.anchor_chrom(sb)
+    assert (got["bitmap1"] == want["bitmap1"]).all()
+    assert (got["low"] == want["bitmap100"]).all()
+    assert (got["bin_hist"] == want["bin_hist"]).all()
+    assert (got["col_sums"] == want["paircounts"]).all()
+    for d, db in enumerate(dbs):
+        assert (eng.get_counters_for_read(d, sb) == db.get_counters_for_read(sb)).all()
+
+
+def test_edge_cases(pan3):
+    eng = Engine(21, 3)
+    eng.add_bitvec(0, pan3["dir"] / "kmc" / "bitvec0")
+    eng.finalize()
+    assert eng.anchor_chrom(b"ACGT")["nkmers"] == 0                        # len < k
+    assert eng.get_counters_for_read(0, b"ACGTACGT") is None
+    r = eng.anchor_chrom(b"N" * 500)                                         # nothing valid
+    assert r["nkmers"] == 480 and not r["bitmap1"].any() and r["bin_hist"][:, 0].sum() == 480
+    r = eng.anchor_chrom(b"ACGT" * 10, hist=False)                           # 20 k-mers: below min_bin_count
+    assert r["nkmers"] == 20 and r["bin_hist"] is None and r["low"].shape == (1, 1)
+    with pytest.raises(_lib.PkError):                                        # ... and asking for bins is an error
+        import ctypes as C
+        buf = np.zeros(64, dtype=np.uint64)
+        seq = np.frombuffer(b"ACGT" * 10, dtype=np.uint8)
+        _lib.check(eng._L.pk_anchor_chrom(eng._h, seq.ctypes.data, seq.size, None, None, buf.ctypes.data, None,
+                                          C.byref(C.c_uint64())))
+    # an engine with an empty genome still answers
+    e2 = Engine(21, 2)
+    e2.add_keys(0, np.array([5], dtype=np.uint64))
+    e2.finalize()
+    assert e2.table_stats(1)["n_keys"] == 0
+    assert not e2.anchor_chrom(b"ACGTTGCA" * 20)["bitmap1"].any()
+    # probing before finalize is a state error, not a crash
+    e3 = Engine(21, 1)
+    with pytest.raises(_lib.PkError) as ei:
+        e3.anchor_chrom(b"A" * 200)
+    assert ei.value.code == -6
+    with pytest.raises(_lib.PkError):
+        Engine(33, 1)                                                       # k > 32 unsupported
+    with pytest.raises(_lib.PkError):
+        eng2 = Engine(31, 3); eng2.add_bitvec(0, pan3["dir"] / "kmc" / "bitvec0")   # k mismatch
+
+
+def test_pinned_buffers_and_anchor_dir(pan3, tmp_path):
+    eng = Engine(pan3["k"], 3)
+    eng.add_bitvec(0, pan3["dir"] / "kmc" / "bitvec0")
+    eng.finalize()
+    name, seq = anchor.parse_fasta(pan3["fasta"]["g0"])[0]
+    nk = seq.size - 21 + 1
+    out = {"bitmap1": pinned_empty((nk, 1)), "low": pinned_empty(((nk + 99) // 100, 1))}
+    r = eng.anchor_chrom(seq, out=out)
+    assert r["bitmap1"].tobytes() == pan3["expected"]["g0"]["bitmap.1"][:nk]
+    s = anchor.anchor_fasta(eng, "g0", pan3["fasta"]["g0"], tmp_path / "anchor" / "g0", genome_names=pan3["names"])
+    exp = pan3["expected"]["g0"]
+    d = tmp_path / "anchor" / "g0"
+    assert layout.read_bgzf(d / "bitmap.1.gz") == exp["bitmap.1"]
+    assert layout.read_bgzf(d / "bitmap.100.gz") == exp["bitmap.100"]
+    assert (d / "chrs.tsv").read_text() == exp["chrs.tsv"]
+    assert (d / "bitsum.bins.tsv").read_text() == exp["bitsum.bins.tsv"]
+    pc = (d / "total_paircounts.csv").read_text().splitlines()
+    assert pc[0] == "name,count,frac" and pc[1].endswith(",1.0") and len(pc) == 4
+    assert layout.query_bytes(d / "bitmap.1.gz", d / "bitmap.1.gzi", 1234, 50) == exp["bitmap.1"][1234:1284]
+    assert s["positions"] == len(exp["bitmap.1"])
+
+
+def test_device_level_sharded_gather_equals_single_engine():
+    """Two genome shards on one GPU stand in for two ranks: per-shard rows, gathered as planes,
+    interleaved, reduced == one engine holding all 16 genomes."""
+    import torch
+    rng = np.random.default_rng(7)
+    k, n = 23, 16
+    sb, ints, member, _ = random_case(rng, n, k, 5000)
+    full = Engine(k, n)
+    shards = [Engine(k, n, 0, 8), Engine(k, n, 8, 16)]
+    for g in range(n):
+        for e in [full] + shards:
+            e.add_keys(g, ints[member[:, g]])            # non-local genomes are ignored by a shard
+    for e in [full] + shards:
+        e.finalize()
+    want = full.anchor_chrom(sb)
+    nk = want["nkmers"]
+    dev = torch.device("cuda:0")
+    asc = torch.frombuffer(bytearray(sb), dtype=torch.uint8).to(dev)
+    nw = full.packed_words(len(sb))
+    words = torch.empty(nw, dtype=torch.int64, device=dev)
+    mask = torch.empty(nw, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    planes = torch.empty((2, nk, 1), dtype=torch.uint8, device=dev)
+    for r, e in enumerate(shards):
+        e.pack_device(asc.data_ptr(), len(sb), words.data_ptr(), mask.data_ptr(), st)
+        e.probe_device(words.data_ptr(), mask.data_ptr(), 0, nk, planes[r].data_ptr(), 1, 0, st)
+    rows = torch.zeros((nk, 2), dtype=torch.uint8, device=dev)
+    full.interleave_device(planes.data_ptr(), 2, nk, 1, rows.data_ptr(), 2, st)
+    binlen = full.bin_len(nk)
+    nbins = (nk + binlen - 1) // binlen
+    hist = torch.zeros((nbins, n + 1), dtype=torch.int64, device=dev)
+    cols = torch.zeros(n, dtype=torch.int64, device=dev)
+    low = torch.zeros(((nk + 99) // 100, 2), dtype=torch.uint8, device=dev)
+    full.reduce_device(rows.data_ptr(), 2, n, 0, nk, binlen, hist.data_ptr(), cols.data_ptr(), low.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert (rows.cpu().numpy() == want["bitmap1"]).all()
+    assert (low.cpu().numpy() == want["low"]).all()
+    assert (hist.cpu().numpy().astype(np.uint64) == want["bin_hist"]).all()
+    assert (cols.cpu().numpy().astype(np.uint64) == want["col_sums"]).all()
+    # direct strided write (col_offset) gives the same rows without the interleave
+    rows2 = torch.zeros((nk, 2), dtype=torch.uint8, device=dev)
+    for r, e in enumerate(shards):
+        e.probe_device(words.data_ptr(), mask.data_ptr(), 0, nk, rows2.data_ptr(), 2, r, st)
+    torch.cuda.synchronize()
+    assert torch.equal(rows, rows2)

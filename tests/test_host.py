@@ -1,0 +1,85 @@
+"""CPU: host-side logic around the kernel — FASTA parsing, BGZF/.gzi layout, text writers,
+synthetic genomes, genome sharding."""
+import gzip
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from panagram_b200 import anchor, layout, synth
+
+
+def test_parse_fasta_matches_reference_rules(pan3):
+    for g, p in pan3["fasta"].items():
+        want = oracle.parse_fasta(p)
+        got = anchor.parse_fasta(p)
+        assert [n for n, _ in got] == [n for n, _ in want]
+        for (_, a), (_, b) in zip(got, want):
+            assert a.tobytes() == b
+        assert any(b"\r" in s for _, s in want), "fixture carries a CRLF line"
+        stripped = anchor.parse_fasta(p, strip_cr=True)
+        assert all(13 not in s for _, s in stripped)
+        assert [n for n, _ in got][1] == "chr2"      # header "chr2 description text" cut at the space
+
+
+def test_parse_fasta_gz_and_no_trailing_newline(tmp_path):
+    txt = b">a b c\nACGT\nAC\n>b\n\nGG\nTT"
+    (tmp_path / "x.fa").write_bytes(txt)
+    with gzip.open(tmp_path / "x.fa.gz", "wb") as fh:
+        fh.write(txt)
+    for p in ("x.fa", "x.fa.gz"):
+        recs = anchor.parse_fasta(tmp_path / p)
+        assert [(n, s.tobytes()) for n, s in recs] == [("a", b"ACGTAC"), ("b", b"GGTT")]
+
+
+@pytest.mark.parametrize("n", [0, 1, 0xFF00 - 1, 0xFF00, 0xFF00 + 1, 300_000])
+def test_bgzf_roundtrip_and_gzi(tmp_path, n):
+    rng = np.random.default_rng(n)
+    data = (rng.integers(0, 4, size=n, dtype=np.uint8) * 85).tobytes()
+    w = layout.BgzfWriter(tmp_path / "b.gz", threads=3)
+    for o in range(0, n, 70_001):            # ragged writes
+        w.write(data[o:o + 70_001])
+    w.close(tmp_path / "b.gzi")
+    raw = (tmp_path / "b.gz").read_bytes()
+    assert raw.endswith(layout.BGZF_EOF)
+    assert gzip.decompress(raw) == data
+    gzi = (tmp_path / "b.gzi").read_bytes()
+    (cnt,) = struct.unpack_from("<Q", gzi)
+    assert cnt == (n + 0xFF00 - 1) // 0xFF00 and len(gzi) == 8 + 16 * cnt
+    blocks = layout.load_bgz_blocks(tmp_path / "b.gzi")
+    assert blocks[0].tolist() == [0, 0]
+    assert (np.diff(blocks[:, 1]) <= 0xFF00).all()
+    for start, ln in ((0, 10), (0xFF00 - 3, 7), (n // 2, 1000), (max(n - 5, 0), 5)):
+        if start + ln <= n:
+            assert layout.query_bytes(tmp_path / "b.gz", tmp_path / "b.gzi", start, ln) == data[start:start + ln]
+
+
+def test_text_writers_match_reference_text(pan3):
+    exp = pan3["expected"]["g0"]
+    chroms = [(l.split("\t")[0], int(l.split("\t")[2])) for l in exp["chrs.tsv"].splitlines()[1:]]
+    assert layout.chrs_tsv(chroms) == exp["chrs.tsv"]
+    rows = [l.split("\t") for l in exp["bitsum.bins.tsv"].splitlines()[1:]]
+    per = []
+    for cid in range(len(chroms)):
+        rr = [r for r in rows if int(r[0]) == cid]
+        binlen = int(rr[1][1]) - int(rr[0][1])
+        per.append((binlen, np.array([[int(x) for x in r[2:]] for r in rr], dtype=np.uint64)))
+    assert layout.bins_tsv(3, per) == exp["bitsum.bins.tsv"]
+
+
+def test_paircounts_csv():
+    txt = layout.paircounts_csv(["a", "b", "c"], np.array([10, 5, 3], dtype=np.uint64), "a")
+    assert txt == "name,count,frac\na,10,1.0\nb,5,0.5\nc,3,0.3\n"
+
+
+def test_synth_is_deterministic_and_shaped():
+    anc = synth.ancestor_codes(50_000, 20260001)
+    a = synth.genome_chroms(anc, 3, 20260001)
+    b = synth.genome_chroms(synth.ancestor_codes(50_000, 20260001), 3, 20260001)
+    assert all((x[1] == y[1]).all() for x, y in zip(a, b))
+    assert [n for n, _ in a] == ["chr1", "chr2", "chr3", "chr4", "chr5"]
+    assert (a[0][1][5000:6000] == ord("N")).all()
+    assert bytes(a[1][1][:100]).islower()
+    g0 = synth.genome_codes(anc, 0, 1)
+    assert 0.001 < (g0 != anc).mean() < 0.003
