@@ -1,0 +1,369 @@
+#!/usr/bin/env python3
+"""bench.py — anchored k-mers/sec (positions x genomes) building the pan-kmer bitmap.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one anchor genome: every k-mer position of the
+anchor probed against every genome's k-mer set and the N-bit rows written.
+
+Workloads (BASELINE.json `configs`; synthetic genomes per SURVEY.md §8d, panagram_b200/synth.py):
+  configs1  8 x 135 Mbp, k=21, 1 anchor — the configuration the metric is quoted on (default)
+  configs2  32 x 150 Mbp, k=21, 1 anchor
+  small     8 x 8 Mbp, k=21 (plumbing check)
+At N GPUs the genomes are sharded by genome (weak scaling: 8 genomes' tables per GPU, 8N
+genomes in total, every rank probes all anchor positions against its shard, one NCCL
+all-gather of the per-rank column bytes + an interleave kernel assemble the N-bit rows).
+
+`value`   device-resident: packed anchor already in HBM, CUDA events around the probe stage
+          (partition + probe kernels [+ all-gather + interleave at N>1]).
+`e2e`     the public call a user makes (Engine.anchor_genome -> pk_anchor_genome) with pinned
+          HOST buffers: ASCII in, bitmap rows / low-res rows / histograms / column sums out.
+`--impl reference`  the reference's own CPU implementation (oracle/_ref/run_anchor, built from
+          the unmodified cpp/anchor.cpp + KMC API) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "configs1": dict(n_per_gpu=8, length=135_000_000, k=21, seed=20260001,
+                     name="configs[1]: 8 synthetic 135 Mbp genomes, k=21, 1 anchor"),
+    "configs2": dict(n_per_gpu=32, length=150_000_000, k=21, seed=20260002,
+                     name="configs[2]: 32 synthetic 150 Mbp genomes, k=21, 1 anchor"),
+    "small": dict(n_per_gpu=8, length=8_000_000, k=21, seed=20260009,
+                  name="small: 8 synthetic 8 Mbp genomes, k=21, 1 anchor"),
+}
+CPU_SAMPLE_LEN = 6_000_000      # per-genome length of the bounded CPU sample
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        if shutil.which("nvidia-smi") is None:
+            return
+        self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_genome(anc, g, seed):
+    from panagram_b200 import synth
+    return [s for _, s in synth.genome_chroms(anc, g, seed)]
+
+
+# ------------------------------------------------------------------------ reference arm
+def run_reference(args, wl, cores):
+    """The reference's CPU path on a bounded sample of the workload: KMC databases are built once
+    (untimed, like our table build); each step times `run_anchor N . g0 g0.fa` (cpp/Snakefile:55)."""
+    from oracle import refpipe
+    from panagram_b200 import synth
+    n = wl["n_per_gpu"] * 1          # the CPU arm always runs the 1-GPU genome count
+    if not refpipe.have_ref():
+        return {"impl": "reference", "unavailable": "oracle/_ref binaries missing (build with make -C oracle ref)"}
+    length = min(wl["length"], CPU_SAMPLE_LEN)
+    tmp = Path(tempfile.mkdtemp(prefix="pk_ref_"))
+    try:
+        samples = synth.make_pangenome(tmp / "fa", n, length, wl["seed"])
+        timings = {}
+        names = [s[0] for s in samples]
+        for i, (name, fa) in enumerate(samples):
+            refpipe.kmc_count(tmp / "idx", name, fa, i, wl["k"], threads=cores, timings=timings)
+        ndb = refpipe.write_opdefs(tmp / "idx", names)
+        refpipe.kmc_bitvec(tmp / "idx", ndb, timings)
+        positions = sum(len(s) - wl["k"] + 1 for _, s in
+                        __import__("oracle.oracle", fromlist=["x"]).parse_fasta(samples[0][1]))
+        times = []
+        for it in range(args.warmup + args.steps):
+            t = {}
+            refpipe.run_anchor(tmp / "idx", n, [samples[0]], threads=cores, timings=t)
+            if it >= args.warmup:
+                times.append(t["run_anchor_s"])
+        ms = 1e3 * sum(times) / len(times)
+        value = positions * n / (ms / 1e3)
+        sample = (f"{n} genomes x {length / 1e6:g} Mbp of the same generator (seed {wl['seed']}), k={wl['k']}, "
+                  f"1 anchor = {positions} positions; KMC DB build untimed "
+                  f"(kmc {timings.get('kmc_count_s', 0):.1f}s, set_counts {timings.get('set_counts_s', 0):.1f}s, "
+                  f"complex {timings.get('kmc_bitvec_s', 0):.1f}s)")
+        return {"value": value, "ms_per_step": ms, "positions": positions, "sample": sample,
+                "cores": 1, "cores_available": cores, "kind": "reference"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="configs1", choices=sorted(WORKLOADS))
+    ap.add_argument("--load-factor", type=float, default=0.5)
+    ap.add_argument("--probe-mode", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    unit = "anchored k-mers/s"
+    metric = "anchored k-mers/sec (positions x genomes) building pan-kmer bitmap"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference(args, wl, cores)
+        if "unavailable" in r:
+            print(json.dumps(r)); return
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic", "config": {"workload": wl["name"], "k": wl["k"], "sample": r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference",
+                                 "sample": r["sample"],
+                                 "note": f"run_anchor parallelises over anchors only (cpp/anchor.cpp:217): 1 anchor "
+                                         f"uses 1 of {cores} host cores"},
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line)); return
+
+    import torch
+    import torch.distributed as dist
+    from panagram_b200 import synth
+    from panagram_b200.engine import Engine, pinned_empty
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    npg, k = wl["n_per_gpu"], wl["k"]
+    n_total = npg * world
+    g_begin, g_end = rank * npg, (rank + 1) * npg
+    hbm_peak, peak_src = peaks()
+
+    # ---- setup (untimed): synthetic genomes -> per-genome tables on this rank's shard
+    t0 = time.perf_counter()
+    anc = synth.ancestor_codes(wl["length"], wl["seed"])
+    eng = Engine(k, n_total, g_begin, g_end, device=local_rank, load_factor=args.load_factor,
+                 probe_mode=args.probe_mode)
+    anchor_chroms = None
+    for g in range(g_begin, g_end):
+        chroms = make_genome(anc, g, wl["seed"])
+        if g == 0:
+            anchor_chroms = chroms
+        eng.reserve(g, sum(c.size for c in chroms))
+        for c in chroms:
+            eng.add_sequence(g, c)
+    if anchor_chroms is None:
+        anchor_chroms = make_genome(anc, 0, wl["seed"])
+    del anc
+    eng.finalize()
+    tstats = [eng.table_stats(g) for g in range(g_begin, g_end)]
+    setup_s = time.perf_counter() - t0
+
+    # anchor as one concatenated sequence ('N' between chromosomes), the layout pk_anchor_genome uses
+    lens = [c.size for c in anchor_chroms]
+    positions = sum(l - k + 1 for l in lens)
+    cat = np.full(sum(lens) + len(lens) - 1, ord("N"), dtype=np.uint8)
+    o = 0
+    for c in anchor_chroms:
+        cat[o:o + c.size] = c
+        o += c.size + 1
+    ltot = cat.size
+    npos = ltot - k + 1
+    rb_local = eng.row_bytes
+    rb_full = (n_total + 7) // 8
+    d_ascii = torch.from_numpy(cat).to(dev)
+    nw = eng.packed_words(ltot)
+    d_words = torch.empty(nw, dtype=torch.int64, device=dev)
+    d_mask = torch.empty(nw, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    eng.pack_device(d_ascii.data_ptr(), ltot, d_words.data_ptr(), d_mask.data_ptr(), st)
+    d_local = torch.empty((npos, rb_local), dtype=torch.uint8, device=dev)
+    if world > 1:
+        d_planes = torch.empty((world, npos, rb_local), dtype=torch.uint8, device=dev)
+        d_rows = torch.empty((npos, rb_full), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def device_step():
+        eng.probe_device(d_words.data_ptr(), d_mask.data_ptr(), 0, npos, d_local.data_ptr(), rb_local, 0, st)
+        if world > 1:
+            dist.all_gather_into_tensor(d_planes.view(-1), d_local.view(-1))
+            eng.interleave_device(d_planes.data_ptr(), world, npos, rb_local, d_rows.data_ptr(), rb_full, st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kstats = []
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        device_step()
+        ev[i + 1].record()
+    barrier()
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    ks = eng.stats()            # kernels of the last launch, CUDA events on the launching stream
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = positions * n_total / (ms_per_step / 1e3)
+
+    # ---- e2e: the public call with pinned host buffers, H2D + D2H inside the timed region
+    h_chroms = []
+    for c in anchor_chroms:
+        h = pinned_empty(c.size)
+        h[:] = c
+        h_chroms.append(h)
+    e2e_ms = None
+    if world == 1:
+        for _ in range(max(1, args.warmup - 1)):
+            res = eng.anchor_genome(h_chroms, pinned=True)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.steps):
+            t1 = time.perf_counter()
+            res = eng.anchor_genome(h_chroms, pinned=True)
+            ts.append((time.perf_counter() - t1) * 1e3)
+        e2e_ms = sum(ts) / len(ts)
+        e2e_stats = eng.stats()
+        h2d = sum(lens)
+        d2h = sum(r["bitmap1"].nbytes + r["low"].nbytes + r["bin_hist"].nbytes for r in res["chroms"]) + 8 * npg
+        e2e_launches = e2e_stats["kernel_launches"]
+    else:
+        # rank r: H2D of the anchor, pack, probe its shard, all-gather, interleave; rank 0 reads the rows back
+        h_cat = pinned_empty(ltot); h_cat[:] = cat
+        t_cat = torch.from_numpy(h_cat)
+        h_out = torch.empty((npos, rb_full), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+        def e2e_step():
+            d_ascii.copy_(t_cat, non_blocking=True)
+            eng.pack_device(d_ascii.data_ptr(), ltot, d_words.data_ptr(), d_mask.data_ptr(), st)
+            device_step()
+            if rank == 0:
+                h_out.copy_(d_rows, non_blocking=True)
+        e2e_step(); barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t1) * 1e3 / args.steps
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        h2d, d2h = ltot, npos * rb_full
+        e2e_launches = ks["kernel_launches"] + 2
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        # roofline of the dominant kernel (probe_part): algorithmic bytes per launch / its duration
+        nbytes_local = rb_local
+        alg_bytes = positions * (npg * 32 + 0.375 + nbytes_local * 1.01)
+        k3_ms = ks["k_probe_ms"] if ks["k_probe_ms"] > 0 else ms_per_step
+        stage_ms = statistics.median(step_ms)
+        roof = {"bound": "hbm", "kernel": "probe_part_kernel" if ks["k_probe_ms"] > 0 else "probe_kernel",
+                "achieved": alg_bytes / (k3_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (k3_ms / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k3_ms,
+                "stage": {"what": "all kernels of the probe stage (partition_seq + partition_fine + probe_part + spill)",
+                          "ms": stage_ms, "achieved": alg_bytes / (stage_ms / 1e3) / 1e9,
+                          "frac": alg_bytes / (stage_ms / 1e3) / 1e9 / hbm_peak,
+                          "kernels_ms": {"partition_seq": ks["k_partition_ms"], "partition_fine": ks["k_fine_ms"],
+                                         "probe_part": ks["k_probe_ms"], "spill": ks["k_spill_ms"]}}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            a2 = argparse.Namespace(steps=1, warmup=0)
+            r = run_reference(a2, wl, cores)
+            if "unavailable" not in r:
+                cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"],
+                       "ms": r["ms_per_step"]}
+            else:
+                cpu = {"value": None, "unit": unit, "cores": 0, "kind": "reference", "sample": r["unavailable"]}
+        launches = (ks["kernel_launches"] + (1 if world > 1 else 0)) * args.steps
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": wl["name"] + (f" x{world} genome shards ({n_total} genomes)" if world > 1 else ""),
+                           "k": k, "n_genomes": n_total, "genomes_per_gpu": npg, "positions": positions,
+                           "load_factor": args.load_factor, "probe_mode": args.probe_mode,
+                           "l2": "inputs (per-genome tables, %.1f GB/GPU) are far larger than L2; no flush needed"
+                                 % (sum(t["bytes"] for t in tstats) / 1e9),
+                           "parallelism": f"genome-sharded x{world}" if world > 1 else "1 GPU",
+                           "setup_s": round(setup_s, 1)},
+                "e2e": {"value": positions * n_total / (e2e_ms / 1e3), "unit": unit, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "tables": {"keys": [t["n_keys"] for t in tstats], "overflow_frac": sum(t["n_overflow"] for t in tstats) /
+                           max(1, sum(t["n_keys"] for t in tstats))}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

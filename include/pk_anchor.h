@@ -77,7 +77,8 @@ typedef struct pk_config {
     uint32_t max_bin_len;    /* 200000 (cpp/anchor.cpp:114; max_bin_kbp*1000) */
     uint32_t min_bin_count;  /* 100 (cpp/anchor.cpp:116; min_bin_count) */
     float load_factor;       /* table fill target, 0 < f <= 0.9; 0 selects the default 0.5 */
-    uint32_t chunk_positions;/* positions per pipelined chunk in pk_anchor_chrom; 0 = default */
+    uint32_t chunk_positions;/* max positions per probe launch (0 = default 512 Mi); a tuning/testing knob */
+    uint32_t probe_mode;     /* 0 auto (partitioned for launches >= 1 Mi positions), 1 direct, 2 partitioned */
 } pk_config;
 int pk_engine_create(const pk_config *cfg, pk_engine **out);
 void pk_engine_destroy(pk_engine *e);
@@ -121,7 +122,7 @@ int pk_engine_table_stats(const pk_engine *e, uint32_t genome, pk_table_stats *o
  *   Genome._write_bitmap + the per-chromosome reductions of Genome.run_anchor
  *   (index.py:949-969,1044-1051) for ONE chromosome, with the
  *   CKMCFile::GetCountersForRead calls (kmc_file.cpp:873-1027) inside it.
- *   H2D, pack, probe, reduce and D2H are pipelined over chunks.
+ *   Equivalent to pk_anchor_genome with one chromosome.
  *     ascii      [len]                          chromosome bytes, any case
  *     bitmap1    [nkmers * row_bytes]           step-1 rows, nkmers = len-k+1
  *     bitmap_low [ceil(nkmers/step) * row_bytes] rows with p % lowres_step == 0
@@ -135,6 +136,15 @@ int pk_engine_table_stats(const pk_engine *e, uint32_t genome, pk_table_stats *o
  *   by zero in the reference, cpp/anchor.cpp:116-120): bitmaps and col_sums are
  *   produced, bin_hist must be NULL or PK_EINVAL is returned. */
 uint64_t pk_bin_len(const pk_config *cfg, uint64_t nkmers);
+/* pk_anchor_genome: all chromosomes of one anchor in ONE batch (what KMCdb::anchor_fasta,
+ *   cpp/anchor.cpp:37-109, does chromosome by chromosome). Batching matters: every probe
+ *   launch streams each genome table through L2 once, so its cost is amortised over all
+ *   positions of the batch. Arrays are indexed by chromosome; per-chromosome outputs have
+ *   the sizes listed above; any array (or entry) may be NULL. col_sums accumulates over the
+ *   whole genome; nkmers_out[c] receives len-k+1 (0 when lens[c] < k). */
+int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                     uint8_t *const *bitmap1, uint8_t *const *bitmap_low, uint64_t *const *bin_hist,
+                     uint64_t *col_sums, uint64_t *nkmers_out);
 int pk_anchor_chrom(pk_engine *e, const char *ascii, uint64_t len,
                     uint8_t *bitmap1, uint8_t *bitmap_low,
                     uint64_t *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out);
@@ -183,6 +193,9 @@ int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t n_ranks, u
 /* timing / accounting of the last pk_anchor_chrom or pk_get_counters_for_read */
 typedef struct pk_stats {
     float h2d_ms, pack_ms, probe_ms, reduce_ms, d2h_ms, total_ms;
+    /* CUDA-event durations of the kernels of the last partitioned probe launch, on the stream
+     * they ran on: K1 partition_seq, K2 partition_fine, K3 probe_part, K3 over the spill list */
+    float k_partition_ms, k_fine_ms, k_probe_ms, k_spill_ms;
     uint64_t positions, probes, probe_launches, kernel_launches;
 } pk_stats;
 int pk_engine_stats(const pk_engine *e, pk_stats *out);

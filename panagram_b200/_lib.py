@@ -28,7 +28,7 @@ class PkConfig(C.Structure):
     _fields_ = [("k", C.c_uint32), ("n_genomes", C.c_uint32), ("genome_begin", C.c_uint32),
                 ("genome_end", C.c_uint32), ("device", C.c_int32), ("lowres_step", C.c_uint32),
                 ("max_bin_len", C.c_uint32), ("min_bin_count", C.c_uint32),
-                ("load_factor", C.c_float), ("chunk_positions", C.c_uint32)]
+                ("load_factor", C.c_float), ("chunk_positions", C.c_uint32), ("probe_mode", C.c_uint32)]
 
 
 class PkKmcdbInfo(C.Structure):
@@ -46,6 +46,8 @@ class PkTableStats(C.Structure):
 class PkStats(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("probe_ms", C.c_float),
                 ("reduce_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
+                ("k_partition_ms", C.c_float), ("k_fine_ms", C.c_float), ("k_probe_ms", C.c_float),
+                ("k_spill_ms", C.c_float),
                 ("positions", C.c_uint64), ("probes", C.c_uint64), ("probe_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64)]
 
@@ -72,6 +74,7 @@ SIGNATURES = {
     "pk_engine_finalize": (C.c_int, [_vp]),
     "pk_engine_table_stats": (C.c_int, [_vp, _u32, C.POINTER(PkTableStats)]),
     "pk_bin_len": (_u64, [C.POINTER(PkConfig), _u64]),
+    "pk_anchor_genome": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pk_anchor_chrom": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _pu64]),
     "pk_get_counters_for_read": (C.c_int, [_vp, _u32, _vp, _u64, _vp, _pu64]),
     "pk_host_alloc": (C.c_int, [_pp, _sz]),

@@ -21,8 +21,9 @@ def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
     """[(name, uint8 sequence)] with the C++ reference's rules (cpp/anchor.cpp:74-100):
     the record name is the header up to the first space, sequence lines are
     concatenated verbatim (a trailing \\r stays in the sequence unless strip_cr,
-    which gives Biopython's behaviour, index.py:922-930). gzip-aware like
-    Genome.iter_fasta."""
+    which drops every control byte (< 32) the way `kmc -fm` reads a FASTA
+    (kmc_core/splitter.cpp: "c < 32 // newliners") and Biopython strips line ends,
+    index.py:922-930). gzip-aware like Genome.iter_fasta."""
     path = str(path)
     if path.endswith(".gz") or path.endswith(".bgz"):
         with gzip.open(path, "rb") as fh:
@@ -44,7 +45,7 @@ def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
     keep = np.ones(buf.size, dtype=bool)
     keep[nl] = False
     if strip_cr:
-        keep[np.flatnonzero(buf == 13)] = False
+        keep[buf < 32] = False
     for j, hi in enumerate(hdr_idx):
         name = raw[starts[hi] + 1:ends[hi]].split(b" ")[0].decode()
         if strip_cr:
@@ -72,20 +73,21 @@ def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[st
     w1 = layout.BgzfWriter(outdir / "bitmap.1.gz", bgzf_level, threads)
     wl = layout.BgzfWriter(outdir / f"bitmap.{step}.gz", bgzf_level, threads)
     chroms, bins = [], []
-    col = np.zeros(engine.n_local, dtype=np.uint64)
     positions = 0
-    for cname, seq in parse_fasta(fasta, strip_cr=strip_cr):
+    recs = parse_fasta(fasta, strip_cr=strip_cr)
+    for cname, seq in recs:
         nk = seq.size - engine.k + 1
         if nk < 1 or engine.bin_len(nk) == 0:
             raise ValueError(f"{fasta}: chromosome {cname!r} has {max(nk, 0)} k-mers; the reference "
                              "needs at least min_bin_count (cpp/anchor.cpp:116-120)")
-        r = engine.anchor_chrom(seq)
+    res = engine.anchor_genome([s for _, s in recs], pinned=True)     # the whole genome in one batch
+    col = res["col_sums"]
+    for (cname, _), r in zip(recs, res["chroms"]):
         w1.write(r["bitmap1"])
         wl.write(r["low"])
-        chroms.append((cname, nk))
+        chroms.append((cname, r["nkmers"]))
         bins.append((r["binlen"], r["bin_hist"]))
-        col += r["col_sums"]
-        positions += nk
+        positions += r["nkmers"]
     w1.close(outdir / "bitmap.1.gzi")
     wl.close(outdir / f"bitmap.{step}.gzi")
     (outdir / "chrs.tsv").write_text(layout.chrs_tsv(chroms))

@@ -37,15 +37,6 @@ struct HostTable {
     bool reserved = false;
 };
 
-struct Slot {                    // one pipeline slot of pk_anchor_chrom
-    cudaStream_t stream = nullptr;
-    uint8_t *d_ascii = nullptr;
-    uint64_t *d_words = nullptr;
-    uint32_t *d_mask = nullptr;
-    uint8_t *d_rows = nullptr, *d_low = nullptr;
-    cudaEvent_t ev[6] = {};      // h2d start, pack start, probe start, reduce start, d2h start, end
-};
-
 struct pk_engine {
     pk_config cfg{};
     uint32_t n_local = 0, row_bytes = 0;
@@ -54,12 +45,22 @@ struct pk_engine {
     unsigned long long *d_counters = nullptr;   // [3 * n_local]
     bool finalized = false;
     cudaStream_t stream = nullptr;              // build stream / default stream for device-level calls
-    static const int kSlots = 3;
-    Slot slots[kSlots];
-    uint64_t chunk = 0;                         // positions per chunk
-    bool slots_ready = false;
-    unsigned long long *d_hist = nullptr;       // per-chromosome bin histogram
+    cudaStream_t copy_stream = nullptr;         // D2H of finished chromosomes
+    cudaEvent_t ev[6] = {};                     // begin, h2d done, pack done, probe done, reduce done, end
+    // genome-batch buffers (grow-only)
+    uint8_t *g_ascii = nullptr; uint64_t g_ascii_cap = 0;
+    uint64_t *g_words = nullptr; uint64_t g_words_cap = 0;
+    uint32_t *g_mask = nullptr; uint64_t g_mask_cap = 0;
+    uint8_t *g_rows = nullptr; uint64_t g_rows_cap = 0;
+    uint8_t *g_low = nullptr; uint64_t g_low_cap = 0;
+    uint32_t *g_u32 = nullptr; uint64_t g_u32_cap = 0;
+    unsigned long long *d_hist = nullptr;       // per-chromosome bin histograms
     uint64_t hist_cap = 0;
+    cudaEvent_t pev[5] = {};                    // around K1 / K2 / K3 / spill of the last partitioned launch
+    bool pev_valid = false;
+    PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
+    PkPartPlan sc_plan{};
+    int l2_prefetch = 1;
     unsigned long long *d_colsums = nullptr;    // [n_local]
     // staging for KMC ingestion
     uint8_t *h_stage = nullptr, *d_stage = nullptr;
@@ -122,7 +123,8 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (e->cfg.max_bin_len == 0) e->cfg.max_bin_len = 200000;
     if (e->cfg.min_bin_count == 0) e->cfg.min_bin_count = 100;
     if (e->cfg.load_factor == 0.f) e->cfg.load_factor = 0.5f;
-    e->chunk = cfg->chunk_positions ? cfg->chunk_positions : (4u << 20);
+    if (e->cfg.probe_mode > 2) { pk_set_error("probe_mode %u out of range", e->cfg.probe_mode); return PK_EINVAL; }
+    if (const char *pf = getenv("PK_L2_PREFETCH")) e->l2_prefetch = atoi(pf);
     e->n_local = cfg->genome_end - cfg->genome_begin;
     e->row_bytes = (e->n_local + 7) / 8;
     e->tabs.resize(e->n_local);
@@ -133,18 +135,9 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     CU(cudaMalloc(&e->d_counters, sizeof(unsigned long long) * 3 * e->n_local));
     CU(cudaMemset(e->d_counters, 0, sizeof(unsigned long long) * 3 * e->n_local));
     CU(cudaMalloc(&e->d_colsums, sizeof(unsigned long long) * e->n_local));
+    for (auto &ev : e->pev) CU(cudaEventCreate(&ev));
     *out = e.release();
     return PK_OK;
-}
-
-static void free_slots(pk_engine *e) {
-    for (auto &s : e->slots) {
-        if (s.stream) cudaStreamDestroy(s.stream);
-        cudaFree(s.d_ascii); cudaFree(s.d_words); cudaFree(s.d_mask); cudaFree(s.d_rows); cudaFree(s.d_low);
-        for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
-        s = Slot();
-    }
-    e->slots_ready = false;
 }
 
 extern "C" void pk_engine_destroy(pk_engine *e) {
@@ -152,7 +145,12 @@ extern "C" void pk_engine_destroy(pk_engine *e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (auto &t : e->tabs) cudaFree(t.dev.slots);
-    free_slots(e);
+    cudaFree(e->sc.buf1); cudaFree(e->sc.buf2); cudaFree(e->sc.spill);
+    cudaFree(e->sc.cursor1); cudaFree(e->sc.cursor2); cudaFree(e->sc.spill_cursor); cudaFree(e->sc.err);
+    cudaFree(e->g_ascii); cudaFree(e->g_words); cudaFree(e->g_mask); cudaFree(e->g_rows); cudaFree(e->g_low); cudaFree(e->g_u32);
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->pev) if (ev) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     cudaFree(e->d_tables); cudaFree(e->d_counters); cudaFree(e->d_colsums); cudaFree(e->d_hist);
     cudaFree(e->d_stage);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -389,18 +387,6 @@ extern "C" int pk_pack_device(pk_engine *e, const void *d_ascii, uint64_t len, v
     return PK_OK;
 }
 
-extern "C" int pk_probe_device(pk_engine *e, const void *d_words, const void *d_mask, uint64_t p0, uint64_t n,
-                               void *d_rows, uint32_t row_stride, uint32_t col_offset, void *stream) {
-    NEED_FINAL(e);
-    if (!d_words || !d_mask || !d_rows) { pk_set_error("null argument"); return PK_EINVAL; }
-    if (col_offset + e->row_bytes > row_stride) { pk_set_error("row_stride %u too small for %u bytes at offset %u", row_stride, e->row_bytes, col_offset); return PK_EINVAL; }
-    int rc = set_device(e); if (rc) return rc;
-    pk_launch_probe((const uint64_t *)d_words, (const uint32_t *)d_mask, p0, n, e->cfg.k, e->d_tables, e->n_local,
-                    (uint8_t *)d_rows, row_stride, col_offset, stream ? (pk_stream_t)stream : e->stream);
-    CU(cudaGetLastError());
-    return PK_OK;
-}
-
 extern "C" int pk_reduce_device(pk_engine *e, const void *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first,
                                 uint64_t n, uint64_t binlen, void *d_bin_hist, void *d_col_sums, void *d_rows_low,
                                 uint32_t lowres_step, void *stream) {
@@ -426,124 +412,203 @@ extern "C" int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t
     return PK_OK;
 }
 
-// ------------------------------------------------------------------ host-level hot path
-static int ensure_slots(pk_engine *e) {
-    if (e->slots_ready) return PK_OK;
-    const uint64_t C = e->chunk, k = e->cfg.k;
-    const uint64_t nw = pk_packed_words(C + k);
-    const uint64_t low_rows = C / e->cfg.lowres_step + 2;
-    for (auto &s : e->slots) {
-        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CU(cudaMalloc(&s.d_ascii, C + k + 32));
-        CU(cudaMalloc(&s.d_words, nw * 8));
-        CU(cudaMalloc(&s.d_mask, nw * 4));
-        CU(cudaMalloc(&s.d_rows, C * e->row_bytes));
-        CU(cudaMalloc(&s.d_low, low_rows * e->row_bytes));
-        for (auto &ev : s.ev) CU(cudaEventCreate(&ev));
-    }
-    e->slots_ready = true;
+// ------------------------------------------------------------------ probe dispatch
+static void free_scratch(pk_engine *e) {
+    cudaFree(e->sc.buf1); cudaFree(e->sc.buf2); cudaFree(e->sc.spill);
+    cudaFree(e->sc.cursor1); cudaFree(e->sc.cursor2); cudaFree(e->sc.spill_cursor); cudaFree(e->sc.err);
+    e->sc = PkPartScratch{};
+    e->sc_plan = PkPartPlan{};
+}
+
+static int ensure_scratch(pk_engine *e, const PkPartPlan &pl) {
+    const PkPartPlan &have = e->sc_plan;
+    if (e->sc.buf1 && have.buf1_items >= pl.buf1_items && have.buf2_items >= pl.buf2_items &&
+        have.spill_items >= pl.spill_items && have.n_regions1 >= pl.n_regions1 && have.n_regions2 >= pl.n_regions2)
+        return PK_OK;
+    CU(cudaDeviceSynchronize());
+    free_scratch(e);
+    CU(cudaMalloc(&e->sc.buf1, std::max<uint64_t>(pl.buf1_items, 1) * 8));
+    CU(cudaMalloc(&e->sc.buf2, std::max<uint64_t>(pl.buf2_items, 1) * 8));
+    CU(cudaMalloc(&e->sc.spill, std::max<uint64_t>(pl.spill_items, 1) * 8));
+    CU(cudaMalloc(&e->sc.cursor1, sizeof(uint32_t) * std::max(pl.n_regions1, 1u)));
+    CU(cudaMalloc(&e->sc.cursor2, sizeof(uint32_t) * std::max(pl.n_regions2, 1u)));
+    CU(cudaMalloc(&e->sc.spill_cursor, sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->sc.err, sizeof(uint32_t)));
+    CU(cudaMemset(e->sc.err, 0, sizeof(uint32_t)));
+    e->sc_plan = pl;
     return PK_OK;
 }
 
-struct ChunkTimes { int slot; };
+// rows for positions [p0, p0+n): the partitioned path for large batches, the direct kernel otherwise
+static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n,
+                     uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, cudaStream_t s) {
+    const uint32_t mode = e->cfg.probe_mode;
+    const uint64_t sub = e->cfg.chunk_positions ? e->cfg.chunk_positions : PK_PART_MAX_N;
+    for (uint64_t o = 0; o < n; o += sub) {
+        const uint64_t m = std::min(sub, n - o);
+        const bool part = mode == 2 || (mode == 0 && m >= (1ull << 20));
+        if (part) {
+            PkPartPlan pl;
+            pk_part_plan(m, &pl);
+            int rc = ensure_scratch(e, pl); if (rc) return rc;
+            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->cfg.k, e->d_tables, e->n_local,
+                                            d_rows + o * row_stride, row_stride, col_offset, pl, e->sc, e->l2_prefetch, s, e->pev)) {
+                pk_set_error("partitioned probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return PK_ECUDA;
+            }
+            e->stats.kernel_launches += 3 + (pl.pb2 ? 1 : 0);
+            e->stats.probe_launches += 1;
+            e->pev_valid = true;
+        } else {
+            pk_launch_probe(d_words, d_mask, p0 + o, m, e->cfg.k, e->d_tables, e->n_local, d_rows + o * row_stride,
+                            row_stride, col_offset, s);
+            e->stats.kernel_launches += 1;
+            e->stats.probe_launches += 1;
+        }
+        CU(cudaGetLastError());
+    }
+    return PK_OK;
+}
+
+static int check_part_error(pk_engine *e) {
+    if (!e->sc.err) return PK_OK;
+    uint32_t err = 0;
+    CU(cudaMemcpy(&err, e->sc.err, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) { pk_set_error("partitioned probe: spill list overflow (internal error)"); return PK_ECUDA; }
+    return PK_OK;
+}
+
+extern "C" int pk_probe_device(pk_engine *e, const void *d_words, const void *d_mask, uint64_t p0, uint64_t n,
+                               void *d_rows, uint32_t row_stride, uint32_t col_offset, void *stream) {
+    NEED_FINAL(e);
+    if (!d_words || !d_mask || !d_rows) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (col_offset + e->row_bytes > row_stride) { pk_set_error("row_stride %u too small for %u bytes at offset %u", row_stride, e->row_bytes, col_offset); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    return probe_any(e, (const uint64_t *)d_words, (const uint32_t *)d_mask, p0, n, (uint8_t *)d_rows, row_stride,
+                     col_offset, stream ? (cudaStream_t)stream : e->stream);
+}
+
+// ------------------------------------------------------------------ host-level hot path
+template <typename T> static int grow(T *&p, uint64_t &cap, uint64_t need) {
+    if (cap >= need) return PK_OK;
+    CU(cudaDeviceSynchronize());
+    cudaFree(p); p = nullptr; cap = 0;
+    CU(cudaMalloc(&p, need * sizeof(T)));
+    cap = need;
+    return PK_OK;
+}
+
+extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                                uint8_t *const *bitmap1, uint8_t *const *bitmap_low, uint64_t *const *bin_hist,
+                                uint64_t *col_sums, uint64_t *nkmers_out) {
+    NEED_FINAL(e);
+    if (n_chroms && (!seqs || !lens)) { pk_set_error("null argument"); return PK_EINVAL; }
+    const uint32_t k = e->cfg.k, step = e->cfg.lowres_step, rb = e->row_bytes, N = e->n_local;
+    memset(&e->stats, 0, sizeof e->stats);
+    // layout of the concatenated sequence: chromosome c at off[c], one 'N' between neighbours so
+    // that no window spans two chromosomes
+    std::vector<uint64_t> off(n_chroms), nk(n_chroms), binlen(n_chroms), nbins(n_chroms), lowoff(n_chroms), histoff(n_chroms);
+    uint64_t ltot = 0, lowtot = 0, histtot = 0, postot = 0;
+    for (uint32_t c = 0; c < n_chroms; c++) {
+        if (!seqs[c] && lens[c]) { pk_set_error("null sequence %u", c); return PK_EINVAL; }
+        off[c] = ltot;
+        ltot += lens[c] + 1;
+        nk[c] = lens[c] >= k ? lens[c] - k + 1 : 0;        // len < k: nothing (kmc_file.cpp:878-882)
+        binlen[c] = nk[c] ? pk_bin_len(&e->cfg, nk[c]) : 0;
+        const bool want_hist = bin_hist && bin_hist[c] && nk[c];
+        if (want_hist && binlen[c] == 0) {
+            pk_set_error("chromosome %u with %llu k-mers (< min_bin_count %u) has no defined bins", c,
+                         (unsigned long long)nk[c], e->cfg.min_bin_count);
+            return PK_EINVAL;
+        }
+        nbins[c] = want_hist ? (nk[c] + binlen[c] - 1) / binlen[c] : 0;
+        lowoff[c] = lowtot; lowtot += (nk[c] + step - 1) / step;
+        histoff[c] = histtot; histtot += nbins[c] * (N + 1);
+        postot += nk[c];
+        if (nkmers_out) nkmers_out[c] = nk[c];
+    }
+    if (postot == 0) return PK_OK;
+    int rc = set_device(e); if (rc) return rc;
+    const uint64_t nw = pk_packed_words(ltot);
+    rc = grow(e->g_ascii, e->g_ascii_cap, ltot + 64); if (rc) return rc;
+    rc = grow(e->g_words, e->g_words_cap, nw); if (rc) return rc;
+    rc = grow(e->g_mask, e->g_mask_cap, nw); if (rc) return rc;
+    rc = grow(e->g_rows, e->g_rows_cap, ltot * rb); if (rc) return rc;
+    rc = grow(e->g_low, e->g_low_cap, (lowtot + 1) * rb); if (rc) return rc;
+    rc = grow(e->d_hist, e->hist_cap, histtot + 1); if (rc) return rc;
+    if (!e->ev[0]) for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
+    if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t s = e->stream, cs = e->copy_stream;
+    CU(cudaEventRecord(e->ev[0], s));
+    CU(cudaMemsetAsync(e->g_ascii, 'N', ltot + 64, s));
+    for (uint32_t c = 0; c < n_chroms; c++)
+        if (lens[c]) CU(cudaMemcpyAsync(e->g_ascii + off[c], seqs[c], lens[c], cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(e->d_hist, 0, (histtot + 1) * 8, s));
+    CU(cudaMemsetAsync(e->d_colsums, 0, N * 8, s));
+    CU(cudaEventRecord(e->ev[1], s));
+    pk_launch_pack(e->g_ascii, ltot, nw, e->g_words, e->g_mask, s);
+    CU(cudaEventRecord(e->ev[2], s));
+    const uint64_t npos = ltot >= k ? ltot - k + 1 : 0;
+    rc = probe_any(e, e->g_words, e->g_mask, 0, npos, e->g_rows, rb, 0, s); if (rc) return rc;
+    CU(cudaEventRecord(e->ev[3], s));
+    // per chromosome: reduce on the compute stream, rows/low-res rows home on the copy stream
+    std::vector<cudaEvent_t> done(n_chroms, nullptr);
+    for (uint32_t c = 0; c < n_chroms; c++) {
+        if (!nk[c]) continue;
+        const uint8_t *rows_c = e->g_rows + off[c] * rb;
+        uint8_t *low_c = e->g_low + lowoff[c] * rb;
+        const bool want_low = bitmap_low && bitmap_low[c];
+        if (nbins[c] || col_sums || want_low) {
+            pk_launch_reduce(rows_c, rb, N, 0, nk[c], nbins[c] ? binlen[c] : 0, nbins[c] ? e->d_hist + histoff[c] : nullptr,
+                             col_sums ? e->d_colsums : nullptr, want_low ? low_c : nullptr, step, s);
+            e->stats.kernel_launches += 1;
+        }
+        CU(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+        CU(cudaEventRecord(done[c], s));
+        CU(cudaStreamWaitEvent(cs, done[c], 0));
+        if (bitmap1 && bitmap1[c]) CU(cudaMemcpyAsync(bitmap1[c], rows_c, nk[c] * rb, cudaMemcpyDeviceToHost, cs));
+        if (want_low) CU(cudaMemcpyAsync(bitmap_low[c], low_c, ((nk[c] + step - 1) / step) * rb, cudaMemcpyDeviceToHost, cs));
+    }
+    CU(cudaEventRecord(e->ev[4], s));
+    std::vector<unsigned long long> hist_h, col_h;
+    if (histtot) {
+        hist_h.resize(histtot);
+        CU(cudaMemcpyAsync(hist_h.data(), e->d_hist, histtot * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (col_sums) {
+        col_h.resize(N);
+        CU(cudaMemcpyAsync(col_h.data(), e->d_colsums, N * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    CU(cudaStreamSynchronize(cs));
+    CU(cudaEventRecord(e->ev[5], s));
+    CU(cudaEventSynchronize(e->ev[5]));
+    for (auto ev : done) if (ev) cudaEventDestroy(ev);
+    rc = check_part_error(e); if (rc) return rc;
+    for (uint32_t c = 0; c < n_chroms; c++)
+        if (nbins[c]) memcpy(bin_hist[c], hist_h.data() + histoff[c], nbins[c] * (N + 1) * 8);
+    if (col_sums) for (uint32_t g = 0; g < N; g++) col_sums[g] += col_h[g];
+    CU(cudaEventElapsedTime(&e->stats.h2d_ms, e->ev[0], e->ev[1]));
+    CU(cudaEventElapsedTime(&e->stats.pack_ms, e->ev[1], e->ev[2]));
+    CU(cudaEventElapsedTime(&e->stats.probe_ms, e->ev[2], e->ev[3]));
+    CU(cudaEventElapsedTime(&e->stats.reduce_ms, e->ev[3], e->ev[4]));
+    CU(cudaEventElapsedTime(&e->stats.d2h_ms, e->ev[4], e->ev[5]));
+    CU(cudaEventElapsedTime(&e->stats.total_ms, e->ev[0], e->ev[5]));
+    e->stats.kernel_launches += 1;   // pack
+    e->stats.positions = postot;
+    e->stats.probes = postot * N;
+    return PK_OK;
+}
 
 extern "C" int pk_anchor_chrom(pk_engine *e, const char *ascii, uint64_t len, uint8_t *bitmap1, uint8_t *bitmap_low,
                                uint64_t *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out) {
-    NEED_FINAL(e);
-    if (!ascii && len) { pk_set_error("null sequence"); return PK_EINVAL; }
-    const uint32_t k = e->cfg.k, step = e->cfg.lowres_step, rb = e->row_bytes;
-    if (nkmers_out) *nkmers_out = 0;
-    memset(&e->stats, 0, sizeof e->stats);
-    if (len < k) return PK_OK;                      // GetCountersForRead: clears and returns false (kmc_file.cpp:878-882)
-    const uint64_t nk = len - k + 1;
-    const uint64_t binlen = pk_bin_len(&e->cfg, nk);
-    if (bin_hist && binlen == 0) {
-        pk_set_error("chromosome with %llu k-mers (< min_bin_count %u) has no defined bins", (unsigned long long)nk, e->cfg.min_bin_count);
-        return PK_EINVAL;
-    }
-    int rc = set_device(e); if (rc) return rc;
-    rc = ensure_slots(e); if (rc) return rc;
-    const uint64_t nbins = binlen ? (nk + binlen - 1) / binlen : 0;
-    const uint64_t hist_words = nbins * (e->n_local + 1);
-    if (bin_hist) {
-        if (e->hist_cap < hist_words) {
-            cudaFree(e->d_hist); e->d_hist = nullptr; e->hist_cap = 0;
-            CU(cudaMalloc(&e->d_hist, hist_words * 8));
-            e->hist_cap = hist_words;
-        }
-        CU(cudaMemsetAsync(e->d_hist, 0, hist_words * 8, e->stream));
-    }
-    if (col_sums) CU(cudaMemsetAsync(e->d_colsums, 0, e->n_local * 8, e->stream));
-    cudaEvent_t ev_begin, ev_ready, ev_end;
-    CU(cudaEventCreate(&ev_begin)); CU(cudaEventCreate(&ev_ready)); CU(cudaEventCreate(&ev_end));
-    CU(cudaEventRecord(ev_begin, e->stream));
-    CU(cudaEventRecord(ev_ready, e->stream));
-    const uint64_t C = e->chunk;
-    const uint64_t nchunks = (nk + C - 1) / C;
-    std::vector<float> t_h2d, t_pack, t_probe, t_red, t_d2h;
-    auto harvest = [&](Slot &s) -> int {      // the slot's previous chunk has completed: collect its timings
-        float ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1])); e->stats.h2d_ms += ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[1], s.ev[2])); e->stats.pack_ms += ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3])); e->stats.probe_ms += ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[3], s.ev[4])); e->stats.reduce_ms += ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[4], s.ev[5])); e->stats.d2h_ms += ms;
-        return PK_OK;
-    };
-    for (uint64_t c = 0; c < nchunks; c++) {
-        Slot &s = e->slots[c % pk_engine::kSlots];
-        const uint64_t p0 = c * C, n = std::min(C, nk - p0);
-        if (c >= (uint64_t)pk_engine::kSlots) {
-            CU(cudaStreamSynchronize(s.stream));
-            rc = harvest(s); if (rc) return rc;
-        } else {
-            CU(cudaStreamWaitEvent(s.stream, ev_ready, 0));   // hist/colsum memsets
-        }
-        const uint64_t nbytes_in = n + k - 1;
-        CU(cudaEventRecord(s.ev[0], s.stream));
-        CU(cudaMemcpyAsync(s.d_ascii, ascii + p0, nbytes_in, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaEventRecord(s.ev[1], s.stream));
-        pk_launch_pack(s.d_ascii, nbytes_in, pk_packed_words(nbytes_in), s.d_words, s.d_mask, s.stream);
-        CU(cudaEventRecord(s.ev[2], s.stream));
-        pk_launch_probe(s.d_words, s.d_mask, 0, n, k, e->d_tables, e->n_local, s.d_rows, rb, 0, s.stream);
-        CU(cudaEventRecord(s.ev[3], s.stream));
-        const bool want_low = bitmap_low != nullptr;
-        if (bin_hist || col_sums || want_low)
-            pk_launch_reduce(s.d_rows, rb, e->n_local, p0, n, bin_hist ? binlen : 0, bin_hist ? e->d_hist : nullptr,
-                             col_sums ? e->d_colsums : nullptr, want_low ? s.d_low : nullptr, step, s.stream);
-        CU(cudaEventRecord(s.ev[4], s.stream));
-        if (bitmap1) CU(cudaMemcpyAsync(bitmap1 + p0 * rb, s.d_rows, n * rb, cudaMemcpyDeviceToHost, s.stream));
-        if (want_low) {
-            const uint64_t l0 = (p0 + step - 1) / step, l1 = (p0 + n + step - 1) / step;   // low rows in [l0, l1)
-            if (l1 > l0) CU(cudaMemcpyAsync(bitmap_low + l0 * rb, s.d_low, (l1 - l0) * rb, cudaMemcpyDeviceToHost, s.stream));
-        }
-        CU(cudaEventRecord(s.ev[5], s.stream));
-        CU(cudaGetLastError());
-        e->stats.probe_launches += 1;
-        e->stats.kernel_launches += 2 + ((bin_hist || col_sums || want_low) ? 1 : 0);
-    }
-    for (uint64_t c = 0; c < std::min<uint64_t>(nchunks, pk_engine::kSlots); c++) {
-        Slot &s = e->slots[(nchunks - 1 - c) % pk_engine::kSlots];
-        CU(cudaStreamSynchronize(s.stream));
-        rc = harvest(s); if (rc) return rc;
-    }
-    std::vector<unsigned long long> tmp;
-    if (bin_hist) {
-        CU(cudaMemcpyAsync(bin_hist, e->d_hist, hist_words * 8, cudaMemcpyDeviceToHost, e->stream));
-    }
-    if (col_sums) {
-        tmp.resize(e->n_local);
-        CU(cudaMemcpyAsync(tmp.data(), e->d_colsums, e->n_local * 8, cudaMemcpyDeviceToHost, e->stream));
-    }
-    CU(cudaEventRecord(ev_end, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    if (col_sums) for (uint32_t g = 0; g < e->n_local; g++) col_sums[g] += tmp[g];
-    CU(cudaEventElapsedTime(&e->stats.total_ms, ev_begin, ev_end));
-    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_ready); cudaEventDestroy(ev_end);
-    e->stats.positions = nk;
-    e->stats.probes = nk * e->n_local;
-    if (nkmers_out) *nkmers_out = nk;
-    return PK_OK;
+    const char *seqs[1] = {ascii};
+    uint8_t *b1[1] = {bitmap1}, *bl[1] = {bitmap_low};
+    uint64_t *bh[1] = {bin_hist};
+    uint64_t nk = 0;
+    int rc = pk_anchor_genome(e, 1, seqs, &len, b1, bl, bh, col_sums, &nk);
+    if (nkmers_out) *nkmers_out = rc == PK_OK ? nk : 0;
+    return rc;
 }
 
 extern "C" int pk_get_counters_for_read(pk_engine *e, uint32_t dbi, const char *read, uint64_t len, uint32_t *counters,
@@ -563,22 +628,22 @@ extern "C" int pk_get_counters_for_read(pk_engine *e, uint32_t dbi, const char *
     const uint32_t shift = g_lo - 32 * dbi;                              // multiple of 8
     const uint32_t nbits = g_hi - g_lo, nbytes = (nbits + 7) / 8;
     const uint32_t mask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1);
-    uint8_t *d_ascii = nullptr, *d_rows = nullptr; uint64_t *d_words = nullptr; uint32_t *d_mask = nullptr, *d_out = nullptr;
     const uint64_t nw = pk_packed_words(len);
-    struct Freer { void *p = nullptr; ~Freer() { cudaFree(p); } } f[5];
-    CU(cudaMalloc(&d_ascii, len)); f[0].p = d_ascii;
-    CU(cudaMalloc(&d_words, nw * 8)); f[1].p = d_words;
-    CU(cudaMalloc(&d_mask, nw * 4)); f[2].p = d_mask;
-    CU(cudaMalloc(&d_rows, nk * rb)); f[3].p = d_rows;
-    CU(cudaMalloc(&d_out, nk * 4)); f[4].p = d_out;
+    rc = grow(e->g_ascii, e->g_ascii_cap, len + 64); if (rc) return rc;
+    rc = grow(e->g_words, e->g_words_cap, nw); if (rc) return rc;
+    rc = grow(e->g_mask, e->g_mask_cap, nw); if (rc) return rc;
+    rc = grow(e->g_rows, e->g_rows_cap, (len + 1) * rb); if (rc) return rc;
+    rc = grow(e->g_u32, e->g_u32_cap, nk); if (rc) return rc;
     cudaStream_t s = e->stream;
-    CU(cudaMemcpyAsync(d_ascii, read, len, cudaMemcpyHostToDevice, s));
-    pk_launch_pack(d_ascii, len, nw, d_words, d_mask, s);
-    pk_launch_probe(d_words, d_mask, 0, nk, k, e->d_tables, e->n_local, d_rows, rb, 0, s);
-    pk_launch_rows_to_u32(d_rows, rb, byte_off, nbytes, mask, nk, d_out, s);
+    memset(&e->stats, 0, sizeof e->stats);
+    CU(cudaMemcpyAsync(e->g_ascii, read, len, cudaMemcpyHostToDevice, s));
+    pk_launch_pack(e->g_ascii, len, nw, e->g_words, e->g_mask, s);
+    rc = probe_any(e, e->g_words, e->g_mask, 0, nk, e->g_rows, rb, 0, s); if (rc) return rc;
+    pk_launch_rows_to_u32(e->g_rows, rb, byte_off, nbytes, mask, nk, e->g_u32, s);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(counters, d_out, nk * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(counters, e->g_u32, nk * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    rc = check_part_error(e); if (rc) return rc;
     if (shift) for (uint64_t i = 0; i < nk; i++) counters[i] <<= shift;
     *n_out = nk;
     return PK_OK;
@@ -587,5 +652,13 @@ extern "C" int pk_get_counters_for_read(pk_engine *e, uint32_t dbi, const char *
 extern "C" int pk_engine_stats(const pk_engine *e, pk_stats *out) {
     if (!e || !out) { pk_set_error("null argument"); return PK_EINVAL; }
     *out = e->stats;
+    out->k_partition_ms = out->k_fine_ms = out->k_probe_ms = out->k_spill_ms = 0.f;
+    if (e->pev_valid) {      // kernels of the last partitioned launch, timed on their own stream
+        CU(cudaEventSynchronize(e->pev[4]));
+        CU(cudaEventElapsedTime(&out->k_partition_ms, e->pev[0], e->pev[1]));
+        CU(cudaEventElapsedTime(&out->k_fine_ms, e->pev[1], e->pev[2]));
+        CU(cudaEventElapsedTime(&out->k_probe_ms, e->pev[2], e->pev[3]));
+        CU(cudaEventElapsedTime(&out->k_spill_ms, e->pev[3], e->pev[4]));
+    }
     return PK_OK;
 }

@@ -71,4 +71,22 @@ void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n,
 void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
                            uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
 void pk_launch_table_overflow_count(PkTable t, unsigned long long *d_out, pk_stream_t s);
+
+// ---- partitioned probe (pk_partition.cu) ----
+#define PK_PART_MAX_N (512ull << 20)   // positions per partitioned launch (2^18 partitions of <= 2560 mean fill)
+struct PkPartPlan {
+    uint32_t pb1, pb2, cap1, cap2, n_regions1, n_regions2;
+    uint64_t buf1_items, buf2_items, spill_items;   // 8-byte (hash, pos) items
+};
+struct PkPartScratch {
+    void *buf1, *buf2, *spill;
+    uint32_t *cursor1, *cursor2;
+    unsigned long long *spill_cursor;
+    uint32_t *err;
+};
+void pk_part_plan(uint64_t n, PkPartPlan *pl);
+int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
+                                const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
+                                uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, int prefetch,
+                                pk_stream_t s, struct CUevent_st **evs /*5 events or NULL*/);
 #endif

@@ -45,11 +45,13 @@ class Engine:
 
     def __init__(self, k: int, n_genomes: int, genome_begin: int = 0, genome_end: int | None = None,
                  device: int = 0, lowres_step: int = 100, max_bin_kbp: int = 200,
-                 min_bin_count: int = 100, load_factor: float = 0.5, chunk_positions: int = 0):
+                 min_bin_count: int = 100, load_factor: float = 0.5, chunk_positions: int = 0,
+                 probe_mode: str | int = "auto"):
         self._L = _lib.lib()
         genome_end = n_genomes if genome_end is None else genome_end
+        mode = {"auto": 0, "direct": 1, "partitioned": 2}.get(probe_mode, probe_mode)
         self.cfg = PkConfig(k, n_genomes, genome_begin, genome_end, device, lowres_step,
-                            max_bin_kbp * 1000, min_bin_count, load_factor, chunk_positions)
+                            max_bin_kbp * 1000, min_bin_count, load_factor, chunk_positions, mode)
         self.k, self.n_genomes = k, n_genomes
         self.genome_begin, self.genome_end = genome_begin, genome_end
         self.n_local = genome_end - genome_begin
@@ -137,6 +139,36 @@ class Engine:
         res.update(bitmap1=None if b1 is None else b1[:nk], low=lo, bin_hist=hi, col_sums=cs,
                    binlen=binlen)
         return res
+
+    def anchor_genome(self, seqs, bitmap1=True, low=True, hist=True, colsums=True, pinned=False) -> dict:
+        """All chromosomes of one anchor in one batch (pk_anchor_genome).
+
+        Returns {'chroms': [per-chromosome dicts as anchor_chrom], 'col_sums': [N_local]}.
+        Chromosomes with fewer than min_bin_count k-mers get no histogram.
+        """
+        arrs = [_u8(s) for s in seqs]
+        n = len(arrs)
+        rb, step = self.row_bytes, self.lowres_step
+        alloc = pinned_empty if pinned else (lambda shape, dtype=np.uint8: np.empty(shape, dtype=dtype))
+        nks = [max(a.size - self.k + 1, 0) for a in arrs]
+        b1 = [alloc((nk, rb)) if (bitmap1 and nk) else None for nk in nks]
+        lo = [alloc(((nk + step - 1) // step, rb)) if (low and nk) else None for nk in nks]
+        bl = [self.bin_len(nk) if nk else 0 for nk in nks]
+        hi = [np.zeros(((nk + b - 1) // b, self.n_local + 1), dtype=np.uint64) if (hist and nk and b) else None
+              for nk, b in zip(nks, bl)]
+        cs = np.zeros(self.n_local, dtype=np.uint64) if colsums else None
+
+        def ptrs(lst):
+            return (C.c_void_p * n)(*[None if x is None else x.ctypes.data for x in lst])
+
+        lens = (C.c_uint64 * n)(*[a.size for a in arrs])
+        nko = (C.c_uint64 * n)()
+        check(self._L.pk_anchor_genome(self._h, n, ptrs(arrs), lens, ptrs(b1), ptrs(lo), ptrs(hi),
+                                       None if cs is None else cs.ctypes.data, nko))
+        assert list(nko) == nks
+        chroms = [{"nkmers": nk, "bitmap1": x, "low": y, "bin_hist": z, "binlen": b}
+                  for nk, x, y, z, b in zip(nks, b1, lo, hi, bl)]
+        return {"chroms": chroms, "col_sums": cs}
 
     def get_counters_for_read(self, dbi: int, read) -> np.ndarray | None:
         """uint32 counters of bitvec database `dbi` for every k-mer of `read`

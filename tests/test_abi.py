@@ -29,9 +29,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes():
-    assert C.sizeof(_lib.PkConfig) == 40
+    assert C.sizeof(_lib.PkConfig) == 44
     assert C.sizeof(_lib.PkKmcdbInfo) == 56
-    assert C.sizeof(_lib.PkStats) == 56
+    assert C.sizeof(_lib.PkStats) == 72
 
 
 @pytest.mark.parametrize("name", ["kmc_db", "kmc_db_sorted"])
@@ -68,7 +68,7 @@ def test_bin_len_rule():
     L = _lib.lib()
     for nk in (0, 99, 100, 199, 4321, 19_999_999, 20_000_000, 135_000_000):
         assert L.pk_bin_len(None, nk) == oracle.binlen(nk)
-    cfg = _lib.PkConfig(21, 1, 0, 1, 0, 100, 50_000, 10, 0.5, 0)
+    cfg = _lib.PkConfig(21, 1, 0, 1, 0, 100, 50_000, 10, 0.5, 0, 0)
     assert L.pk_bin_len(C.byref(cfg), 1_000_000) == 50_000
     assert L.pk_bin_len(C.byref(cfg), 1000) == 100
 

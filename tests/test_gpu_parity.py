@@ -10,22 +10,29 @@ from panagram_b200.engine import Engine, pinned_empty
 pytestmark = pytest.mark.gpu
 
 
-def anchor_outputs(eng, fasta, n_genomes):
-    """What cpp/anchor.cpp writes for one anchor, assembled from Engine.anchor_chrom."""
+def anchor_outputs(eng, fasta, n_genomes, batch=False):
+    """What cpp/anchor.cpp writes for one anchor, assembled from Engine.anchor_chrom (one call per
+    chromosome) or Engine.anchor_genome (one batch)."""
     b1, lo, chroms, bins = [], [], [], []
     col = np.zeros(eng.n_local, dtype=np.uint64)
-    for name, seq in anchor.parse_fasta(fasta):
-        r = eng.anchor_chrom(seq)
+    recs = anchor.parse_fasta(fasta)
+    if batch:
+        res = eng.anchor_genome([s for _, s in recs])
+        rs, col = res["chroms"], res["col_sums"]
+    else:
+        rs = [eng.anchor_chrom(seq) for _, seq in recs]
+        for r in rs:
+            col += r["col_sums"]
+    for (name, _), r in zip(recs, rs):
         b1.append(r["bitmap1"].tobytes()); lo.append(r["low"].tobytes())
         chroms.append((name, r["nkmers"])); bins.append((r["binlen"], r["bin_hist"]))
-        col += r["col_sums"]
     return {"bitmap.1": b"".join(b1), "bitmap.100": b"".join(lo), "chrs.tsv": layout.chrs_tsv(chroms),
             "bitsum.bins.tsv": layout.bins_tsv(n_genomes, bins), "col_sums": col}
 
 
 def check_against_golden(eng, pan):
-    for a in pan["anchors"]:
-        got = anchor_outputs(eng, pan["fasta"][a], pan["n_genomes"])
+    for ai, a in enumerate(pan["anchors"]):
+        got = anchor_outputs(eng, pan["fasta"][a], pan["n_genomes"], batch=bool(ai % 2))
         for key, want in pan["expected"][a].items():
             assert got[key] == want, f"{a}/{key}"
         rows = np.frombuffer(got["bitmap.1"], dtype=np.uint8).reshape(-1, eng.row_bytes)
@@ -34,10 +41,10 @@ def check_against_golden(eng, pan):
 
 
 @pytest.mark.parametrize("which", ["pan3", "pan35"])
-@pytest.mark.parametrize("chunk", [0, 777])
-def test_bitvec_db_engine_equals_reference(which, chunk, request):
+@pytest.mark.parametrize("mode,chunk", [("auto", 0), ("direct", 777), ("partitioned", 0), ("partitioned", 1000)])
+def test_bitvec_db_engine_equals_reference(which, mode, chunk, request):
     pan = request.getfixturevalue(which)
-    eng = Engine(pan["k"], pan["n_genomes"], chunk_positions=chunk)
+    eng = Engine(pan["k"], pan["n_genomes"], chunk_positions=chunk, probe_mode=mode)
     for i in range(pan["ndb"]):
         eng.add_bitvec(32 * i, pan["dir"] / "kmc" / f"bitvec{i}")
     eng.finalize()
@@ -58,10 +65,12 @@ def test_per_genome_kmc_dbs_equal_reference(pan3, kind):
 
 
 def test_tables_built_from_fasta_equal_reference(pan3):
-    """On-GPU k-mer set construction straight from the sequences == kmc -ci1 (FASTA input)."""
+    """On-GPU k-mer set construction straight from the sequences == kmc -ci1 (FASTA input).
+    kmc drops control bytes (the fixture's CRLF) when reading, so the set is built that way;
+    the anchor side keeps cpp/anchor.cpp's verbatim lines."""
     eng = Engine(pan3["k"], 3)
     for g, name in enumerate(pan3["names"]):
-        recs = anchor.parse_fasta(pan3["fasta"][name])
+        recs = anchor.parse_fasta(pan3["fasta"][name], strip_cr=True)
         eng.reserve(g, sum(max(s.size - pan3["k"] + 1, 0) for _, s in recs))
         for _, s in recs:
             eng.add_sequence(g, s)
@@ -231,3 +240,75 @@ def test_device_level_sharded_gather_equals_single_engine():
         e.probe_device(words.data_ptr(), mask.data_ptr(), 0, nk, rows2.data_ptr(), 2, r, st)
     torch.cuda.synchronize()
     assert torch.equal(rows, rows2)
+
+
+def big_case(n_genomes, k, length, seed, repeats=False):
+    """A seeded pan-genome too large for the Python oracle loops but fine for the C oracle."""
+    from panagram_b200 import synth
+    anc = synth.ancestor_codes(length, seed)
+    if repeats:      # skew: long low-complexity stretches hash to a handful of partitions
+        anc[length // 4: length // 2] = np.tile(np.array([0, 1], dtype=np.uint8), length // 8 + 1)[: length // 2 - length // 4]
+        anc[length // 2: length // 2 + length // 8] = 0
+    return [synth.genome_chroms(anc, g, seed, n_chroms=3, n_run=700, lower_run=3000) for g in range(n_genomes)]
+
+
+@pytest.mark.parametrize("n_genomes,k,repeats,load", [(8, 21, False, 0.5), (5, 31, True, 0.8), (40, 25, False, 0.6)])
+def test_partitioned_path_large_vs_oracle_and_direct(n_genomes, k, repeats, load):
+    """>= 1 Mi positions so the auto mode takes the partitioned path; the repeat-rich case overflows
+    partition capacity and exercises the spill list."""
+    length = 2_600_000 if n_genomes <= 8 else 1_300_000
+    genomes = big_case(n_genomes, k, length, 31 + n_genomes, repeats)
+    engs = {m: Engine(k, n_genomes, load_factor=load, probe_mode=m) for m in ("partitioned", "direct")}
+    for g, chroms in enumerate(genomes):
+        for e in engs.values():
+            e.reserve(g, sum(s.size for _, s in chroms))
+            for _, s in chroms:
+                e.add_sequence(g, s)
+    for e in engs.values():
+        e.finalize()
+    anchor_seqs = [s for _, s in genomes[1]]
+    rp = engs["partitioned"].anchor_genome(anchor_seqs)
+    rd = engs["direct"].anchor_genome(anchor_seqs)
+    assert (rp["col_sums"] == rd["col_sums"]).all()
+    for a, b in zip(rp["chroms"], rd["chroms"]):
+        assert a["nkmers"] == b["nkmers"]
+        assert (a["bitmap1"] == b["bitmap1"]).all()
+        assert (a["low"] == b["low"]).all()
+        assert (a["bin_hist"] == b["bin_hist"]).all()
+    # the anchor's own column is set exactly where the window is valid (structural invariant)
+    own = (rp["chroms"][0]["bitmap1"][:, 0] >> 1) & 1
+    seq = anchor_seqs[0]
+    bad = ~np.isin(seq, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+    badwin = np.convolve(bad.astype(np.int32), np.ones(k, dtype=np.int32))[k - 1: seq.size] > 0
+    assert (own == (~badwin).astype(np.uint8)).all()
+    # C oracle on the first chromosome (keys listed from the sequences by the oracle's own code path)
+    kk = {}
+    for g, chroms in enumerate(genomes):
+        for _, s in chroms:
+            codes = np.full(256, 255, dtype=np.uint8)
+            for i, c in enumerate(b"ACGT"):
+                codes[c] = codes[c | 0x20] = i
+            v = codes[s]
+            ok = v < 4
+            okwin = np.convolve((~ok).astype(np.int32), np.ones(k, dtype=np.int32))[k - 1: s.size] == 0
+            f = np.zeros(s.size - k + 1, dtype=np.uint64)
+            r = np.zeros(s.size - k + 1, dtype=np.uint64)
+            vv = np.where(ok, v, 0).astype(np.uint64)
+            for j in range(k):
+                f = (f << np.uint64(2)) | vv[j: j + f.size]
+                r = r | ((np.uint64(3) - vv[j: j + f.size]) << np.uint64(2 * j))
+            can = np.minimum(f, r)[okwin]
+            kk[g] = np.unique(can)
+    allk = np.unique(np.concatenate(list(kk.values())))
+    dbs = []
+    for d in range((n_genomes + 31) // 32):
+        cnt = np.zeros(allk.size, dtype=np.uint32)
+        for g in range(32 * d, min(32 * d + 32, n_genomes)):
+            cnt[np.searchsorted(allk, kk[g])] |= np.uint32(1 << (g - 32 * d))
+        keep = cnt != 0
+        dbs.append(oracle.OracleDB.from_kmers(k, allk[keep], cnt[keep]))
+    for g in range(n_genomes):
+        assert engs["partitioned"].table_stats(g)["n_keys"] == kk[g].size
+    want = oracle.anchor_chrom(dbs, n_genomes, anchor_seqs[0].tobytes())
+    assert (rp["chroms"][0]["bitmap1"] == want["bitmap1"]).all()
+    assert (rp["chroms"][0]["bin_hist"] == want["bin_hist"]).all()
