@@ -41,10 +41,10 @@ def _run(cmd, cwd, log, env=None):
 def kmc_count(root: Path, name: str, fasta: str, idx: int, k: int, threads: int = 1,
               memory: int = 8, fastq: bool = False, timings: dict | None = None):
     """rule kmc_count: kmc (-ci1 -fm | -ci2 -fq) then kmc_tools transform set_counts."""
-    (root / "kmc").mkdir(exist_ok=True)
+    (root / "kmc").mkdir(parents=True, exist_ok=True)
     tmp = root / "tmp" / name
     tmp.mkdir(parents=True, exist_ok=True)
-    (root / "logs").mkdir(exist_ok=True)
+    (root / "logs").mkdir(parents=True, exist_ok=True)
     log = root / "logs" / f"kmc.{name}.txt"
     t0 = time.perf_counter()
     _run([str(REF_DIR / "kmc"), f"-k{k}", f"-t{threads}", f"-m{memory}",

@@ -140,23 +140,34 @@ class Engine:
                    binlen=binlen)
         return res
 
-    def anchor_genome(self, seqs, bitmap1=True, low=True, hist=True, colsums=True, pinned=False) -> dict:
+    def anchor_genome(self, seqs, bitmap1=True, low=True, hist=True, colsums=True, pinned=False,
+                      out: dict | None = None) -> dict:
         """All chromosomes of one anchor in one batch (pk_anchor_genome).
 
         Returns {'chroms': [per-chromosome dicts as anchor_chrom], 'col_sums': [N_local]}.
-        Chromosomes with fewer than min_bin_count k-mers get no histogram.
+        Chromosomes with fewer than min_bin_count k-mers get no histogram. `out` = a previous
+        result for the same chromosome lengths whose (pinned) arrays are reused.
         """
         arrs = [_u8(s) for s in seqs]
         n = len(arrs)
         rb, step = self.row_bytes, self.lowres_step
         alloc = pinned_empty if pinned else (lambda shape, dtype=np.uint8: np.empty(shape, dtype=dtype))
         nks = [max(a.size - self.k + 1, 0) for a in arrs]
-        b1 = [alloc((nk, rb)) if (bitmap1 and nk) else None for nk in nks]
-        lo = [alloc(((nk + step - 1) // step, rb)) if (low and nk) else None for nk in nks]
         bl = [self.bin_len(nk) if nk else 0 for nk in nks]
-        hi = [np.zeros(((nk + b - 1) // b, self.n_local + 1), dtype=np.uint64) if (hist and nk and b) else None
-              for nk, b in zip(nks, bl)]
-        cs = np.zeros(self.n_local, dtype=np.uint64) if colsums else None
+        if out is not None:
+            assert [c["nkmers"] for c in out["chroms"]] == nks, "out= must come from the same chromosome lengths"
+            b1 = [c["bitmap1"] for c in out["chroms"]]
+            lo = [c["low"] for c in out["chroms"]]
+            hi = [c["bin_hist"] for c in out["chroms"]]
+            cs = out["col_sums"]
+            if cs is not None:
+                cs[:] = 0
+        else:
+            b1 = [alloc((nk, rb)) if (bitmap1 and nk) else None for nk in nks]
+            lo = [alloc(((nk + step - 1) // step, rb)) if (low and nk) else None for nk in nks]
+            hi = [np.zeros(((nk + b - 1) // b, self.n_local + 1), dtype=np.uint64) if (hist and nk and b) else None
+                  for nk, b in zip(nks, bl)]
+            cs = np.zeros(self.n_local, dtype=np.uint64) if colsums else None
 
         def ptrs(lst):
             return (C.c_void_p * n)(*[None if x is None else x.ctypes.data for x in lst])

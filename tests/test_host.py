@@ -83,3 +83,27 @@ def test_synth_is_deterministic_and_shaped():
     assert bytes(a[1][1][:100]).islower()
     g0 = synth.genome_codes(anc, 0, 1)
     assert 0.001 < (g0 != anc).mean() < 0.003
+
+
+def test_index_prepare_writes_reference_config_files(pan3, tmp_path):
+    """`panagram index samples.tsv -k 21 --prepare` (index.py:269-295,347-353): samples.tsv with
+    name/fasta/gff/id/anchor and a config.yaml carrying the keys the reference's reader needs."""
+    import yaml
+    from panagram_b200.cli import main
+    tsv = tmp_path / "samples.tsv"
+    tsv.write_text("name\tfasta\n" + "".join(f"{n}\t{p}\n" for n, p in pan3["fasta"].items()))
+    assert main(["index", str(tsv), "-k", "21", "-o", str(tmp_path / "idx"), "--prepare",
+                 "--anchor_genomes", "g0", "g2"]) == 0
+    rows = [l.split("\t") for l in (tmp_path / "idx" / "samples.tsv").read_text().splitlines()]
+    assert rows[0] == ["name", "fasta", "gff", "id", "anchor"]
+    assert [(r[0], r[3], r[4]) for r in rows[1:]] == [("g0", "0", "True"), ("g1", "1", "False"), ("g2", "2", "True")]
+    cfg = yaml.safe_load((tmp_path / "idx" / "config.yaml").read_text())
+    for key in ("k", "lowres_step", "anchor_genomes", "gff_anno_types", "gff_gene_types", "gff_name", "max_bin_kbp",
+                "min_bin_count"):
+        assert key in cfg
+    assert cfg["k"] == 21 and cfg["anchor_genomes"] == ["g0", "g2"]
+    assert not (tmp_path / "idx" / "anchor").exists()
+    bad = tmp_path / "bad.tsv"
+    bad.write_text("name\tfasta\nbad name!\tx.fa\n")
+    with pytest.raises(ValueError):
+        main(["index", str(bad), "--prepare"])
