@@ -194,8 +194,9 @@ int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t n_ranks, u
 typedef struct pk_stats {
     float h2d_ms, pack_ms, probe_ms, reduce_ms, d2h_ms, total_ms;
     /* CUDA-event durations of the kernels of the last partitioned probe launch, on the stream
-     * they ran on: K1 partition_seq, K2 partition_fine, K3 probe_part, K3 over the spill list */
-    float k_partition_ms, k_fine_ms, k_probe_ms, k_spill_ms;
+     * they ran on: K1 partition_seq, K2 partition_fine, K3 probe_part, K3 over the spill list,
+     * K4 unpermute */
+    float k_partition_ms, k_fine_ms, k_probe_ms, k_spill_ms, k_unpermute_ms, _pad;
     uint64_t positions, probes, probe_launches, kernel_launches;
 } pk_stats;
 int pk_engine_stats(const pk_engine *e, pk_stats *out);

@@ -47,7 +47,7 @@ class PkStats(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("probe_ms", C.c_float),
                 ("reduce_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("k_partition_ms", C.c_float), ("k_fine_ms", C.c_float), ("k_probe_ms", C.c_float),
-                ("k_spill_ms", C.c_float),
+                ("k_spill_ms", C.c_float), ("k_unpermute_ms", C.c_float), ("_pad", C.c_float),
                 ("positions", C.c_uint64), ("probes", C.c_uint64), ("probe_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64)]
 

@@ -56,7 +56,8 @@ struct pk_engine {
     uint32_t *g_u32 = nullptr; uint64_t g_u32_cap = 0;
     unsigned long long *d_hist = nullptr;       // per-chromosome bin histograms
     uint64_t hist_cap = 0;
-    cudaEvent_t pev[5] = {};                    // around K1 / K2 / K3 / spill of the last partitioned launch
+    cudaEvent_t pev[6] = {};                    // around K1 / K2 / K3 / spill / K4 of the last partitioned launch
+    int unpermute = 1;
     bool pev_valid = false;
     PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
     PkPartPlan sc_plan{};
@@ -125,6 +126,8 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (e->cfg.load_factor == 0.f) e->cfg.load_factor = 0.5f;
     if (e->cfg.probe_mode > 2) { pk_set_error("probe_mode %u out of range", e->cfg.probe_mode); return PK_EINVAL; }
     if (const char *pf = getenv("PK_L2_PREFETCH")) e->l2_prefetch = atoi(pf);
+    if (const char *up = getenv("PK_UNPERMUTE")) e->unpermute = atoi(up);
+    if (const char *kv = getenv("PK_K3_VARIANT")) pk_part_set_variant(atoi(kv));
     e->n_local = cfg->genome_end - cfg->genome_begin;
     e->row_bytes = (e->n_local + 7) / 8;
     e->tabs.resize(e->n_local);
@@ -416,14 +419,18 @@ extern "C" int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t
 static void free_scratch(pk_engine *e) {
     cudaFree(e->sc.buf1); cudaFree(e->sc.buf2); cudaFree(e->sc.spill);
     cudaFree(e->sc.cursor1); cudaFree(e->sc.cursor2); cudaFree(e->sc.spill_cursor); cudaFree(e->sc.err);
+    cudaFree(e->sc.out_list); cudaFree(e->sc.out_cursor);
     e->sc = PkPartScratch{};
     e->sc_plan = PkPartPlan{};
 }
 
 static int ensure_scratch(pk_engine *e, const PkPartPlan &pl) {
     const PkPartPlan &have = e->sc_plan;
+    const uint32_t n_groups = (e->n_local + 31) / 32;
+    const uint64_t out_items = e->unpermute ? (uint64_t)n_groups * pk_part_obins() << pl.out_shift : 0;
     if (e->sc.buf1 && have.buf1_items >= pl.buf1_items && have.buf2_items >= pl.buf2_items &&
-        have.spill_items >= pl.spill_items && have.n_regions1 >= pl.n_regions1 && have.n_regions2 >= pl.n_regions2)
+        have.spill_items >= pl.spill_items && have.n_regions1 >= pl.n_regions1 && have.n_regions2 >= pl.n_regions2 &&
+        e->sc.out_items >= out_items)
         return PK_OK;
     CU(cudaDeviceSynchronize());
     free_scratch(e);
@@ -435,6 +442,11 @@ static int ensure_scratch(pk_engine *e, const PkPartPlan &pl) {
     CU(cudaMalloc(&e->sc.spill_cursor, sizeof(unsigned long long)));
     CU(cudaMalloc(&e->sc.err, sizeof(uint32_t)));
     CU(cudaMemset(e->sc.err, 0, sizeof(uint32_t)));
+    if (out_items) {
+        CU(cudaMalloc(&e->sc.out_list, out_items * 8));
+        CU(cudaMalloc(&e->sc.out_cursor, sizeof(uint32_t) * n_groups * pk_part_obins()));
+    }
+    e->sc.out_items = out_items;
     e->sc_plan = pl;
     return PK_OK;
 }
@@ -456,7 +468,7 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
                 pk_set_error("partitioned probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return PK_ECUDA;
             }
-            e->stats.kernel_launches += 3 + (pl.pb2 ? 1 : 0);
+            e->stats.kernel_launches += 3 + (pl.pb2 ? 1 : 0) + (e->unpermute ? 1 : 0);
             e->stats.probe_launches += 1;
             e->pev_valid = true;
         } else {
@@ -652,9 +664,10 @@ extern "C" int pk_get_counters_for_read(pk_engine *e, uint32_t dbi, const char *
 extern "C" int pk_engine_stats(const pk_engine *e, pk_stats *out) {
     if (!e || !out) { pk_set_error("null argument"); return PK_EINVAL; }
     *out = e->stats;
-    out->k_partition_ms = out->k_fine_ms = out->k_probe_ms = out->k_spill_ms = 0.f;
+    out->k_partition_ms = out->k_fine_ms = out->k_probe_ms = out->k_spill_ms = out->k_unpermute_ms = 0.f;
     if (e->pev_valid) {      // kernels of the last partitioned launch, timed on their own stream
-        CU(cudaEventSynchronize(e->pev[4]));
+        CU(cudaEventSynchronize(e->pev[5]));
+        CU(cudaEventElapsedTime(&out->k_unpermute_ms, e->pev[4], e->pev[5]));
         CU(cudaEventElapsedTime(&out->k_partition_ms, e->pev[0], e->pev[1]));
         CU(cudaEventElapsedTime(&out->k_fine_ms, e->pev[1], e->pev[2]));
         CU(cudaEventElapsedTime(&out->k_probe_ms, e->pev[2], e->pev[3]));

@@ -77,16 +77,22 @@ void pk_launch_table_overflow_count(PkTable t, unsigned long long *d_out, pk_str
 struct PkPartPlan {
     uint32_t pb1, pb2, cap1, cap2, n_regions1, n_regions2;
     uint64_t buf1_items, buf2_items, spill_items;   // 8-byte (hash, pos) items
+    uint32_t out_shift, out_bins;                   // un-permute lists: out_bins bins of 2^out_shift positions
 };
 struct PkPartScratch {
     void *buf1, *buf2, *spill;
     uint32_t *cursor1, *cursor2;
     unsigned long long *spill_cursor;
     uint32_t *err;
+    void *out_list;                                 // NULL: probe_part scatters row bytes itself
+    uint32_t *out_cursor;
+    uint64_t out_items;
 };
+uint32_t pk_part_obins(void);
+void pk_part_set_variant(int v);
 void pk_part_plan(uint64_t n, PkPartPlan *pl);
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
                                 const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                                 uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, int prefetch,
-                                pk_stream_t s, struct CUevent_st **evs /*5 events or NULL*/);
+                                pk_stream_t s, struct CUevent_st **evs /*6 events or NULL*/);
 #endif

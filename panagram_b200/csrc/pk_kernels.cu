@@ -284,39 +284,41 @@ void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p
 // rows: n full rows (n_cols bit columns, ceil(n_cols/8) bytes used of row_stride). For chromosome
 // position p = p_first + i:  hist[(p / binlen) * (n_cols+1) + popcount(row)]++ ; col_sums[g] += bit g ;
 // rows_low[(p/step - ceil(p_first/step))] = row  when p % step == 0.
-#define PK_RED_ITEMS 8
+#define PK_RED_ITEMS 16
+// IDX = uint32_t when every position fits 32 bits (the common case: 32-bit divides), else uint64_t.
+template <typename IDX>
 __global__ void __launch_bounds__(256) reduce_kernel(const uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t n_cols,
-                                                     uint64_t p_first, uint64_t n, uint64_t binlen,
-                                                     unsigned long long *__restrict__ hist, unsigned long long *__restrict__ col_sums,
-                                                     uint8_t *__restrict__ rows_low, uint32_t step) {
+                                                     uint64_t p_first64, uint64_t n64, uint64_t binlen64,
+                                                     unsigned long long *__restrict__ hist, unsigned long long *__restrict__ col_sums) {
     extern __shared__ unsigned int sh[];
     const uint32_t n_words = (n_cols + 31) / 32, nbytes = (n_cols + 7) / 8;
     unsigned int *sh_hist = sh;                    // [n_cols + 1]
     unsigned int *sh_col = sh + n_cols + 1;        // [n_words * 32]
     for (uint32_t q = threadIdx.x; q < n_cols + 1 + n_words * 32; q += blockDim.x) sh[q] = 0;
     __syncthreads();
-    const uint64_t base = blockIdx.x * (uint64_t)(256 * PK_RED_ITEMS);
-    const uint64_t bin0 = binlen ? (p_first + base) / binlen : 0;
-    const uint64_t low0 = step ? (p_first + step - 1) / step : 0;
+    const IDX p_first = (IDX)p_first64, n = (IDX)n64, binlen = (IDX)binlen64;
+    const IDX base = (IDX)blockIdx.x * (IDX)(256 * PK_RED_ITEMS);
+    const IDX bin0 = binlen ? (p_first + base) / binlen : 0;
     const uint32_t lane = threadIdx.x & 31;
+    const bool vec1 = nbytes == 1 && row_stride == 1;
     for (int it = 0; it < PK_RED_ITEMS; it++) {
-        const uint64_t i = base + (uint64_t)it * 256 + threadIdx.x;
-        if (base + (uint64_t)it * 256 + (threadIdx.x & ~31u) >= n) break;   // whole warp out of range (warp-uniform)
+        if (base + (IDX)it * 256 + (threadIdx.x & ~31u) >= n) break;   // whole warp out of range (warp-uniform)
+        const IDX i = base + (IDX)it * 256 + threadIdx.x;
         const bool active = i < n;
-        const uint64_t p = p_first + i;
-        const uint8_t *row = rows + i * row_stride;
+        const uint8_t *row = rows + (uint64_t)i * row_stride;
         uint32_t pc = 0;
         for (uint32_t wd = 0; wd < n_words; wd++) {
             uint32_t w = 0;
             if (active) {
-                for (uint32_t b = 0; b < 4 && 4 * wd + b < nbytes; b++) w |= (uint32_t)row[4 * wd + b] << (8 * b);
+                if (vec1) w = row[0];
+                else for (uint32_t b = 0; b < 4 && 4 * wd + b < nbytes; b++) w |= (uint32_t)row[4 * wd + b] << (8 * b);
                 if (wd == n_words - 1 && (n_cols & 31)) w &= (1u << (n_cols & 31)) - 1;
             }
             pc += __popc(w);
             if (col_sums) {
+                const uint32_t nbits = min(32u, n_cols - 32 * wd);
                 uint32_t mine = 0;
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
+                for (uint32_t j = 0; j < nbits; j++) {
                     const uint32_t m = __ballot_sync(0xffffffffu, (w >> j) & 1);
                     if (lane == j) mine = __popc(m);
                 }
@@ -324,36 +326,55 @@ __global__ void __launch_bounds__(256) reduce_kernel(const uint8_t *__restrict__
             }
         }
         if (hist && binlen) {
-            const uint64_t bin = p / binlen;
-            const uint32_t key = active ? (uint32_t)((bin - bin0) << 16 | pc) : 0xffffffffu;   // a block spans <= 2048 positions, so bin - bin0 < 2^16
+            const IDX bin = (p_first + i) / binlen;
+            const uint32_t key = active ? (uint32_t)((bin - bin0) << 16 | pc) : 0xffffffffu;   // a block spans <= 4096 positions, so bin - bin0 < 2^16
             const uint32_t peers = __match_any_sync(0xffffffffu, key);
             if (active && lane == (uint32_t)(__ffs(peers) - 1)) {
                 const uint32_t cnt = __popc(peers);
                 if (bin == bin0) atomicAdd(&sh_hist[pc], cnt);
-                else atomicAdd(&hist[bin * (n_cols + 1) + pc], (unsigned long long)cnt);
+                else atomicAdd(&hist[(uint64_t)bin * (n_cols + 1) + pc], (unsigned long long)cnt);
             }
-        }
-        if (rows_low && active && p % step == 0) {
-            uint8_t *d = rows_low + (p / step - low0) * row_stride;
-            for (uint32_t b = 0; b < nbytes; b++) d[b] = row[b];
         }
     }
     __syncthreads();
     if (hist && binlen)
         for (uint32_t q = threadIdx.x; q < n_cols + 1; q += blockDim.x)
-            if (sh_hist[q]) atomicAdd(&hist[bin0 * (n_cols + 1) + q], (unsigned long long)sh_hist[q]);
+            if (sh_hist[q]) atomicAdd(&hist[(uint64_t)bin0 * (n_cols + 1) + q], (unsigned long long)sh_hist[q]);
     if (col_sums)
         for (uint32_t q = threadIdx.x; q < n_cols; q += blockDim.x)
             if (sh_col[q]) atomicAdd(&col_sums[q], (unsigned long long)sh_col[q]);
 }
+
+// low-res rows: rows_low[l - l0] = rows[l * step - p_first] for l in [l0, l1), l0 = ceil(p_first/step)
+__global__ void __launch_bounds__(256) lowres_kernel(const uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t nbytes,
+                                                     uint64_t p_first, uint64_t l0, uint64_t n_low, uint32_t step,
+                                                     uint8_t *__restrict__ rows_low) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n_low; q += stride) {
+        const uint8_t *src = rows + ((l0 + q) * step - p_first) * row_stride;
+        uint8_t *dst = rows_low + q * row_stride;
+        for (uint32_t b = 0; b < nbytes; b++) dst[b] = src[b];
+    }
+}
+
 void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
                       uint64_t binlen, unsigned long long *d_bin_hist, unsigned long long *d_col_sums,
                       uint8_t *d_rows_low, uint32_t step, pk_stream_t s) {
     if (!n) return;
-    const uint32_t n_words = (n_cols + 31) / 32;
-    const size_t shmem = (size_t)(n_cols + 1 + n_words * 32) * sizeof(unsigned int);
-    const unsigned grid = (unsigned)((n + 256 * PK_RED_ITEMS - 1) / (256 * PK_RED_ITEMS));
-    reduce_kernel<<<grid, 256, shmem, s>>>(d_rows, row_stride, n_cols, p_first, n, binlen, d_bin_hist, d_col_sums, d_rows_low, step);
+    if (d_bin_hist || d_col_sums) {
+        const uint32_t n_words = (n_cols + 31) / 32;
+        const size_t shmem = (size_t)(n_cols + 1 + n_words * 32) * sizeof(unsigned int);
+        const unsigned grid = (unsigned)((n + 256 * PK_RED_ITEMS - 1) / (256 * PK_RED_ITEMS));
+        if (p_first + n < (1ull << 32) && binlen < (1ull << 32))
+            reduce_kernel<uint32_t><<<grid, 256, shmem, s>>>(d_rows, row_stride, n_cols, p_first, n, binlen, d_bin_hist, d_col_sums);
+        else
+            reduce_kernel<uint64_t><<<grid, 256, shmem, s>>>(d_rows, row_stride, n_cols, p_first, n, binlen, d_bin_hist, d_col_sums);
+    }
+    if (d_rows_low) {
+        const uint64_t l0 = (p_first + step - 1) / step, l1 = (p_first + n + step - 1) / step;
+        if (l1 > l0)
+            lowres_kernel<<<grid_for(l1 - l0), 256, 0, s>>>(d_rows, row_stride, (n_cols + 7) / 8, p_first, l0, l1 - l0, step, d_rows_low);
+    }
 }
 
 // ------------------------------------------------------------------ interleave / unpack

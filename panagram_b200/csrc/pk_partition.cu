@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(PT_THREADS) partition_fine_kernel(PartArgs a) 
 #define PP_CAP 3072                       // items per fine partition (shared memory: 16 B each)
 #define PP_IPT (PP_CAP / PP_THREADS)      // 12
 #define PP_ILP 4
+#define PP_OBINS 128                      // position bins of the un-permute lists
+#define PP_WARPS (PP_THREADS / 32)
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -211,6 +213,12 @@ struct ProbeArgs {
     uint8_t *rows;
     uint32_t row_stride, col_offset, nbl;
     int prefetch;
+    // un-permute: instead of scattering row bytes over the whole bitmap (32x write amplification and a
+    // read-modify-write per byte in DRAM), results are appended as (pos, bits) to lists binned by
+    // pos >> out_shift; unpermute_kernel then scatters each list inside its own L2-resident slice
+    uint2 *out_list;                  // [(grp * PP_OBINS + bin) << out_shift]
+    uint32_t *out_cursor;             // [n_groups * PP_OBINS]
+    uint32_t out_shift;
 };
 
 __device__ __noinline__ bool pk_probe_slow_ca(const PkTable t, unsigned long long key, uint32_t b) {
@@ -223,12 +231,14 @@ __device__ __noinline__ bool pk_probe_slow_ca(const PkTable t, unsigned long lon
     return false;
 }
 
-__global__ void __launch_bounds__(PP_THREADS) probe_part_kernel(ProbeArgs a) {
+__global__ void __launch_bounds__(PP_THREADS, 3) probe_part_kernel(ProbeArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t *s_canon = (uint64_t *)smem_raw;                    // [PP_CAP]
     uint32_t *s_h = (uint32_t *)(s_canon + PP_CAP);              // [PP_CAP]
     uint32_t *s_pos = s_h + PP_CAP;                              // [PP_CAP]
-    const uint32_t tid = threadIdx.x;
+    __shared__ uint16_t o_wc[PP_WARPS][PP_OBINS];
+    __shared__ uint32_t o_gb[PP_OBINS];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint64_t nreg = a.n_regions;
     unsigned long long flat = 0;
     if (!a.counts) { flat = *a.flat_total; nreg = (flat + a.cap - 1) / a.cap; }
@@ -297,15 +307,61 @@ __global__ void __launch_bounds__(PP_THREADS) probe_part_kernel(ProbeArgs a) {
                     }
                 }
             }
-            const uint32_t nb = min(4u, a.nbl - g0 / 8);
-            const bool al4 = nb == 4 && ((a.row_stride | a.col_offset) & 3) == 0;
+            if (a.out_list) {
+                // append (pos, bits) to the list of bin = pos >> out_shift: rank inside the block by
+                // warp match, one atomicAdd per (block, bin) reserves the run
+                for (uint32_t q = tid; q < PP_WARPS * PP_OBINS; q += PP_THREADS) (&o_wc[0][0])[q] = 0;
+                __syncthreads();
+                uint16_t rank[PP_IPT];
 #pragma unroll
-            for (int j = 0; j < PP_IPT; j++) {
-                const uint32_t i = tid + j * PP_THREADS;
-                if (i < cnt) {
-                    uint8_t *dst = a.rows + (uint64_t)s_pos[i] * a.row_stride + a.col_offset + g0 / 8;
-                    if (al4) *(uint32_t *)dst = bits[j];
-                    else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(bits[j] >> (8 * qb));
+                for (int j = 0; j < PP_IPT; j++) {
+                    const uint32_t i = tid + j * PP_THREADS;
+                    const bool v = i < cnt;
+                    const uint32_t bin = v ? s_pos[i] >> a.out_shift : 0xffffffffu;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                    const uint32_t leader = __ffs(peers) - 1;
+                    uint32_t old = 0;
+                    if (v && lane == leader) {
+                        old = o_wc[wid][bin];
+                        o_wc[wid][bin] = (uint16_t)(old + __popc(peers));
+                    }
+                    old = __shfl_sync(0xffffffffu, old, leader);
+                    rank[j] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
+                    __syncwarp();
+                }
+                __syncthreads();
+                for (uint32_t b = tid; b < PP_OBINS; b += PP_THREADS) {
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int ww = 0; ww < PP_WARPS; ww++) {
+                        const uint32_t t = o_wc[ww][b];
+                        o_wc[ww][b] = (uint16_t)run;
+                        run += t;
+                    }
+                    if (run) o_gb[b] = atomicAdd(&a.out_cursor[(g0 / 32) * PP_OBINS + b], run);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < PP_IPT; j++) {
+                    const uint32_t i = tid + j * PP_THREADS;
+                    if (i < cnt) {
+                        const uint32_t pos = s_pos[i], bin = pos >> a.out_shift;
+                        const uint64_t slot = (((uint64_t)(g0 / 32) * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + o_wc[wid][bin] + rank[j];
+                        a.out_list[slot] = make_uint2(pos, bits[j]);
+                    }
+                }
+                __syncthreads();
+            } else {
+                const uint32_t nb = min(4u, a.nbl - g0 / 8);
+                const bool al4 = nb == 4 && ((a.row_stride | a.col_offset) & 3) == 0;
+#pragma unroll
+                for (int j = 0; j < PP_IPT; j++) {
+                    const uint32_t i = tid + j * PP_THREADS;
+                    if (i < cnt) {
+                        uint8_t *dst = a.rows + (uint64_t)s_pos[i] * a.row_stride + a.col_offset + g0 / 8;
+                        if (al4) *(uint32_t *)dst = bits[j];
+                        else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(bits[j] >> (8 * qb));
+                    }
                 }
             }
         }
@@ -313,24 +369,229 @@ __global__ void __launch_bounds__(PP_THREADS) probe_part_kernel(ProbeArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ K3, item-major variant
+// One item per thread at a time, GILP genomes in flight for it: a block's round trips to memory drop
+// from (genomes x rounds) to (items-per-thread x genome-groups); the walk-on to the next bucket is
+// batched over the GILP genomes instead of serialised. Partitions are smaller (<= T*IPT items) so that
+// the GILP windows a block has live stay small (8 KB each at 2^18 partitions of a 2 GB table).
+template <int T, int IPT, int GILP, int MINB>
+__global__ void __launch_bounds__(T, MINB) probe_item_kernel(ProbeArgs a) {
+    __shared__ uint16_t o_wc[T / 32][PP_OBINS];
+    __shared__ uint32_t o_gb[PP_OBINS];
+    __shared__ PkTable s_tb[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint64_t nreg = a.n_regions;
+    unsigned long long flat = 0;
+    if (!a.counts) { flat = *a.flat_total; nreg = (flat + a.cap - 1) / a.cap; }
+    for (uint64_t q = blockIdx.x; q < nreg; q += gridDim.x) {
+        uint32_t cnt;
+        if (a.counts) cnt = min(a.counts[q], a.cap);
+        else cnt = (uint32_t)min((unsigned long long)a.cap, flat - q * a.cap);
+        if (cnt == 0) continue;
+        const bool do_pf = a.prefetch && a.counts && a.pb;
+        const uint32_t h_lo = do_pf ? (uint32_t)(q << (32 - a.pb)) : 0;
+        const uint32_t h_hi = do_pf ? (uint32_t)(((q + 1) << (32 - a.pb)) - 1) : 0;
+        if (do_pf && tid < min((uint32_t)GILP, a.n_local)) {
+            const PkTable t = a.tables[tid];
+            const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
+            if (b1 - b0 < 8192) l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
+        }
+        const uint2 *src = a.buf + q * (uint64_t)a.cap;
+        uint64_t canon[IPT];
+        uint32_t h[IPT], pos[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const uint32_t i = tid + j * T;
+            canon[j] = 0; h[j] = 0; pos[j] = 0;
+            if (i < cnt) {
+                const uint2 it = src[i];
+                const uint64_t p = a.p0 + it.y;
+                const uint64_t w0 = a.words[p >> 5], w1 = a.words[(p >> 5) + 1];
+                const uint32_t s = 2 * ((uint32_t)p & 31);
+                const uint64_t x = (w0 << s) | ((w1 >> 1) >> (63 - s));
+                const uint64_t fwd = x >> (64 - 2 * a.k);
+                const uint64_t rc = pk_revcomp(fwd, a.k);
+                canon[j] = fwd < rc ? fwd : rc;
+                h[j] = it.x; pos[j] = it.y;
+            }
+        }
+        for (uint32_t g0 = 0; g0 < a.n_local; g0 += 32) {
+            uint32_t bits[IPT];
+#pragma unroll
+            for (int j = 0; j < IPT; j++) bits[j] = 0;
+            const uint32_t ng = min(32u, a.n_local - g0);
+            __syncthreads();
+            if (tid < 32) s_tb[tid] = a.tables[min(g0 + tid, a.n_local - 1)];
+            __syncthreads();
+            for (uint32_t gs = 0; gs < ng; gs += GILP) {
+                if (do_pf && tid < GILP && g0 + gs + GILP + tid < a.n_local) {      // next group's windows
+                    const PkTable t = a.tables[g0 + gs + GILP + tid];
+                    const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
+                    if (b1 - b0 < 8192) l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
+                }
+                const PkTable *tb = s_tb + gs;            // descriptors stay in shared memory (uniform LDS)
+                const uint32_t nu = min((uint32_t)GILP, ng - gs);
+#pragma unroll
+                for (int j = 0; j < IPT; j++) {
+                    if (tid + j * T < cnt) {
+                        u64x4 v[GILP];
+                        uint32_t need = 0;
+                        const uint64_t key = canon[j];
+#pragma unroll
+                        for (int u = 0; u < GILP; u++) {
+                            if ((uint32_t)u < nu)
+                                v[u] = pk_ld_bucket_ca(tb[u].slots + 4ull * __umulhi(h[j], tb[u].n_buckets));
+                        }
+#pragma unroll
+                        for (int u = 0; u < GILP; u++) {
+                            if ((uint32_t)u < nu) {
+                                const bool hit = v[u].a == key || v[u].b == key || v[u].c == key || v[u].d == key;
+                                const bool full = v[u].a != PK_EMPTY && v[u].b != PK_EMPTY && v[u].c != PK_EMPTY && v[u].d != PK_EMPTY;
+                                bits[j] |= (uint32_t)hit << (gs + u);
+                                need |= (uint32_t)(!hit && full) << u;
+                            }
+                        }
+                        for (uint32_t r = 1; need && r < 0xffffffu; r++) {       // batched walk-on (rare)
+#pragma unroll
+                            for (int u = 0; u < GILP; u++) {
+                                if ((need >> u) & 1) {
+                                    const uint32_t nbk = tb[u].n_buckets;
+                                    uint32_t bb = __umulhi(h[j], nbk) + r % nbk;
+                                    if (bb >= nbk) bb -= nbk;
+                                    v[u] = pk_ld_bucket_ca(tb[u].slots + 4ull * bb);
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < GILP; u++) {
+                                if ((need >> u) & 1) {
+                                    const bool hit = v[u].a == key || v[u].b == key || v[u].c == key || v[u].d == key;
+                                    const bool full = v[u].a != PK_EMPTY && v[u].b != PK_EMPTY && v[u].c != PK_EMPTY && v[u].d != PK_EMPTY;
+                                    bits[j] |= (uint32_t)hit << (gs + u);
+                                    if (hit || !full || r >= tb[u].n_buckets) need &= ~(1u << u);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (a.out_list) {
+                for (uint32_t qq = tid; qq < (T / 32) * PP_OBINS; qq += T) (&o_wc[0][0])[qq] = 0;
+                __syncthreads();
+                uint16_t rank[IPT];
+#pragma unroll
+                for (int j = 0; j < IPT; j++) {
+                    const bool v = tid + j * T < cnt;
+                    const uint32_t bin = v ? pos[j] >> a.out_shift : 0xffffffffu;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                    const uint32_t leader = __ffs(peers) - 1;
+                    uint32_t old = 0;
+                    if (v && lane == leader) {
+                        old = o_wc[wid][bin];
+                        o_wc[wid][bin] = (uint16_t)(old + __popc(peers));
+                    }
+                    old = __shfl_sync(0xffffffffu, old, leader);
+                    rank[j] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
+                    __syncwarp();
+                }
+                __syncthreads();
+                for (uint32_t b = tid; b < PP_OBINS; b += T) {
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int ww = 0; ww < T / 32; ww++) {
+                        const uint32_t t = o_wc[ww][b];
+                        o_wc[ww][b] = (uint16_t)run;
+                        run += t;
+                    }
+                    if (run) o_gb[b] = atomicAdd(&a.out_cursor[(g0 / 32) * PP_OBINS + b], run);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < IPT; j++) {
+                    if (tid + j * T < cnt) {
+                        const uint32_t bin = pos[j] >> a.out_shift;
+                        const uint64_t slot = (((uint64_t)(g0 / 32) * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + o_wc[wid][bin] + rank[j];
+                        a.out_list[slot] = make_uint2(pos[j], bits[j]);
+                    }
+                }
+                __syncthreads();
+            } else {
+                const uint32_t nb = min(4u, a.nbl - g0 / 8);
+                const bool al4 = nb == 4 && ((a.row_stride | a.col_offset) & 3) == 0;
+#pragma unroll
+                for (int j = 0; j < IPT; j++) {
+                    if (tid + j * T < cnt) {
+                        uint8_t *dst = a.rows + (uint64_t)pos[j] * a.row_stride + a.col_offset + g0 / 8;
+                        if (al4) *(uint32_t *)dst = bits[j];
+                        else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(bits[j] >> (8 * qb));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// variants of K3 selectable at run time (PK_K3_VARIANT) while the design is being tuned
+struct K3Variant { int threads, cap; size_t shmem; void (*fn)(ProbeArgs); };
+static const K3Variant k3_variants[] = {
+    {PP_THREADS, PP_CAP, (size_t)PP_CAP * 16, probe_part_kernel},          // 0: genome-sequential, items in smem
+    {256, 768, 0, probe_item_kernel<256, 3, 8, 2>},                         // 1
+    {256, 768, 0, probe_item_kernel<256, 3, 8, 3>},                         // 2
+    {256, 768, 0, probe_item_kernel<256, 3, 4, 4>},                         // 3
+    {128, 768, 0, probe_item_kernel<128, 6, 4, 8>},                         // 4
+    {512, 1536, 0, probe_item_kernel<512, 3, 4, 2>},                        // 5
+    {256, 1536, 0, probe_item_kernel<256, 6, 4, 4>},                        // 6
+    {256, 768, 0, probe_item_kernel<256, 3, 2, 5>},                         // 7
+};
+static int g_k3_variant = 7;
+void pk_part_set_variant(int v) { if (v >= 0 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
+
+// K4: scatter the (pos, bits) lists into rows. All blocks of one bin write inside a slice of
+// 2^out_shift rows, which stays in L2 until its sectors are complete.
+#define UP_TILE 4096
+__global__ void __launch_bounds__(256) unpermute_kernel(const uint2 *__restrict__ list, const uint32_t *__restrict__ cursor,
+                                                        uint32_t out_shift, uint8_t *__restrict__ rows, uint32_t row_stride,
+                                                        uint32_t col_offset, uint32_t nbl) {
+    const uint32_t bin = blockIdx.y, grp = blockIdx.z;
+    const uint32_t cnt = cursor[grp * PP_OBINS + bin];
+    const uint32_t t0 = blockIdx.x * UP_TILE;
+    if (t0 >= cnt) return;
+    const uint2 *src = list + (((uint64_t)grp * PP_OBINS + bin) << out_shift);
+    const uint32_t nb = min(4u, nbl - 4 * grp);
+    const bool al4 = nb == 4 && ((row_stride | col_offset) & 3) == 0;
+    const uint32_t t1 = min(cnt, t0 + UP_TILE);
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += 256) {
+        const uint2 e = src[i];
+        uint8_t *dst = rows + (uint64_t)e.x * row_stride + col_offset + 4 * grp;
+        if (al4) *(uint32_t *)dst = e.y;
+        else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(e.y >> (8 * qb));
+    }
+}
+
 // ------------------------------------------------------------------ host orchestration
 static uint32_t ceil_log2(uint64_t v) { uint32_t b = 0; while ((1ull << b) < v) b++; return b; }
 
 void pk_part_plan(uint64_t n, PkPartPlan *pl) {
-    // mean fill <= 2560 of PP_CAP = 3072 (>= 20% head-room for the Poisson spread)
-    uint32_t pb = ceil_log2((n + 2559) / 2560);
+    // mean fill <= 5/6 of the K3 block capacity (>= 20% head-room for the Poisson spread)
+    const uint32_t cap = (uint32_t)k3_variants[g_k3_variant].cap;
+    const uint64_t fill = (uint64_t)cap * 5 / 6;
+    uint32_t pb = ceil_log2((n + fill - 1) / fill);
     if (pb > 18) pb = 18;
     if (pb < 1) pb = 1;
     pl->pb1 = pb > 9 ? 9 : pb;
     pl->pb2 = pb - pl->pb1;
-    pl->cap2 = PP_CAP;
-    pl->cap1 = pl->pb2 ? PP_CAP << pl->pb2 : PP_CAP;
+    pl->cap2 = cap;
+    pl->cap1 = pl->pb2 ? cap << pl->pb2 : cap;
     pl->n_regions1 = 1u << pl->pb1;
     pl->n_regions2 = pl->pb2 ? 1u << pb : 0;
     pl->buf1_items = (uint64_t)pl->n_regions1 * pl->cap1;
     pl->buf2_items = (uint64_t)pl->n_regions2 * pl->cap2;
     pl->spill_items = n;
+    // un-permute lists: <= PP_OBINS bins of 2^out_shift positions, one set per group of 32 genomes
+    pl->out_shift = ceil_log2((n + PP_OBINS - 1) / PP_OBINS);
+    if (pl->out_shift < 8) pl->out_shift = 8;
+    pl->out_bins = (uint32_t)((n + (1ull << pl->out_shift) - 1) >> pl->out_shift);
 }
+uint32_t pk_part_obins(void) { return PP_OBINS; }
 
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
                                 const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
@@ -338,14 +599,18 @@ int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask,
                                 pk_stream_t s, cudaEvent_t *evs) {
     if (!n) return 0;
     static bool attr_set = false;
-    const size_t shmem = (size_t)PP_CAP * 16;
+    const K3Variant &kv = k3_variants[g_k3_variant];
+    const size_t shmem = kv.shmem;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(probe_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(probe_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)PP_CAP * 16)) != cudaSuccess) return -1;
         attr_set = true;
     }
     cudaMemsetAsync(sc.cursor1, 0, sizeof(uint32_t) * pl.n_regions1, s);
     if (pl.n_regions2) cudaMemsetAsync(sc.cursor2, 0, sizeof(uint32_t) * pl.n_regions2, s);
     cudaMemsetAsync(sc.spill_cursor, 0, sizeof(unsigned long long), s);
+    const uint32_t n_groups = (n_local + 31) / 32;
+    const bool unperm = sc.out_list != nullptr;
+    if (unperm) cudaMemsetAsync(sc.out_cursor, 0, sizeof(uint32_t) * n_groups * PP_OBINS, s);
     PartArgs a{};
     a.words = d_words; a.mask64 = (const uint64_t *)d_mask; a.p0 = p0; a.n = n; a.k = k;
     a.pb1 = pl.pb1; a.pb2 = pl.pb2; a.cap1 = pl.cap1; a.cap2 = pl.cap2;
@@ -369,12 +634,21 @@ int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask,
     p.words = d_words; p.p0 = p0; p.k = k; p.tables = d_tables; p.n_local = n_local;
     p.rows = d_rows; p.row_stride = row_stride; p.col_offset = col_offset; p.nbl = a.nbl;
     p.prefetch = prefetch;
+    p.out_list = unperm ? (uint2 *)sc.out_list : nullptr;
+    p.out_cursor = sc.out_cursor;
+    p.out_shift = pl.out_shift;
     if (evs) cudaEventRecord(evs[2], s);
-    probe_part_kernel<<<p.n_regions, PP_THREADS, shmem, s>>>(p);
+    kv.fn<<<p.n_regions, kv.threads, shmem, s>>>(p);
     if (evs) cudaEventRecord(evs[3], s);
     ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)
-    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = PP_CAP; sp.pb = 0;
-    probe_part_kernel<<<148 * 2, PP_THREADS, shmem, s>>>(sp);
+    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
+    kv.fn<<<148 * 2, kv.threads, shmem, s>>>(sp);
     if (evs) cudaEventRecord(evs[4], s);
+    if (unperm) {
+        dim3 grid((unsigned)(((1ull << pl.out_shift) + UP_TILE - 1) / UP_TILE), pl.out_bins, n_groups);
+        unpermute_kernel<<<grid, 256, 0, s>>>((const uint2 *)sc.out_list, sc.out_cursor, pl.out_shift, d_rows, row_stride,
+                                              col_offset, a.nbl);
+    }
+    if (evs) cudaEventRecord(evs[5], s);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

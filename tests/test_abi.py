@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes():
     assert C.sizeof(_lib.PkConfig) == 44
     assert C.sizeof(_lib.PkKmcdbInfo) == 56
-    assert C.sizeof(_lib.PkStats) == 72
+    assert C.sizeof(_lib.PkStats) == 80
 
 
 @pytest.mark.parametrize("name", ["kmc_db", "kmc_db_sorted"])
