@@ -42,6 +42,7 @@ struct pk_engine {
     uint32_t n_local = 0, row_bytes = 0;
     std::vector<HostTable> tabs;
     PkTable *d_tables = nullptr;
+    std::vector<PkTable> h_tables;              // host copy of the descriptors (kernel-parameter path)
     unsigned long long *d_counters = nullptr;   // [3 * n_local]
     bool finalized = false;
     cudaStream_t stream = nullptr;              // build stream / default stream for device-level calls
@@ -162,7 +163,8 @@ extern "C" void pk_engine_destroy(pk_engine *e) {
 }
 
 static int upload_tables(pk_engine *e) {
-    std::vector<PkTable> h(e->n_local);
+    std::vector<PkTable> &h = e->h_tables;
+    h.resize(e->n_local);
     for (uint32_t i = 0; i < e->n_local; i++) h[i] = e->tabs[i].dev;
     CU(cudaMemcpyAsync(e->d_tables, h.data(), sizeof(PkTable) * e->n_local, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -463,7 +465,7 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
             PkPartPlan pl;
             pk_part_plan(m, &pl);
             int rc = ensure_scratch(e, pl); if (rc) return rc;
-            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->cfg.k, e->d_tables, e->n_local,
+            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->cfg.k, e->d_tables, e->h_tables.data(), e->n_local,
                                             d_rows + o * row_stride, row_stride, col_offset, pl, e->sc, e->l2_prefetch, s, e->pev)) {
                 pk_set_error("partitioned probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return PK_ECUDA;

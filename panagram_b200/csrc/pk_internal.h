@@ -92,7 +92,7 @@ uint32_t pk_part_obins(void);
 void pk_part_set_variant(int v);
 void pk_part_plan(uint64_t n, PkPartPlan *pl);
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
-                                const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
-                                uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, int prefetch,
-                                pk_stream_t s, struct CUevent_st **evs /*6 events or NULL*/);
+                                const PkTable *d_tables, const PkTable *h_tables, uint32_t n_local, uint8_t *d_rows,
+                                uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
+                                int prefetch, pk_stream_t s, struct CUevent_st **evs /*6 events or NULL*/);
 #endif

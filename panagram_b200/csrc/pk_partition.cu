@@ -49,19 +49,25 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
     for (uint32_t i = tid; i < PT_WARPS * PT_MAXB; i += PT_THREADS) (&S.warp_cnt[0][0])[i] = 0;
     __syncthreads();
     uint16_t rank[PT_IPT];
+    uint32_t peers[PT_IPT];
+    // all MATCH.ANY first (independent, long latency), then the serial per-warp counter updates
+#pragma unroll
+    for (int j = 0; j < PT_IPT; j++) {
+        const bool v = (validmask >> j) & 1;
+        peers[j] = __match_any_sync(0xffffffffu, v ? (h[j] >> shift) & (nb - 1) : 0xffffffffu);
+    }
 #pragma unroll
     for (int j = 0; j < PT_IPT; j++) {
         const bool v = (validmask >> j) & 1;
         const uint32_t d = (h[j] >> shift) & (nb - 1);
-        const uint32_t peers = __match_any_sync(0xffffffffu, v ? d : 0xffffffffu);
-        const uint32_t leader = __ffs(peers) - 1;
+        const uint32_t leader = __ffs(peers[j]) - 1;
         uint32_t old = 0;
         if (v && lane == leader) {
             old = S.warp_cnt[w][d];
-            S.warp_cnt[w][d] = (uint16_t)(old + __popc(peers));
+            S.warp_cnt[w][d] = (uint16_t)(old + __popc(peers[j]));
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        rank[j] = (uint16_t)(old + __popc(peers & lt));
+        rank[j] = (uint16_t)(old + __popc(peers[j] & lt));
         __syncwarp();
     }
     __syncthreads();
@@ -138,7 +144,7 @@ struct PartArgs {
 
 // K1: positions [p0, p0+n) -> (hash, i) pairs (i = position - p0), partitioned by the top pb1 bits.
 // Invalid windows get their all-zero row here and never enter the pipeline.
-__global__ void __launch_bounds__(PT_THREADS) partition_seq_kernel(PartArgs a) {
+__global__ void __launch_bounds__(PT_THREADS, 3) partition_seq_kernel(PartArgs a) {
     __shared__ PartSmem S;
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint64_t base = blockIdx.x * (uint64_t)PT_TILE + (uint64_t)w * (32 * PT_IPT) + lane;
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(PT_THREADS) partition_seq_kernel(PartArgs a) {
 }
 
 // K2: coarse region c = blockIdx.y, tile blockIdx.x of it -> fine regions c * 2^pb2 + next pb2 bits.
-__global__ void __launch_bounds__(PT_THREADS) partition_fine_kernel(PartArgs a) {
+__global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs a) {
     __shared__ PartSmem S;
     const uint32_t c = blockIdx.y;
     const uint32_t cnt = min(a.cursor1[c], a.cap1);
@@ -379,6 +385,11 @@ __global__ void __launch_bounds__(T, MINB) probe_item_kernel(ProbeArgs a) {
     __shared__ uint16_t o_wc[T / 32][PP_OBINS];
     __shared__ uint32_t o_gb[PP_OBINS];
     __shared__ PkTable s_tb[32];
+    constexpr int QCAP = T * IPT;
+    __shared__ uint32_t s_bits[QCAP];              // results of the deferred walk-ons, by item
+    __shared__ unsigned long long q_key[QCAP];     // deferred walk-on queue
+    __shared__ uint32_t q_h[QCAP], q_meta[QCAP];
+    __shared__ uint32_t q_n;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint64_t nreg = a.n_regions;
     unsigned long long flat = 0;
@@ -422,6 +433,8 @@ __global__ void __launch_bounds__(T, MINB) probe_item_kernel(ProbeArgs a) {
             const uint32_t ng = min(32u, a.n_local - g0);
             __syncthreads();
             if (tid < 32) s_tb[tid] = a.tables[min(g0 + tid, a.n_local - 1)];
+            if (tid == 0) q_n = 0;
+            for (uint32_t qq = tid; qq < (uint32_t)QCAP; qq += T) s_bits[qq] = 0;
             __syncthreads();
             for (uint32_t gs = 0; gs < ng; gs += GILP) {
                 if (do_pf && tid < GILP && g0 + gs + GILP + tid < a.n_local) {      // next group's windows
@@ -433,9 +446,9 @@ __global__ void __launch_bounds__(T, MINB) probe_item_kernel(ProbeArgs a) {
                 const uint32_t nu = min((uint32_t)GILP, ng - gs);
 #pragma unroll
                 for (int j = 0; j < IPT; j++) {
-                    if (tid + j * T < cnt) {
+                    const uint32_t i = tid + j * T;
+                    if (i < cnt) {
                         u64x4 v[GILP];
-                        uint32_t need = 0;
                         const uint64_t key = canon[j];
 #pragma unroll
                         for (int u = 0; u < GILP; u++) {
@@ -446,34 +459,53 @@ __global__ void __launch_bounds__(T, MINB) probe_item_kernel(ProbeArgs a) {
                         for (int u = 0; u < GILP; u++) {
                             if ((uint32_t)u < nu) {
                                 const bool hit = v[u].a == key || v[u].b == key || v[u].c == key || v[u].d == key;
-                                const bool full = v[u].a != PK_EMPTY && v[u].b != PK_EMPTY && v[u].c != PK_EMPTY && v[u].d != PK_EMPTY;
                                 bits[j] |= (uint32_t)hit << (gs + u);
-                                need |= (uint32_t)(!hit && full) << u;
-                            }
-                        }
-                        for (uint32_t r = 1; need && r < 0xffffffu; r++) {       // batched walk-on (rare)
-#pragma unroll
-                            for (int u = 0; u < GILP; u++) {
-                                if ((need >> u) & 1) {
-                                    const uint32_t nbk = tb[u].n_buckets;
-                                    uint32_t bb = __umulhi(h[j], nbk) + r % nbk;
-                                    if (bb >= nbk) bb -= nbk;
-                                    v[u] = pk_ld_bucket_ca(tb[u].slots + 4ull * bb);
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < GILP; u++) {
-                                if ((need >> u) & 1) {
-                                    const bool hit = v[u].a == key || v[u].b == key || v[u].c == key || v[u].d == key;
-                                    const bool full = v[u].a != PK_EMPTY && v[u].b != PK_EMPTY && v[u].c != PK_EMPTY && v[u].d != PK_EMPTY;
-                                    bits[j] |= (uint32_t)hit << (gs + u);
-                                    if (hit || !full || r >= tb[u].n_buckets) need &= ~(1u << u);
+                                // slots fill in order, so the bucket is full iff its last slot is taken. A full
+                                // bucket without the key means the key may sit in a later bucket: that rare
+                                // walk-on is queued and resolved densely below instead of diverging here.
+                                if (!hit && v[u].d != PK_EMPTY) {
+                                    const uint32_t slot = atomicAdd(&q_n, 1u);
+                                    if (slot < QCAP) {
+                                        q_key[slot] = key;
+                                        q_h[slot] = h[j];
+                                        q_meta[slot] = (i << 5) | (gs + u);
+                                    } else {            // queue full (pathological): walk here
+                                        const uint32_t nbk = tb[u].n_buckets;
+                                        uint32_t bb = __umulhi(h[j], nbk);
+                                        for (uint32_t r = 1; r < nbk; r++) {
+                                            bb = bb + 1 == nbk ? 0 : bb + 1;
+                                            const u64x4 w = pk_ld_bucket_ca(tb[u].slots + 4ull * bb);
+                                            if (w.a == key || w.b == key || w.c == key || w.d == key) { bits[j] |= 1u << (gs + u); break; }
+                                            if (w.d == PK_EMPTY) break;
+                                        }
+                                    }
                                 }
                             }
                         }
                     }
                 }
             }
+            __syncthreads();
+            {   // deferred walk-ons, one per thread, all lanes busy
+                const uint32_t nq = min(q_n, (uint32_t)QCAP);
+                for (uint32_t e = tid; e < nq; e += T) {
+                    const uint64_t key = q_key[e];
+                    const uint32_t meta = q_meta[e], g = meta & 31;
+                    const PkTable t = s_tb[g];
+                    const uint32_t b0 = __umulhi(q_h[e], t.n_buckets);
+                    uint32_t bb = b0;
+                    for (uint32_t r = 1; r < t.n_buckets; r++) {
+                        bb = bb + 1 == t.n_buckets ? 0 : bb + 1;
+                        const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * bb);
+                        if (v.a == key || v.b == key || v.c == key || v.d == key) { atomicOr(&s_bits[meta >> 5], 1u << g); break; }
+                        if (v.d == PK_EMPTY) break;
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++)
+                if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
             if (a.out_list) {
                 for (uint32_t qq = tid; qq < (T / 32) * PP_OBINS; qq += T) (&o_wc[0][0])[qq] = 0;
                 __syncthreads();
@@ -530,8 +562,232 @@ __global__ void __launch_bounds__(T, MINB) probe_item_kernel(ProbeArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ K3, bucket-sorted variant
+// The L1TEX tag stage handles ~1 sector per clock per SM, and with one 32 B bucket per lane every probe is
+// a sector of its own (profiles/r1_k3_*.md: l1tex 87 % busy). Here the block first counting-sorts its
+// <= T*IPT items by the hash bits just below the partition bits (shared memory), so the 32 lanes of a warp
+// probe ~16 neighbouring buckets: half the tag lookups, more L1 hits, and DRAM sees 512 B runs.
+// One launch covers one group of <= 32 genomes whose table descriptors travel as kernel parameters
+// (constant bank: no LDS/LDG per probe).
+struct ProbeArgs2 {
+    const uint2 *buf;
+    const uint32_t *counts;
+    const unsigned long long *flat_total;
+    uint32_t cap, n_regions, pb;
+    const uint64_t *words;
+    uint64_t p0;
+    uint32_t k, ng, grp;
+    uint8_t *rows;
+    uint32_t row_stride, col_offset, nbl;
+    int prefetch;
+    uint2 *out_list;
+    uint32_t *out_cursor;
+    uint32_t out_shift;
+    PkTable tabs[32];
+};
+
+#define PS_BINS 1024
+template <int T, int IPT, int MINB>
+__global__ void __launch_bounds__(T, MINB) probe_sorted_kernel(const __grid_constant__ ProbeArgs2 a) {
+    constexpr int CAP = T * IPT;
+    __shared__ unsigned long long s_canon[CAP];
+    __shared__ uint32_t s_h[CAP], s_pos[CAP], s_bits[CAP];
+    __shared__ uint32_t s_cnt[PS_BINS];
+    __shared__ unsigned long long q_key[CAP];
+    __shared__ uint32_t q_meta[CAP], q_h[CAP];
+    __shared__ uint32_t q_n, s_ws[T / 32];
+    __shared__ uint16_t o_wc[T / 32][PP_OBINS];
+    __shared__ uint32_t o_gb[PP_OBINS];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint64_t nreg = a.n_regions;
+    unsigned long long flat = 0;
+    if (!a.counts) { flat = *a.flat_total; nreg = (flat + a.cap - 1) / a.cap; }
+    const uint32_t sshift = a.pb + 10 <= 32 ? 32 - a.pb - 10 : 0;
+    for (uint64_t q = blockIdx.x; q < nreg; q += gridDim.x) {
+        uint32_t cnt;
+        if (a.counts) cnt = min(a.counts[q], a.cap);
+        else cnt = (uint32_t)min((unsigned long long)a.cap, flat - q * a.cap);
+        if (cnt == 0) continue;
+        const bool do_pf = a.prefetch && a.counts && a.pb;
+        const uint32_t h_lo = do_pf ? (uint32_t)(q << (32 - a.pb)) : 0;
+        const uint32_t h_hi = do_pf ? (uint32_t)(((q + 1) << (32 - a.pb)) - 1) : 0;
+        if (do_pf && tid < min(2u, a.ng)) {
+            const PkTable t = a.tabs[tid];
+            const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
+            if (b1 - b0 < 8192) l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
+        }
+        // ---- load items, derive canonical k-mers, counting sort by the next 10 hash bits
+        for (uint32_t i = tid; i < PS_BINS; i += T) s_cnt[i] = 0;
+        for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
+        if (tid == 0) q_n = 0;
+        __syncthreads();
+        const uint2 *src = a.buf + q * (uint64_t)a.cap;
+        uint64_t canon[IPT];
+        uint32_t h[IPT], pos[IPT], rnk[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const uint32_t i = tid + j * T;
+            canon[j] = 0; h[j] = 0; pos[j] = 0; rnk[j] = 0;
+            if (i < cnt) {
+                const uint2 it = src[i];
+                const uint64_t p = a.p0 + it.y;
+                const uint64_t w0 = a.words[p >> 5], w1 = a.words[(p >> 5) + 1];
+                const uint32_t sh = 2 * ((uint32_t)p & 31);
+                const uint64_t x = (w0 << sh) | ((w1 >> 1) >> (63 - sh));
+                const uint64_t fwd = x >> (64 - 2 * a.k);
+                const uint64_t rc = pk_revcomp(fwd, a.k);
+                canon[j] = fwd < rc ? fwd : rc;
+                h[j] = it.x; pos[j] = it.y;
+                rnk[j] = atomicAdd(&s_cnt[(it.x >> sshift) & (PS_BINS - 1)], 1u);
+            }
+        }
+        __syncthreads();
+        {   // exclusive scan of s_cnt[PS_BINS], PS_BINS / T bins per thread
+            constexpr int BPT = PS_BINS / T;
+            uint32_t c[BPT], sum = 0;
+#pragma unroll
+            for (int b = 0; b < BPT; b++) { c[b] = s_cnt[tid * BPT + b]; sum += c[b]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            if (lane == 31) s_ws[wid] = inc;
+            __syncthreads();
+            uint32_t off = inc - sum;
+#pragma unroll
+            for (int ww = 0; ww < T / 32; ww++) off += ww < (int)wid ? s_ws[ww] : 0;
+#pragma unroll
+            for (int b = 0; b < BPT; b++) { s_cnt[tid * BPT + b] = off; off += c[b]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            if (tid + j * T < cnt) {
+                const uint32_t d = s_cnt[(h[j] >> sshift) & (PS_BINS - 1)] + rnk[j];
+                s_canon[d] = canon[j]; s_h[d] = h[j]; s_pos[d] = pos[j];
+            }
+        }
+        __syncthreads();
+        uint32_t bits[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const uint32_t i = tid + j * T;
+            bits[j] = 0;
+            if (i < cnt) { canon[j] = s_canon[i]; h[j] = s_h[i]; }
+        }
+        // ---- probe: genome by genome, neighbouring lanes hit neighbouring buckets
+        for (uint32_t g = 0; g < a.ng; g++) {
+            const PkTable t = a.tabs[g];
+            if (do_pf && tid == 0 && g + 2 < a.ng) {
+                const PkTable tn = a.tabs[g + 2];
+                const uint32_t b0 = __umulhi(h_lo, tn.n_buckets), b1 = __umulhi(h_hi, tn.n_buckets);
+                if (b1 - b0 < 8192) l2_prefetch_bulk(tn.slots + 4ull * b0, (b1 - b0 + 1) * 32);
+            }
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                const uint32_t i = tid + j * T;
+                if (i < cnt) {
+                    const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
+                    const uint64_t key = canon[j];
+                    const bool hit = v.a == key || v.b == key || v.c == key || v.d == key;
+                    bits[j] |= (uint32_t)hit << g;
+                    if (!hit && v.d != PK_EMPTY) {          // full bucket without the key: deferred walk-on
+                        const uint32_t slot = atomicAdd(&q_n, 1u);
+                        if (slot < (uint32_t)CAP) {
+                            q_key[slot] = key; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
+                        } else {
+                            uint32_t bb = __umulhi(h[j], t.n_buckets);
+                            for (uint32_t r = 1; r < t.n_buckets; r++) {
+                                bb = bb + 1 == t.n_buckets ? 0 : bb + 1;
+                                const u64x4 w = pk_ld_bucket_ca(t.slots + 4ull * bb);
+                                if (w.a == key || w.b == key || w.c == key || w.d == key) { bits[j] |= 1u << g; break; }
+                                if (w.d == PK_EMPTY) break;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const uint32_t nq = min(q_n, (uint32_t)CAP);
+            for (uint32_t e = tid; e < nq; e += T) {
+                const uint64_t key = q_key[e];
+                const uint32_t meta = q_meta[e], g = meta & 31;
+                const PkTable t = a.tabs[g];
+                uint32_t bb = __umulhi(q_h[e], t.n_buckets);
+                for (uint32_t r = 1; r < t.n_buckets; r++) {
+                    bb = bb + 1 == t.n_buckets ? 0 : bb + 1;
+                    const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * bb);
+                    if (v.a == key || v.b == key || v.c == key || v.d == key) { atomicOr(&s_bits[meta >> 5], 1u << g); break; }
+                    if (v.d == PK_EMPTY) break;
+                }
+            }
+        }
+        for (uint32_t qq = tid; qq < (T / 32) * PP_OBINS; qq += T) (&o_wc[0][0])[qq] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const uint32_t i = tid + j * T;
+            if (i < cnt) { bits[j] |= s_bits[i]; pos[j] = s_pos[i]; }
+        }
+        if (a.out_list) {
+            uint16_t rank[IPT];
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                const bool v = tid + j * T < cnt;
+                const uint32_t bin = v ? pos[j] >> a.out_shift : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (v && lane == leader) {
+                    old = o_wc[wid][bin];
+                    o_wc[wid][bin] = (uint16_t)(old + __popc(peers));
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rank[j] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
+                __syncwarp();
+            }
+            __syncthreads();
+            for (uint32_t b = tid; b < PP_OBINS; b += T) {
+                uint32_t run = 0;
+#pragma unroll
+                for (int ww = 0; ww < T / 32; ww++) {
+                    const uint32_t tt = o_wc[ww][b];
+                    o_wc[ww][b] = (uint16_t)run;
+                    run += tt;
+                }
+                if (run) o_gb[b] = atomicAdd(&a.out_cursor[a.grp * PP_OBINS + b], run);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                if (tid + j * T < cnt) {
+                    const uint32_t bin = pos[j] >> a.out_shift;
+                    const uint64_t slot = (((uint64_t)a.grp * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + o_wc[wid][bin] + rank[j];
+                    a.out_list[slot] = make_uint2(pos[j], bits[j]);
+                }
+            }
+        } else {
+            const uint32_t nb = min(4u, a.nbl - 4 * a.grp);
+            const bool al4 = nb == 4 && ((a.row_stride | a.col_offset) & 3) == 0;
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                if (tid + j * T < cnt) {
+                    uint8_t *dst = a.rows + (uint64_t)pos[j] * a.row_stride + a.col_offset + 4 * a.grp;
+                    if (al4) *(uint32_t *)dst = bits[j];
+                    else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(bits[j] >> (8 * qb));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // variants of K3 selectable at run time (PK_K3_VARIANT) while the design is being tuned
-struct K3Variant { int threads, cap; size_t shmem; void (*fn)(ProbeArgs); };
+struct K3Variant { int threads, cap; size_t shmem; void (*fn)(ProbeArgs); void (*fn2)(ProbeArgs2); };
 static const K3Variant k3_variants[] = {
     {PP_THREADS, PP_CAP, (size_t)PP_CAP * 16, probe_part_kernel},          // 0: genome-sequential, items in smem
     {256, 768, 0, probe_item_kernel<256, 3, 8, 2>},                         // 1
@@ -541,8 +797,15 @@ static const K3Variant k3_variants[] = {
     {512, 1536, 0, probe_item_kernel<512, 3, 4, 2>},                        // 5
     {256, 1536, 0, probe_item_kernel<256, 6, 4, 4>},                        // 6
     {256, 768, 0, probe_item_kernel<256, 3, 2, 5>},                         // 7
+    {256, 768, 0, probe_item_kernel<256, 3, 2, 4>},                         // 8
+    {256, 768, 0, probe_item_kernel<256, 3, 4, 3>},                         // 9
+    {256, 768, 0, probe_item_kernel<256, 3, 1, 6>},                         // 10
+    {256, 768, 0, nullptr, probe_sorted_kernel<256, 3, 5>},                 // 11
+    {256, 768, 0, nullptr, probe_sorted_kernel<256, 3, 4>},                 // 12
+    {256, 512, 0, nullptr, probe_sorted_kernel<256, 2, 6>},                 // 13
+    {128, 768, 0, nullptr, probe_sorted_kernel<128, 6, 8>},                 // 14
 };
-static int g_k3_variant = 7;
+static int g_k3_variant = 11;
 void pk_part_set_variant(int v) { if (v >= 0 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
 
 // K4: scatter the (pos, bits) lists into rows. All blocks of one bin write inside a slice of
@@ -594,9 +857,9 @@ void pk_part_plan(uint64_t n, PkPartPlan *pl) {
 uint32_t pk_part_obins(void) { return PP_OBINS; }
 
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
-                                const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
-                                uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, int prefetch,
-                                pk_stream_t s, cudaEvent_t *evs) {
+                                const PkTable *d_tables, const PkTable *h_tables, uint32_t n_local, uint8_t *d_rows,
+                                uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
+                                int prefetch, pk_stream_t s, cudaEvent_t *evs) {
     if (!n) return 0;
     static bool attr_set = false;
     const K3Variant &kv = k3_variants[g_k3_variant];
@@ -638,11 +901,32 @@ int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask,
     p.out_cursor = sc.out_cursor;
     p.out_shift = pl.out_shift;
     if (evs) cudaEventRecord(evs[2], s);
-    kv.fn<<<p.n_regions, kv.threads, shmem, s>>>(p);
-    if (evs) cudaEventRecord(evs[3], s);
-    ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)
-    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
-    kv.fn<<<148 * 2, kv.threads, shmem, s>>>(sp);
+    if (kv.fn) {
+        kv.fn<<<p.n_regions, kv.threads, shmem, s>>>(p);
+        if (evs) cudaEventRecord(evs[3], s);
+        ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)
+        sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
+        kv.fn<<<148 * 2, kv.threads, shmem, s>>>(sp);
+    } else {
+        ProbeArgs2 p2{};
+        p2.buf = p.buf; p2.counts = p.counts; p2.cap = p.cap; p2.n_regions = p.n_regions; p2.pb = p.pb;
+        p2.words = d_words; p2.p0 = p0; p2.k = k;
+        p2.rows = d_rows; p2.row_stride = row_stride; p2.col_offset = col_offset; p2.nbl = a.nbl;
+        p2.prefetch = prefetch; p2.out_list = p.out_list; p2.out_cursor = p.out_cursor; p2.out_shift = p.out_shift;
+        for (uint32_t grp = 0; grp < n_groups; grp++) {       // one launch per group of 32 genomes
+            p2.grp = grp; p2.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
+            for (uint32_t g = 0; g < p2.ng; g++) p2.tabs[g] = h_tables[32 * grp + g];
+            kv.fn2<<<p2.n_regions, kv.threads, 0, s>>>(p2);
+        }
+        if (evs) cudaEventRecord(evs[3], s);
+        ProbeArgs2 sp = p2;
+        sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
+        for (uint32_t grp = 0; grp < n_groups; grp++) {
+            sp.grp = grp; sp.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
+            for (uint32_t g = 0; g < sp.ng; g++) sp.tabs[g] = h_tables[32 * grp + g];
+            kv.fn2<<<148 * 2, kv.threads, 0, s>>>(sp);
+        }
+    }
     if (evs) cudaEventRecord(evs[4], s);
     if (unperm) {
         dim3 grid((unsigned)(((1ull << pl.out_shift) + UP_TILE - 1) / UP_TILE), pl.out_bins, n_groups);
