@@ -18,6 +18,8 @@
 // repeats) go to a spill list that the same probe kernel drains with unconfined probes.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "pk_device.cuh"
 #include "pk_internal.h"
 
@@ -39,6 +41,7 @@ struct PartSmem {
 
 // Scatter a tile of items (h, pos) into fixed-capacity regions by digit = (h >> shift) & (nb-1).
 // Region r = region0 + digit holds items dst[r * cap .. r * cap + min(cursor[r], cap)).
+template <int RANK>
 __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)[PT_IPT], const uint32_t (&pos)[PT_IPT],
                                                 uint32_t validmask, uint32_t shift, uint32_t nb, uint2 *__restrict__ dst,
                                                 uint64_t region0, uint32_t cap, uint32_t *__restrict__ cursor,
@@ -46,9 +49,19 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
                                                 uint64_t spill_cap, uint32_t *__restrict__ err) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t lt = (1u << lane) - 1;
+    uint16_t rank[PT_IPT];
+    if (RANK == 1) {
+        // block-wide counters: one shared-memory atomic per item returns its rank inside (tile, digit)
+        for (uint32_t d = tid; d < nb; d += PT_THREADS) S.tot[d] = 0;
+        for (uint32_t i = tid; i < PT_WARPS * PT_MAXB; i += PT_THREADS) (&S.warp_cnt[0][0])[i] = 0;   // prefix over warps = 0
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PT_IPT; j++)
+            rank[j] = (validmask >> j) & 1 ? (uint16_t)atomicAdd(&S.tot[(h[j] >> shift) & (nb - 1)], 1u) : 0;
+        __syncthreads();
+    } else {
     for (uint32_t i = tid; i < PT_WARPS * PT_MAXB; i += PT_THREADS) (&S.warp_cnt[0][0])[i] = 0;
     __syncthreads();
-    uint16_t rank[PT_IPT];
     uint32_t peers[PT_IPT];
     // all MATCH.ANY first (independent, long latency), then the serial per-warp counter updates
 #pragma unroll
@@ -82,6 +95,7 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
         S.tot[d] = run;
     }
     __syncthreads();
+    }
     {   // exclusive scan of tot[0..nb) with 2 digits per thread (nb <= 512 = 2 * PT_THREADS)
         const uint32_t a = 2 * tid < nb ? S.tot[2 * tid] : 0, b = 2 * tid + 1 < nb ? S.tot[2 * tid + 1] : 0;
         uint32_t s = a + b;
@@ -144,6 +158,7 @@ struct PartArgs {
 
 // K1: positions [p0, p0+n) -> (hash, i) pairs (i = position - p0), partitioned by the top pb1 bits.
 // Invalid windows get their all-zero row here and never enter the pipeline.
+template <int RANK>
 __global__ void __launch_bounds__(PT_THREADS, 3) partition_seq_kernel(PartArgs a) {
     __shared__ PartSmem S;
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -164,11 +179,12 @@ __global__ void __launch_bounds__(PT_THREADS, 3) partition_seq_kernel(PartArgs a
             }
         }
     }
-    block_partition(S, h, pos, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill, a.spill_cursor,
-                    a.spill_cap, a.err);
+    block_partition<RANK>(S, h, pos, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill, a.spill_cursor,
+                          a.spill_cap, a.err);
 }
 
 // K2: coarse region c = blockIdx.y, tile blockIdx.x of it -> fine regions c * 2^pb2 + next pb2 bits.
+template <int RANK>
 __global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs a) {
     __shared__ PartSmem S;
     const uint32_t c = blockIdx.y;
@@ -188,8 +204,8 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs 
             valid |= 1u << j;
         }
     }
-    block_partition(S, h, pos, valid, 32 - a.pb1 - a.pb2, 1u << a.pb2, a.buf2, (uint64_t)c << a.pb2, a.cap2, a.cursor2,
-                    a.spill, a.spill_cursor, a.spill_cap, a.err);
+    block_partition<RANK>(S, h, pos, valid, 32 - a.pb1 - a.pb2, 1u << a.pb2, a.buf2, (uint64_t)c << a.pb2, a.cap2, a.cursor2,
+                          a.spill, a.spill_cursor, a.spill_cap, a.err);
 }
 
 // ------------------------------------------------------------------ K3: probe one partition per block
@@ -805,7 +821,7 @@ static const K3Variant k3_variants[] = {
     {256, 512, 0, nullptr, probe_sorted_kernel<256, 2, 6>},                 // 13
     {128, 768, 0, nullptr, probe_sorted_kernel<128, 6, 8>},                 // 14
 };
-static int g_k3_variant = 11;
+static int g_k3_variant = 10;
 void pk_part_set_variant(int v) { if (v >= 0 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
 
 // K4: scatter the (pos, bits) lists into rows. All blocks of one bin write inside a slice of
@@ -882,11 +898,14 @@ int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask,
     a.err = sc.err;
     a.rows = d_rows; a.row_stride = row_stride; a.col_offset = col_offset; a.nbl = (n_local + 7) / 8;
     if (evs) cudaEventRecord(evs[0], s);
-    partition_seq_kernel<<<(unsigned)((n + PT_TILE - 1) / PT_TILE), PT_THREADS, 0, s>>>(a);
+    static const int rank_mode = getenv("PK_PART_RANK") ? atoi(getenv("PK_PART_RANK")) : 1;
+    if (rank_mode) partition_seq_kernel<1><<<(unsigned)((n + PT_TILE - 1) / PT_TILE), PT_THREADS, 0, s>>>(a);
+    else partition_seq_kernel<0><<<(unsigned)((n + PT_TILE - 1) / PT_TILE), PT_THREADS, 0, s>>>(a);
     if (evs) cudaEventRecord(evs[1], s);
     if (pl.pb2) {
         dim3 grid((pl.cap1 + PT_TILE - 1) / PT_TILE, pl.n_regions1);
-        partition_fine_kernel<<<grid, PT_THREADS, 0, s>>>(a);
+        if (rank_mode) partition_fine_kernel<1><<<grid, PT_THREADS, 0, s>>>(a);
+        else partition_fine_kernel<0><<<grid, PT_THREADS, 0, s>>>(a);
     }
     ProbeArgs p{};
     p.buf = pl.pb2 ? (const uint2 *)sc.buf2 : (const uint2 *)sc.buf1;
