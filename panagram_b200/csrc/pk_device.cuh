@@ -5,15 +5,7 @@
 
 #include "pk_internal.h"
 
-// ------------------------------------------------------------------ helpers
-__device__ __forceinline__ uint32_t pk_hash32(uint64_t x) {
-    x ^= x >> 32;
-    x *= 0x9E3779B97F4A7C15ull;
-    x ^= x >> 29;
-    x *= 0xBF58476D1CE4E5B9ull;
-    return (uint32_t)(x >> 32);
-}
-
+// ------------------------------------------------------------------ sequence window
 // reverse complement of a right-aligned 2k-bit k-mer (A=0 C=1 G=2 T=3: complement = 3-c = ~c)
 __device__ __forceinline__ uint64_t pk_revcomp(uint64_t fwd, uint32_t k) {
     uint64_t x = __brevll(~fwd);
@@ -21,8 +13,19 @@ __device__ __forceinline__ uint64_t pk_revcomp(uint64_t fwd, uint32_t k) {
     return x >> (64 - 2 * k);
 }
 
+// canonical k-mer of the (valid) window starting at base p. words: 32 bases per uint64, first base in
+// the top two bits.
+__device__ __forceinline__ uint64_t pk_canon_at(const uint64_t *__restrict__ words, uint64_t p, uint32_t k) {
+    const uint64_t w0 = words[p >> 5], w1 = words[(p >> 5) + 1];
+    const uint32_t s = 2 * ((uint32_t)p & 31);
+    const uint64_t x = (w0 << s) | ((w1 >> 1) >> (63 - s));
+    const uint64_t fwd = x >> (64 - 2 * k);
+    const uint64_t rc = pk_revcomp(fwd, k);
+    return fwd < rc ? fwd : rc;      // kmer < kmer_rev ? kmer : kmer_rev  (kmc_file.cpp:998-1001)
+}
+
 // canonical k-mer of the window starting at base p; false if the window holds a non-ACGT byte.
-// words: 32 bases per uint64, first base in the top two bits. mask64: 1 bit per base, LSB first.
+// mask64: 1 bit per base, LSB first.
 __device__ __forceinline__ bool pk_window(const uint64_t *__restrict__ words, const uint64_t *__restrict__ mask64,
                                           uint64_t p, uint32_t k, uint64_t &canon) {
     const uint64_t m0 = mask64[p >> 6], m1 = mask64[(p >> 6) + 1];
@@ -30,30 +33,114 @@ __device__ __forceinline__ bool pk_window(const uint64_t *__restrict__ words, co
     const uint64_t win = (m0 >> t) | ((m1 << 1) << (63 - t));
     const uint64_t kmask = k == 64 ? ~0ull : ((1ull << k) - 1);
     if (win & kmask) return false;
-    const uint64_t w0 = words[p >> 5], w1 = words[(p >> 5) + 1];
-    const uint32_t s = 2 * ((uint32_t)p & 31);
-    const uint64_t x = (w0 << s) | ((w1 >> 1) >> (63 - s));
-    const uint64_t fwd = x >> (64 - 2 * k);
-    const uint64_t rc = pk_revcomp(fwd, k);
-    canon = fwd < rc ? fwd : rc;     // kmer < kmer_rev ? kmer : kmer_rev  (kmc_file.cpp:998-1001)
+    canon = pk_canon_at(words, p, k);
     return true;
 }
 
+// ------------------------------------------------------------------ hashing
+__device__ __forceinline__ uint32_t pk_hash64(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0x9E3779B97F4A7C15ull;
+    x ^= x >> 29;
+    x *= 0xBF58476D1CE4E5B9ull;
+    return (uint32_t)(x >> 32);
+}
+__device__ __forceinline__ uint32_t pk_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// The 32-bit hash every table is indexed by (bucket = mulhi(hash, n_buckets)).
+//  S64: any good hash of the whole k-mer; the slot stores the whole k-mer.
+//  S32: the slot stores only the low 28 key bits (+ 4 displacement bits), so the remaining eb = 2k-28 high
+//       key bits must be recoverable from the home bucket: they are XOR-ed with a hash of the low bits
+//       (uniform, and a bijection for fixed low bits) and placed in the TOP eb bits of the hash; with
+//       n_buckets >= 2^eb two k-mers with equal low bits never share a home bucket.
+__device__ __forceinline__ uint32_t pk_key_hash(uint64_t canon, const PkKeySpec ks) {
+    if (ks.fmt == PK_FMT_S64) return pk_hash64(canon);
+    const uint32_t lo = (uint32_t)canon & PK_S32_REM_MASK, m = pk_mix32(lo);
+    if (ks.eb == 0) return m;
+    const uint32_t hi = (uint32_t)(canon >> PK_S32_REM_BITS);
+    return ((hi ^ ((m * 0x9E3779B1u) >> (32 - ks.eb))) << (32 - ks.eb)) | (m >> ks.eb);
+}
+
+// ------------------------------------------------------------------ buckets (32 B = one sector)
 struct u64x4 { unsigned long long a, b, c, d; };
-// one 32-byte bucket in one instruction (LDG.E.256, sm_100+)
-__device__ __forceinline__ u64x4 pk_ld_bucket(const unsigned long long *p) {
+// one 32-byte bucket in one instruction (LDG.E.256, sm_100+), streaming (no L1 allocation)
+__device__ __forceinline__ u64x4 pk_ld_bucket(const void *p) {
     u64x4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
     return v;
 }
-
-
-// same bucket through the default (L1-allocating) path: used where neighbouring probes share sectors
-__device__ __forceinline__ u64x4 pk_ld_bucket_ca(const unsigned long long *p) {
+// same through the default (L1-allocating) path: used where neighbouring probes share sectors
+__device__ __forceinline__ u64x4 pk_ld_bucket_ca(const void *p) {
     u64x4 v;
     asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
     return v;
+}
+
+// what a lookup compares against in a bucket at displacement r from the key's home bucket
+template <int FMT> __device__ __forceinline__ uint64_t pk_target(uint64_t canon, uint32_t r) {
+    return FMT == PK_FMT_S64 ? canon : (uint64_t)((((uint32_t)canon & PK_S32_REM_MASK) << PK_S32_DISP_BITS) | r);
+}
+template <int FMT> __device__ __forceinline__ bool pk_bucket_hit(const u64x4 &v, uint64_t target) {
+    if (FMT == PK_FMT_S64) return v.a == target || v.b == target || v.c == target || v.d == target;
+    const uint32_t t = (uint32_t)target;
+    return (uint32_t)v.a == t || (uint32_t)(v.a >> 32) == t || (uint32_t)v.b == t || (uint32_t)(v.b >> 32) == t ||
+           (uint32_t)v.c == t || (uint32_t)(v.c >> 32) == t || (uint32_t)v.d == t || (uint32_t)(v.d >> 32) == t;
+}
+// slots fill in order (an insert claims the first free slot it meets), so a bucket is full iff its last slot is taken
+template <int FMT> __device__ __forceinline__ bool pk_bucket_full(const u64x4 &v) {
+    return FMT == PK_FMT_S64 ? v.d != PK_EMPTY : (uint32_t)(v.d >> 32) != PK_EMPTY32;
+}
+// how far a key may sit from its home bucket
+template <int FMT> __device__ __forceinline__ uint32_t pk_max_disp(uint32_t n_buckets) {
+    return FMT == PK_FMT_S64 ? n_buckets - 1 : (n_buckets - 1 < PK_S32_MAX_DISP ? n_buckets - 1 : PK_S32_MAX_DISP);
+}
+
+// the stash: keys of S32 tables that found no room within PK_S32_MAX_DISP buckets of home
+__device__ __forceinline__ unsigned long long pk_stash_entry(uint32_t g, uint64_t canon) { return ((unsigned long long)g << 48) | canon; }
+__device__ __forceinline__ bool pk_stash_contains(const PkKeySpec ks, uint32_t g, uint64_t canon) {
+    if (*(volatile unsigned int *)ks.stash_n == 0) return false;
+    const unsigned long long e = pk_stash_entry(g, canon);
+    uint32_t i = pk_hash64(e) & (PK_STASH_SLOTS - 1);
+    for (uint32_t t = 0; t < PK_STASH_SLOTS; t++) {
+        const unsigned long long cur = ks.stash[i];
+        if (cur == e) return true;
+        if (cur == PK_EMPTY) return false;
+        i = (i + 1) & (PK_STASH_SLOTS - 1);
+    }
+    return false;
+}
+// 0 = already there, 1 = inserted, 3 = stash full
+__device__ __forceinline__ int pk_stash_insert(const PkKeySpec ks, uint32_t g, uint64_t canon) {
+    const unsigned long long e = pk_stash_entry(g, canon);
+    uint32_t i = pk_hash64(e) & (PK_STASH_SLOTS - 1);
+    for (uint32_t t = 0; t < PK_STASH_SLOTS / 2; t++) {
+        const unsigned long long cur = *(volatile unsigned long long *)(ks.stash + i);
+        if (cur == e) return 0;
+        if (cur == PK_EMPTY) {
+            const unsigned long long old = atomicCAS(ks.stash + i, PK_EMPTY, e);
+            if (old == PK_EMPTY) { atomicAdd(ks.stash_n, 1u); return 1; }
+            if (old == e) return 0;
+        }
+        i = (i + 1) & (PK_STASH_SLOTS - 1);
+    }
+    return 3;
+}
+
+// full lookup (home bucket + walk-on), used off the hot path. g = local genome index (stash key).
+template <int FMT> __device__ __forceinline__ bool pk_lookup(const PkTable t, uint64_t canon, uint32_t h, uint32_t g, const PkKeySpec ks) {
+    uint32_t b = __umulhi(h, t.n_buckets);
+    const uint32_t maxd = pk_max_disp<FMT>(t.n_buckets);
+    for (uint32_t r = 0;; r++) {
+        const u64x4 v = pk_ld_bucket_ca((const char *)t.slots + 32ull * b);
+        if (pk_bucket_hit<FMT>(v, pk_target<FMT>(canon, r))) return true;
+        if (!pk_bucket_full<FMT>(v)) return false;
+        if (r == maxd) return FMT == PK_FMT_S32 ? pk_stash_contains(ks, g, canon) : false;
+        b = b + 1 == t.n_buckets ? 0 : b + 1;
+    }
 }
 #endif

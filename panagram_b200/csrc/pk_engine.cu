@@ -39,6 +39,7 @@ struct HostTable {
 
 struct pk_engine {
     pk_config cfg{};
+    PkKeySpec ks{};                             // k + slot format of the tables
     uint32_t n_local = 0, row_bytes = 0;
     std::vector<HostTable> tabs;
     PkTable *d_tables = nullptr;
@@ -47,6 +48,7 @@ struct pk_engine {
     bool finalized = false;
     cudaStream_t stream = nullptr;              // build stream / default stream for device-level calls
     cudaStream_t copy_stream = nullptr;         // D2H of finished chromosomes
+    cudaStream_t in_stream = nullptr;           // H2D of the anchor's chromosomes
     cudaEvent_t ev[6] = {};                     // begin, h2d done, pack done, probe done, reduce done, end
     // genome-batch buffers (grow-only)
     uint8_t *g_ascii = nullptr; uint64_t g_ascii_cap = 0;
@@ -126,6 +128,11 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (e->cfg.min_bin_count == 0) e->cfg.min_bin_count = 100;
     if (e->cfg.load_factor == 0.f) e->cfg.load_factor = 0.5f;
     if (e->cfg.probe_mode > 2) { pk_set_error("probe_mode %u out of range", e->cfg.probe_mode); return PK_EINVAL; }
+    // slot format: S32 (8 x 32-bit slots per sector) whenever the 2k-29 high key bits fit the bucket index
+    e->ks.k = cfg->k;
+    e->ks.eb = 2 * cfg->k > PK_S32_REM_BITS ? 2 * cfg->k - PK_S32_REM_BITS : 0;
+    e->ks.fmt = e->ks.eb <= PK_S32_MAX_EB ? PK_FMT_S32 : PK_FMT_S64;
+    if (const char *tf = getenv("PK_TABLE_FMT")) { if (atoi(tf) == 64) e->ks.fmt = PK_FMT_S64; }
     if (const char *pf = getenv("PK_L2_PREFETCH")) e->l2_prefetch = atoi(pf);
     if (const char *up = getenv("PK_UNPERMUTE")) e->unpermute = atoi(up);
     if (const char *kv = getenv("PK_K3_VARIANT")) pk_part_set_variant(atoi(kv));
@@ -140,6 +147,10 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     CU(cudaMemset(e->d_counters, 0, sizeof(unsigned long long) * 3 * e->n_local));
     CU(cudaMalloc(&e->d_colsums, sizeof(unsigned long long) * e->n_local));
     for (auto &ev : e->pev) CU(cudaEventCreate(&ev));
+    CU(cudaMalloc(&e->ks.stash, sizeof(unsigned long long) * PK_STASH_SLOTS));
+    CU(cudaMemset(e->ks.stash, 0xFF, sizeof(unsigned long long) * PK_STASH_SLOTS));
+    CU(cudaMalloc(&e->ks.stash_n, sizeof(unsigned int)));
+    CU(cudaMemset(e->ks.stash_n, 0, sizeof(unsigned int)));
     *out = e.release();
     return PK_OK;
 }
@@ -155,6 +166,8 @@ extern "C" void pk_engine_destroy(pk_engine *e) {
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->pev) if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->in_stream) cudaStreamDestroy(e->in_stream);
+    cudaFree(e->ks.stash); cudaFree(e->ks.stash_n);
     cudaFree(e->d_tables); cudaFree(e->d_counters); cudaFree(e->d_colsums); cudaFree(e->d_hist);
     cudaFree(e->d_stage);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -178,8 +191,11 @@ extern "C" int pk_engine_reserve(pk_engine *e, uint32_t genome, uint64_t max_key
     int rc = set_device(e); if (rc) return rc;
     HostTable &t = e->tabs[genome - e->cfg.genome_begin];
     if (t.reserved) { pk_set_error("genome %u already reserved", genome); return PK_ESTATE; }
-    // buckets of 4 slots; at least 2 so the walk-on probe terminates on an EMPTY slot
-    uint64_t nb = (uint64_t)((double)max_keys / (4.0 * e->cfg.load_factor)) + 2;
+    // 32-byte buckets of 4 (S64) or 8 (S32) slots; S32 needs n_buckets >= 2^eb so that k-mers with equal
+    // low bits never share a home bucket (pk_key_hash), and always a free slot somewhere for walk-ons to stop
+    const double slots_per_bucket = e->ks.fmt == PK_FMT_S32 ? 8.0 : 4.0;
+    uint64_t nb = (uint64_t)((double)max_keys / (slots_per_bucket * e->cfg.load_factor)) + 2;
+    if (e->ks.fmt == PK_FMT_S32) nb = std::max<uint64_t>(nb, std::max<uint64_t>(1ull << e->ks.eb, 16));
     if (nb >= 0xFFFFFFFFull) { pk_set_error("genome %u: %llu keys exceed the 2^32-bucket table limit", genome, (unsigned long long)max_keys); return PK_EUNSUPPORTED; }
     CU(cudaMalloc(&t.dev.slots, nb * 32));
     t.dev.n_buckets = (uint32_t)nb;
@@ -234,6 +250,7 @@ static int ingest_kmc(pk_engine *e, const char *prefix, bool bitvec, uint32_t ge
     PkDecodeArgs a{};
     a.d_lut = d_lut; a.n_lut_slots = db->lut.size() - 1; a.single_lut = db->single_lut;
     a.suf_size = db->suf_size; a.counter_size = I.counter_size; a.rec_size = db->rec_size;
+    a.ks = e->ks;
     a.min_count = I.min_count; a.max_count = I.max_count;
     a.bitvec = bitvec; a.first_genome = genome_or_first; a.gbegin = e->cfg.genome_begin; a.gend = e->cfg.genome_end;
     a.d_tables = e->d_tables; a.local_genome = bitvec ? 0 : genome_or_first - e->cfg.genome_begin;
@@ -280,7 +297,8 @@ extern "C" int pk_engine_add_keys(pk_engine *e, uint32_t genome, const uint64_t 
         CU(cudaMalloc(&d_keys, n * 8));
         struct Freer { void *p; ~Freer() { cudaFree(p); } } freer{d_keys};
         CU(cudaMemcpyAsync(d_keys, keys, n * 8, cudaMemcpyHostToDevice, e->stream));
-        pk_launch_insert_keys(d_keys, n, t.dev, e->d_counters + 3 * (genome - e->cfg.genome_begin), e->stream);
+        pk_launch_insert_keys(d_keys, n, e->ks, t.dev, genome - e->cfg.genome_begin,
+                              e->d_counters + 3 * (genome - e->cfg.genome_begin), e->stream);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(e->stream));
     }
@@ -299,7 +317,7 @@ static int add_sequence_device(pk_engine *e, uint32_t genome, const uint8_t *d_a
     CU(cudaMalloc(&d_mask, nw * 4));
     Freer f2{d_mask};
     pk_launch_pack(d_ascii, len, nw, d_words, d_mask, e->stream);
-    pk_launch_insert_seq(d_words, d_mask, len - e->cfg.k + 1, e->cfg.k, t.dev,
+    pk_launch_insert_seq(d_words, d_mask, len - e->cfg.k + 1, e->ks, t.dev, genome - e->cfg.genome_begin,
                          e->d_counters + 3 * (genome - e->cfg.genome_begin), e->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
@@ -346,7 +364,7 @@ extern "C" int pk_engine_finalize(pk_engine *e) {
     for (uint32_t i = 0; i < e->n_local; i++) {
         e->tabs[i].n_keys = c[3 * i]; e->tabs[i].n_overflow = c[3 * i + 1];
         if (c[3 * i + 2]) {
-            pk_set_error("genome %u: table full (%llu keys did not fit a table reserved for %llu)",
+            pk_set_error("genome %u: table too small (%llu keys did not fit a table reserved for %llu)",
                          e->cfg.genome_begin + i, c[3 * i + 2], (unsigned long long)e->tabs[i].capacity);
             return PK_ENOMEM;
         }
@@ -465,7 +483,7 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
             PkPartPlan pl;
             pk_part_plan(m, &pl);
             int rc = ensure_scratch(e, pl); if (rc) return rc;
-            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->cfg.k, e->d_tables, e->h_tables.data(), e->n_local,
+            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->h_tables.data(), e->n_local,
                                             d_rows + o * row_stride, row_stride, col_offset, pl, e->sc, e->l2_prefetch, s, e->pev)) {
                 pk_set_error("partitioned probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return PK_ECUDA;
@@ -474,7 +492,7 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
             e->stats.probe_launches += 1;
             e->pev_valid = true;
         } else {
-            pk_launch_probe(d_words, d_mask, p0 + o, m, e->cfg.k, e->d_tables, e->n_local, d_rows + o * row_stride,
+            pk_launch_probe(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->n_local, d_rows + o * row_stride,
                             row_stride, col_offset, s);
             e->stats.kernel_launches += 1;
             e->stats.probe_launches += 1;
@@ -519,14 +537,14 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
     if (n_chroms && (!seqs || !lens)) { pk_set_error("null argument"); return PK_EINVAL; }
     const uint32_t k = e->cfg.k, step = e->cfg.lowres_step, rb = e->row_bytes, N = e->n_local;
     memset(&e->stats, 0, sizeof e->stats);
-    // layout of the concatenated sequence: chromosome c at off[c], one 'N' between neighbours so
-    // that no window spans two chromosomes
+    // layout of the concatenated sequence: chromosome c starts at off[c], a multiple of 32 bases (so it owns
+    // whole packed words), with at least one 'N' before it: no window spans two chromosomes
     std::vector<uint64_t> off(n_chroms), nk(n_chroms), binlen(n_chroms), nbins(n_chroms), lowoff(n_chroms), histoff(n_chroms);
     uint64_t ltot = 0, lowtot = 0, histtot = 0, postot = 0;
     for (uint32_t c = 0; c < n_chroms; c++) {
         if (!seqs[c] && lens[c]) { pk_set_error("null sequence %u", c); return PK_EINVAL; }
         off[c] = ltot;
-        ltot += lens[c] + 1;
+        ltot = (ltot + lens[c] + 1 + 31) & ~31ull;
         nk[c] = lens[c] >= k ? lens[c] - k + 1 : 0;        // len < k: nothing (kmc_file.cpp:878-882)
         binlen[c] = nk[c] ? pk_bin_len(&e->cfg, nk[c]) : 0;
         const bool want_hist = bin_hist && bin_hist[c] && nk[c];
@@ -544,6 +562,7 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
     if (postot == 0) return PK_OK;
     int rc = set_device(e); if (rc) return rc;
     const uint64_t nw = pk_packed_words(ltot);
+    const uint64_t npos = ltot >= k ? ltot - k + 1 : 0;
     rc = grow(e->g_ascii, e->g_ascii_cap, ltot + 64); if (rc) return rc;
     rc = grow(e->g_words, e->g_words_cap, nw); if (rc) return rc;
     rc = grow(e->g_mask, e->g_mask_cap, nw); if (rc) return rc;
@@ -552,30 +571,70 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
     rc = grow(e->d_hist, e->hist_cap, histtot + 1); if (rc) return rc;
     if (!e->ev[0]) for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
     if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    cudaStream_t s = e->stream, cs = e->copy_stream;
+    if (!e->in_stream) CU(cudaStreamCreateWithFlags(&e->in_stream, cudaStreamNonBlocking));
+    cudaStream_t s = e->stream, cs = e->copy_stream, hs = e->in_stream;
+    const uint32_t mode = e->cfg.probe_mode;
+    const uint64_t sub = e->cfg.chunk_positions ? e->cfg.chunk_positions : PK_PART_MAX_N;
+    const bool pipelined = (mode == 2 || (mode == 0 && npos >= (1ull << 20))) && npos <= sub;
+    std::vector<cudaEvent_t> in_done(n_chroms, nullptr), done(n_chroms, nullptr);
+    auto cleanup = [&]() { for (auto ev : in_done) if (ev) cudaEventDestroy(ev); for (auto ev : done) if (ev) cudaEventDestroy(ev); };
     CU(cudaEventRecord(e->ev[0], s));
-    CU(cudaMemsetAsync(e->g_ascii, 'N', ltot + 64, s));
-    for (uint32_t c = 0; c < n_chroms; c++)
-        if (lens[c]) CU(cudaMemcpyAsync(e->g_ascii + off[c], seqs[c], lens[c], cudaMemcpyHostToDevice, s));
+    CU(cudaStreamWaitEvent(hs, e->ev[0], 0));
+    // ---- H2D on the input stream, chromosome by chromosome
+    CU(cudaMemsetAsync(e->g_ascii, 'N', ltot + 64, hs));
+    for (uint32_t c = 0; c < n_chroms; c++) {
+        if (lens[c]) CU(cudaMemcpyAsync(e->g_ascii + off[c], seqs[c], lens[c], cudaMemcpyHostToDevice, hs));
+        CU(cudaEventCreateWithFlags(&in_done[c], cudaEventDisableTiming));
+        CU(cudaEventRecord(in_done[c], hs));
+    }
     CU(cudaMemsetAsync(e->d_hist, 0, (histtot + 1) * 8, s));
     CU(cudaMemsetAsync(e->d_colsums, 0, N * 8, s));
+    PkPartPlan pl{};
+    if (pipelined) {
+        pk_part_plan(npos, &pl);
+        rc = ensure_scratch(e, pl); if (rc) { cleanup(); return rc; }
+        pk_part_begin(N, pl, e->sc, s);
+    }
+    // ---- pack (+ K1 of the partitioned probe) per chromosome as soon as its bytes are on the device
+    for (uint32_t c = 0; c < n_chroms; c++) {
+        CU(cudaStreamWaitEvent(s, in_done[c], 0));
+        const uint64_t w0 = off[c] / 32, w1 = c + 1 < n_chroms ? off[c + 1] / 32 : nw;
+        pk_launch_pack(e->g_ascii + off[c], ltot + 64 - off[c], w1 - w0, e->g_words + w0, e->g_mask + w0, s);
+        e->stats.kernel_launches += 1;
+        if (pipelined && nk[c]) {
+            pk_part_append(e->g_words, e->g_mask, 0, off[c], nk[c], e->ks, N, e->g_rows, rb, 0, pl, e->sc, s);
+            e->stats.kernel_launches += 1;
+        }
+    }
     CU(cudaEventRecord(e->ev[1], s));
-    pk_launch_pack(e->g_ascii, ltot, nw, e->g_words, e->g_mask, s);
     CU(cudaEventRecord(e->ev[2], s));
-    const uint64_t npos = ltot >= k ? ltot - k + 1 : 0;
-    rc = probe_any(e, e->g_words, e->g_mask, 0, npos, e->g_rows, rb, 0, s); if (rc) return rc;
+    if (pipelined) {
+        pk_part_probe(e->g_words, e->g_mask, 0, e->ks, e->h_tables.data(), N, e->g_rows, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
+        e->stats.kernel_launches += (pl.pb2 ? 1 : 0) + 2 * ((N + 31) / 32);
+        e->stats.probe_launches += 1;
+    } else {
+        rc = probe_any(e, e->g_words, e->g_mask, 0, npos, e->g_rows, rb, 0, s); if (rc) { cleanup(); return rc; }
+    }
     CU(cudaEventRecord(e->ev[3], s));
-    // per chromosome: reduce on the compute stream, rows/low-res rows home on the copy stream
-    std::vector<cudaEvent_t> done(n_chroms, nullptr);
+    // ---- per chromosome: un-permute its position bins, reduce, and send rows home on the copy stream
+    uint32_t next_bin = 0;
     for (uint32_t c = 0; c < n_chroms; c++) {
         if (!nk[c]) continue;
+        if (pipelined && e->sc.out_list) {
+            const uint32_t b1 = (uint32_t)((off[c] + nk[c] - 1) >> pl.out_shift) + 1;
+            if (b1 > next_bin) {
+                pk_part_unpermute(next_bin, b1, N, e->g_rows, rb, 0, pl, e->sc, s);
+                e->stats.kernel_launches += 1;
+                next_bin = b1;
+            }
+        }
         const uint8_t *rows_c = e->g_rows + off[c] * rb;
         uint8_t *low_c = e->g_low + lowoff[c] * rb;
         const bool want_low = bitmap_low && bitmap_low[c];
         if (nbins[c] || col_sums || want_low) {
             pk_launch_reduce(rows_c, rb, N, 0, nk[c], nbins[c] ? binlen[c] : 0, nbins[c] ? e->d_hist + histoff[c] : nullptr,
                              col_sums ? e->d_colsums : nullptr, want_low ? low_c : nullptr, step, s);
-            e->stats.kernel_launches += 1;
+            e->stats.kernel_launches += 1 + (want_low ? 1 : 0);
         }
         CU(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
         CU(cudaEventRecord(done[c], s));
@@ -597,18 +656,17 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
     CU(cudaStreamSynchronize(cs));
     CU(cudaEventRecord(e->ev[5], s));
     CU(cudaEventSynchronize(e->ev[5]));
-    for (auto ev : done) if (ev) cudaEventDestroy(ev);
+    cleanup();
     rc = check_part_error(e); if (rc) return rc;
     for (uint32_t c = 0; c < n_chroms; c++)
         if (nbins[c]) memcpy(bin_hist[c], hist_h.data() + histoff[c], nbins[c] * (N + 1) * 8);
     if (col_sums) for (uint32_t g = 0; g < N; g++) col_sums[g] += col_h[g];
-    CU(cudaEventElapsedTime(&e->stats.h2d_ms, e->ev[0], e->ev[1]));
-    CU(cudaEventElapsedTime(&e->stats.pack_ms, e->ev[1], e->ev[2]));
+    CU(cudaEventElapsedTime(&e->stats.h2d_ms, e->ev[0], e->ev[1]));      // H2D overlapped with pack + K1
+    e->stats.pack_ms = 0.f;
     CU(cudaEventElapsedTime(&e->stats.probe_ms, e->ev[2], e->ev[3]));
     CU(cudaEventElapsedTime(&e->stats.reduce_ms, e->ev[3], e->ev[4]));
     CU(cudaEventElapsedTime(&e->stats.d2h_ms, e->ev[4], e->ev[5]));
     CU(cudaEventElapsedTime(&e->stats.total_ms, e->ev[0], e->ev[5]));
-    e->stats.kernel_launches += 1;   // pack
     e->stats.positions = postot;
     e->stats.probes = postot * N;
     return PK_OK;

@@ -35,14 +35,39 @@ struct PkTable {
 
 #define PK_EMPTY 0xFFFFFFFFFFFFFFFFull
 
+// Slot formats. S64: 4 x uint64 whole k-mers per bucket (any k <= 32). S32: 8 x uint32 per bucket, each
+// (low 28 key bits << 4) | displacement-from-home (0..14; 15 only occurs in the all-ones EMPTY slot); the
+// other 2k-28 key bits are implied by the home bucket (pk_key_hash). Used when 2k-28 <= 20 (k <= 24):
+// half the bytes per key, twice the slots per sector. A key that finds 15 consecutive full buckets goes to
+// a small engine-wide stash (S64-style set of (genome << 48 | k-mer)), consulted only at the end of a
+// maximal walk-on.
+#define PK_FMT_S64 0
+#define PK_FMT_S32 1
+#define PK_EMPTY32 0xFFFFFFFFu
+#define PK_S32_REM_BITS 28
+#define PK_S32_REM_MASK 0x0FFFFFFFu
+#define PK_S32_DISP_BITS 4
+#define PK_S32_MAX_DISP 14u
+#define PK_S32_MAX_EB 20u
+#define PK_STASH_SLOTS 65536u
+struct PkKeySpec {
+    uint32_t k;
+    uint32_t fmt;       // PK_FMT_*
+    uint32_t eb;        // S32: key bits embedded in the bucket index = max(0, 2k - 28)
+    uint32_t _pad;
+    unsigned long long *stash;      // [PK_STASH_SLOTS], EMPTY-initialised (S32 only)
+    unsigned int *stash_n;          // number of stashed keys
+};
+
 // ---- kernel launchers (pk_kernels.cu); all asynchronous on `stream` ----
 typedef struct CUstream_st *pk_stream_t;
 void pk_launch_fill_empty(unsigned long long *slots, uint64_t n_slots, pk_stream_t s);
 void pk_launch_pack(const uint8_t *d_ascii, uint64_t len, uint64_t n_words, uint64_t *d_words, uint32_t *d_mask, pk_stream_t s);
 // insert every valid canonical k-mer of positions [0, n) of a packed sequence into table t
-void pk_launch_insert_seq(const uint64_t *d_words, const uint32_t *d_mask, uint64_t n, uint32_t k, PkTable t,
+void pk_launch_insert_seq(const uint64_t *d_words, const uint32_t *d_mask, uint64_t n, PkKeySpec ks, PkTable t, uint32_t g_local,
                           unsigned long long *d_counters /*[3]: inserted, overflow, fail*/, pk_stream_t s);
-void pk_launch_insert_keys(const uint64_t *d_keys, uint64_t n, PkTable t, unsigned long long *d_counters, pk_stream_t s);
+void pk_launch_insert_keys(const uint64_t *d_keys, uint64_t n, PkKeySpec ks, PkTable t, uint32_t g_local,
+                           unsigned long long *d_counters, pk_stream_t s);
 // decode KMC suffix records [rec0, rec0+n) and insert. tables: one PkTable* array on device
 // (local genomes); mode 0: all into tables[local_genome]; mode 1 (bitvec): counter bit j ->
 // global genome first_genome + j, inserted when inside [gbegin, gend).
@@ -52,6 +77,7 @@ struct PkDecodeArgs {
     const uint64_t *d_lut;      // n_lut_slots + 1 entries
     uint64_t n_lut_slots, single_lut;
     uint32_t suf_size, counter_size, rec_size;
+    PkKeySpec ks;
     uint64_t min_count, max_count;
     int bitvec;
     uint32_t first_genome, gbegin, gend;
@@ -60,7 +86,7 @@ struct PkDecodeArgs {
     unsigned long long *d_counters;   // [3 * n_local]: inserted, overflow, fail per local genome
 };
 void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s);
-void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
+void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
                      const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                      uint32_t col_offset, pk_stream_t s);
 void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
@@ -70,7 +96,6 @@ void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n,
                           uint32_t row_stride, pk_stream_t s);
 void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
                            uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
-void pk_launch_table_overflow_count(PkTable t, unsigned long long *d_out, pk_stream_t s);
 
 // ---- partitioned probe (pk_partition.cu) ----
 #define PK_PART_MAX_N (512ull << 20)   // positions per partitioned launch (2^18 partitions of <= 2560 mean fill)
@@ -91,7 +116,16 @@ struct PkPartScratch {
 uint32_t pk_part_obins(void);
 void pk_part_set_variant(int v);
 void pk_part_plan(uint64_t n, PkPartPlan *pl);
-int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
+void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
+void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t off, uint64_t n, PkKeySpec ks,
+                    uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                    const PkPartScratch &sc, pk_stream_t s);
+void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, const PkTable *h_tables,
+                   uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                   const PkPartScratch &sc, int prefetch, pk_stream_t s, struct CUevent_st **evs);
+void pk_part_unpermute(uint32_t bin0, uint32_t bin1, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
+                       uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
+int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
                                 const PkTable *d_tables, const PkTable *h_tables, uint32_t n_local, uint8_t *d_rows,
                                 uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
                                 int prefetch, pk_stream_t s, struct CUevent_st **evs /*6 events or NULL*/);

@@ -71,27 +71,46 @@ void pk_launch_pack(const uint8_t *d_ascii, uint64_t len, uint64_t n_words, uint
 
 // ------------------------------------------------------------------ insert
 // Bucket-granular linear probing: a key lives in the first bucket, starting at its home bucket,
-// that had a free slot when it was inserted. Slots only ever go EMPTY -> key, so a lookup that
-// sees an EMPTY slot in a bucket knows the key is in no later bucket.
-// returns 0 = already present, 1 = inserted in home bucket, 2 = inserted in a later bucket, 3 = table full
-__device__ __forceinline__ int pk_table_insert(const PkTable t, unsigned long long key) {
-    const uint32_t home = __umulhi(pk_hash32(key), t.n_buckets);
+// that had a free slot when it was inserted. Slots only ever go EMPTY -> key and fill in order, so a
+// lookup that sees a free last slot in a bucket knows the key is in no later bucket.
+// returns 0 = already present, 1 = inserted in home bucket, 2 = inserted in a later bucket, 3 = no room
+__device__ __forceinline__ int pk_table_insert(const PkTable t, unsigned long long key, const PkKeySpec ks, uint32_t g) {
+    const uint32_t home = __umulhi(pk_key_hash(key, ks), t.n_buckets);
     uint32_t b = home;
-    for (uint32_t tries = 0; tries < t.n_buckets; ++tries) {
-        volatile unsigned long long *slot = t.slots + 4ull * b;
+    if (ks.fmt == PK_FMT_S64) {
+        for (uint32_t tries = 0; tries < t.n_buckets; ++tries) {
+            volatile unsigned long long *slot = t.slots + 4ull * b;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const unsigned long long cur = slot[i];
-            if (cur == key) return 0;
-            if (cur == PK_EMPTY) {
-                const unsigned long long old = atomicCAS((unsigned long long *)slot + i, PK_EMPTY, key);
-                if (old == PK_EMPTY) return b == home ? 1 : 2;
-                if (old == key) return 0;
+            for (int i = 0; i < 4; i++) {
+                const unsigned long long cur = slot[i];
+                if (cur == key) return 0;
+                if (cur == PK_EMPTY) {
+                    const unsigned long long old = atomicCAS((unsigned long long *)slot + i, PK_EMPTY, key);
+                    if (old == PK_EMPTY) return b == home ? 1 : 2;
+                    if (old == key) return 0;
+                }
+            }
+            b = b + 1 == t.n_buckets ? 0 : b + 1;
+        }
+        return 3;
+    }
+    const uint32_t maxd = pk_max_disp<PK_FMT_S32>(t.n_buckets);
+    for (uint32_t r = 0; r <= maxd; ++r) {
+        const uint32_t want = (uint32_t)pk_target<PK_FMT_S32>(key, r);
+        volatile uint32_t *slot = (uint32_t *)t.slots + 8ull * b;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t cur = slot[i];
+            if (cur == want) return 0;
+            if (cur == PK_EMPTY32) {
+                const uint32_t old = atomicCAS((uint32_t *)slot + i, PK_EMPTY32, want);
+                if (old == PK_EMPTY32) return r == 0 ? 1 : 2;
+                if (old == want) return 0;
             }
         }
         b = b + 1 == t.n_buckets ? 0 : b + 1;
     }
-    return 3;
+    return pk_stash_insert(ks, g, key);     // 15 consecutive full buckets: engine-wide stash
 }
 
 __device__ __forceinline__ void pk_flush_counts(unsigned long long *counters, uint32_t ins, uint32_t ovf, uint32_t fail) {
@@ -106,13 +125,13 @@ __device__ __forceinline__ void pk_flush_counts(unsigned long long *counters, ui
 }
 
 __global__ void __launch_bounds__(256) insert_seq_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ mask64,
-                                                         uint64_t n, uint32_t k, PkTable t, unsigned long long *counters) {
+                                                         uint64_t n, PkKeySpec ks, PkTable t, uint32_t g, unsigned long long *counters) {
     uint32_t ins = 0, ovf = 0, fail = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += stride) {
         uint64_t canon;
-        if (!pk_window(words, mask64, p, k, canon)) continue;
-        const int r = pk_table_insert(t, canon);
+        if (!pk_window(words, mask64, p, ks.k, canon)) continue;
+        const int r = pk_table_insert(t, canon, ks, g);
         ins += r == 1 || r == 2; ovf += r == 2; fail += r == 3;
     }
     pk_flush_counts(counters, ins, ovf, fail);
@@ -121,25 +140,26 @@ static unsigned grid_for(uint64_t n, unsigned per_block = 256, unsigned cap = 14
     const uint64_t g = (n + per_block - 1) / per_block;
     return (unsigned)(g < 1 ? 1 : g > cap ? cap : g);
 }
-void pk_launch_insert_seq(const uint64_t *d_words, const uint32_t *d_mask, uint64_t n, uint32_t k, PkTable t,
+void pk_launch_insert_seq(const uint64_t *d_words, const uint32_t *d_mask, uint64_t n, PkKeySpec ks, PkTable t, uint32_t g,
                           unsigned long long *d_counters, pk_stream_t s) {
     if (!n) return;
-    insert_seq_kernel<<<grid_for(n), 256, 0, s>>>(d_words, (const uint64_t *)d_mask, n, k, t, d_counters);
+    insert_seq_kernel<<<grid_for(n), 256, 0, s>>>(d_words, (const uint64_t *)d_mask, n, ks, t, g, d_counters);
 }
 
-__global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t *__restrict__ keys, uint64_t n, PkTable t,
-                                                          unsigned long long *counters) {
+__global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t *__restrict__ keys, uint64_t n, PkKeySpec ks, PkTable t,
+                                                          uint32_t g, unsigned long long *counters) {
     uint32_t ins = 0, ovf = 0, fail = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int r = pk_table_insert(t, keys[i]);
+        const int r = pk_table_insert(t, keys[i], ks, g);
         ins += r == 1 || r == 2; ovf += r == 2; fail += r == 3;
     }
     pk_flush_counts(counters, ins, ovf, fail);
 }
-void pk_launch_insert_keys(const uint64_t *d_keys, uint64_t n, PkTable t, unsigned long long *d_counters, pk_stream_t s) {
+void pk_launch_insert_keys(const uint64_t *d_keys, uint64_t n, PkKeySpec ks, PkTable t, uint32_t g, unsigned long long *d_counters,
+                           pk_stream_t s) {
     if (!n) return;
-    insert_keys_kernel<<<grid_for(n), 256, 0, s>>>(d_keys, n, t, d_counters);
+    insert_keys_kernel<<<grid_for(n), 256, 0, s>>>(d_keys, n, ks, t, g, d_counters);
 }
 
 // KMC record r (global index) belongs to LUT slot j iff lut[j] <= r < lut[j+1]; its prefix is
@@ -167,7 +187,7 @@ __global__ void __launch_bounds__(256) decode_insert_kernel(PkDecodeArgs a) {
             if (cnt < a.min_count || cnt > a.max_count) continue;   // kmc_file.cpp:487 / :1396
         }
         if (!a.bitvec) {
-            const int rr = pk_table_insert(a.d_tables[a.local_genome], key);
+            const int rr = pk_table_insert(a.d_tables[a.local_genome], key, a.ks, a.local_genome);
             unsigned long long *c = a.d_counters + 3 * a.local_genome;
             if (rr == 1 || rr == 2) atomicAdd(c, 1ull);
             if (rr == 2) atomicAdd(c + 1, 1ull);
@@ -179,7 +199,7 @@ __global__ void __launch_bounds__(256) decode_insert_kernel(PkDecodeArgs a) {
                 bits &= bits - 1;
                 const uint32_t g = a.first_genome + j;
                 if (g < a.gbegin || g >= a.gend) continue;
-                const int rr = pk_table_insert(a.d_tables[g - a.gbegin], key);
+                const int rr = pk_table_insert(a.d_tables[g - a.gbegin], key, a.ks, g - a.gbegin);
                 unsigned long long *c = a.d_counters + 3 * (g - a.gbegin);
                 if (rr == 1 || rr == 2) atomicAdd(c, 1ull);
                 if (rr == 2) atomicAdd(c + 1, 1ull);
@@ -193,45 +213,20 @@ void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s) {
     decode_insert_kernel<<<grid_for(a.n), 256, 0, s>>>(a);
 }
 
-__global__ void __launch_bounds__(256) overflow_count_kernel(PkTable t, unsigned long long *out) {
-    uint32_t ovf = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n = 4ull * t.n_buckets;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned long long key = t.slots[i];
-        if (key != PK_EMPTY && __umulhi(pk_hash32(key), t.n_buckets) != (uint32_t)(i >> 2)) ovf++;
-    }
-    ovf = __reduce_add_sync(0xffffffffu, ovf);
-    if ((threadIdx.x & 31) == 0 && ovf) atomicAdd(out, (unsigned long long)ovf);
-}
-void pk_launch_table_overflow_count(PkTable t, unsigned long long *d_out, pk_stream_t s) {
-    overflow_count_kernel<<<grid_for(4ull * t.n_buckets), 256, 0, s>>>(t, d_out);
-}
-
 // ------------------------------------------------------------------ probe (direct)
-__device__ __noinline__ bool pk_probe_slow(const PkTable t, unsigned long long key, uint32_t b) {
-    // the home bucket was full and did not hold the key: walk on until a hit or a free slot
-    for (uint32_t tries = 1; tries < t.n_buckets; ++tries) {
-        b = b + 1 == t.n_buckets ? 0 : b + 1;
-        const u64x4 v = pk_ld_bucket(t.slots + 4ull * b);
-        if (v.a == key || v.b == key || v.c == key || v.d == key) return true;
-        if (v.a == PK_EMPTY || v.b == PK_EMPTY || v.c == PK_EMPTY || v.d == PK_EMPTY) return false;
-    }
-    return false;
-}
-
 // One thread per position; for each local genome one 32 B bucket load (LDG.256), U loads in
 // flight per thread. Row bits accumulate in a register and are stored once per 32 genomes.
-template <int U>
+template <int U, int FMT>
 __global__ void __launch_bounds__(256) probe_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ mask64,
-                                                    uint64_t p0, uint64_t n, uint32_t k,
+                                                    uint64_t p0, uint64_t n, PkKeySpec ks,
                                                     const PkTable *__restrict__ tables, uint32_t n_local,
                                                     uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t col_offset) {
     const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
     if (i >= n) return;
     uint64_t canon = 0;
-    const bool valid = pk_window(words, mask64, p0 + i, k, canon);
-    const uint32_t h = pk_hash32(canon);
+    const bool valid = pk_window(words, mask64, p0 + i, ks.k, canon);
+    const uint32_t h = pk_key_hash(canon, ks);
+    const uint64_t target = pk_target<FMT>(canon, 0);
     const uint32_t nbl = (n_local + 7) / 8;
     uint8_t *dst = rows + i * row_stride + col_offset;
     const bool al4 = ((row_stride | col_offset) & 3) == 0;
@@ -241,21 +236,18 @@ __global__ void __launch_bounds__(256) probe_kernel(const uint64_t *__restrict__
         if (valid) {
             for (uint32_t j0 = 0; j0 < ng; j0 += U) {
                 u64x4 v[U];
-                uint32_t b[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (j0 + u < ng) {
                         const PkTable t = tables[g0 + j0 + u];
-                        b[u] = __umulhi(h, t.n_buckets);
-                        v[u] = pk_ld_bucket(t.slots + 4ull * b[u]);
+                        v[u] = pk_ld_bucket((const char *)t.slots + 32ull * __umulhi(h, t.n_buckets));
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (j0 + u < ng) {
-                        bool hit = v[u].a == canon || v[u].b == canon || v[u].c == canon || v[u].d == canon;
-                        if (!hit && v[u].a != PK_EMPTY && v[u].b != PK_EMPTY && v[u].c != PK_EMPTY && v[u].d != PK_EMPTY)
-                            hit = pk_probe_slow(tables[g0 + j0 + u], canon, b[u]);
+                        bool hit = pk_bucket_hit<FMT>(v[u], target);
+                        if (!hit && pk_bucket_full<FMT>(v[u])) hit = pk_lookup<FMT>(tables[g0 + j0 + u], canon, h, g0 + j0 + u, ks);
                         bits |= (uint32_t)hit << (j0 + u);
                     }
                 }
@@ -269,15 +261,19 @@ __global__ void __launch_bounds__(256) probe_kernel(const uint64_t *__restrict__
         }
     }
 }
-void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
+void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
                      const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                      uint32_t col_offset, pk_stream_t s) {
     if (!n) return;
     const unsigned grid = (unsigned)((n + 255) / 256);
-    if (n_local <= 4)
-        probe_kernel<4><<<grid, 256, 0, s>>>(d_words, (const uint64_t *)d_mask, p0, n, k, d_tables, n_local, d_rows, row_stride, col_offset);
-    else
-        probe_kernel<8><<<grid, 256, 0, s>>>(d_words, (const uint64_t *)d_mask, p0, n, k, d_tables, n_local, d_rows, row_stride, col_offset);
+    const uint64_t *m64 = (const uint64_t *)d_mask;
+    if (ks.fmt == PK_FMT_S32) {
+        if (n_local <= 4) probe_kernel<4, PK_FMT_S32><<<grid, 256, 0, s>>>(d_words, m64, p0, n, ks, d_tables, n_local, d_rows, row_stride, col_offset);
+        else probe_kernel<8, PK_FMT_S32><<<grid, 256, 0, s>>>(d_words, m64, p0, n, ks, d_tables, n_local, d_rows, row_stride, col_offset);
+    } else {
+        if (n_local <= 4) probe_kernel<4, PK_FMT_S64><<<grid, 256, 0, s>>>(d_words, m64, p0, n, ks, d_tables, n_local, d_rows, row_stride, col_offset);
+        else probe_kernel<8, PK_FMT_S64><<<grid, 256, 0, s>>>(d_words, m64, p0, n, ks, d_tables, n_local, d_rows, row_stride, col_offset);
+    }
 }
 
 // ------------------------------------------------------------------ reduce

@@ -143,8 +143,8 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
 struct PartArgs {
     const uint64_t *words;
     const uint64_t *mask64;
-    uint64_t p0, n;
-    uint32_t k;
+    uint64_t p0, off, n;            // batch base position, first position of this launch (relative), count
+    PkKeySpec ks;
     uint32_t pb1, pb2;              // coarse / fine bits
     uint32_t cap1, cap2;            // region capacities
     uint2 *buf1, *buf2, *spill;
@@ -166,12 +166,12 @@ __global__ void __launch_bounds__(PT_THREADS, 3) partition_seq_kernel(PartArgs a
     uint32_t h[PT_IPT], pos[PT_IPT], valid = 0;
 #pragma unroll
     for (int j = 0; j < PT_IPT; j++) {
-        const uint64_t i = base + 32 * j;
+        const uint64_t i = a.off + base + 32 * j;
         h[j] = 0; pos[j] = (uint32_t)i;
-        if (i < a.n) {
+        if (i < a.off + a.n) {
             uint64_t canon;
-            if (pk_window(a.words, a.mask64, a.p0 + i, a.k, canon)) {
-                h[j] = pk_hash32(canon);
+            if (pk_window(a.words, a.mask64, a.p0 + i, a.ks.k, canon)) {
+                h[j] = pk_key_hash(canon, a.ks);
                 valid |= 1u << j;
             } else {
                 uint8_t *dst = a.rows + i * a.row_stride + a.col_offset;
@@ -209,411 +209,59 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs 
 }
 
 // ------------------------------------------------------------------ K3: probe one partition per block
-#define PP_THREADS 256
-#define PP_CAP 3072                       // items per fine partition (shared memory: 16 B each)
-#define PP_IPT (PP_CAP / PP_THREADS)      // 12
-#define PP_ILP 4
 #define PP_OBINS 128                      // position bins of the un-permute lists
-#define PP_WARPS (PP_THREADS / 32)
+#define PS_BINS 1024                      // counting-sort bins of the bucket-sorted variant
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// One launch covers one group of <= 32 genomes; their table descriptors travel as kernel parameters
+// (constant bank: no LDS/LDG per probe).
 struct ProbeArgs {
-    const uint2 *buf;                 // regions of `cap` items
+    const uint2 *buf;                 // regions of `cap` (hash, pos) items
     const uint32_t *counts;           // per-region fill (may exceed cap: clamp); NULL => flat list of *flat_total items
     const unsigned long long *flat_total;
-    uint32_t cap;
-    uint32_t n_regions;               // regions mode
+    uint32_t cap, n_regions;
     uint32_t pb;                      // total partition bits (regions mode; 0 disables prefetch)
     const uint64_t *words;
     uint64_t p0;
-    uint32_t k;
-    const PkTable *tables;
-    uint32_t n_local;
+    PkKeySpec ks;
+    uint32_t ng, grp;                 // genomes in this launch, column group (bytes 4*grp.. of a row)
     uint8_t *rows;
     uint32_t row_stride, col_offset, nbl;
     int prefetch;
     // un-permute: instead of scattering row bytes over the whole bitmap (32x write amplification and a
-    // read-modify-write per byte in DRAM), results are appended as (pos, bits) to lists binned by
-    // pos >> out_shift; unpermute_kernel then scatters each list inside its own L2-resident slice
+    // read-modify-write per byte in DRAM: measured 4.3 GB extra reads + 4.6 GB writes on configs[1]),
+    // results are appended as (pos, bits) to lists binned by pos >> out_shift; unpermute_kernel then
+    // scatters each list inside its own L2-resident slice of the bitmap
     uint2 *out_list;                  // [(grp * PP_OBINS + bin) << out_shift]
     uint32_t *out_cursor;             // [n_groups * PP_OBINS]
-    uint32_t out_shift;
-};
-
-__device__ __noinline__ bool pk_probe_slow_ca(const PkTable t, unsigned long long key, uint32_t b) {
-    for (uint32_t tries = 1; tries < t.n_buckets; ++tries) {
-        b = b + 1 == t.n_buckets ? 0 : b + 1;
-        const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * b);
-        if (v.a == key || v.b == key || v.c == key || v.d == key) return true;
-        if (v.a == PK_EMPTY || v.b == PK_EMPTY || v.c == PK_EMPTY || v.d == PK_EMPTY) return false;
-    }
-    return false;
-}
-
-__global__ void __launch_bounds__(PP_THREADS, 3) probe_part_kernel(ProbeArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint64_t *s_canon = (uint64_t *)smem_raw;                    // [PP_CAP]
-    uint32_t *s_h = (uint32_t *)(s_canon + PP_CAP);              // [PP_CAP]
-    uint32_t *s_pos = s_h + PP_CAP;                              // [PP_CAP]
-    __shared__ uint16_t o_wc[PP_WARPS][PP_OBINS];
-    __shared__ uint32_t o_gb[PP_OBINS];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint64_t nreg = a.n_regions;
-    unsigned long long flat = 0;
-    if (!a.counts) { flat = *a.flat_total; nreg = (flat + a.cap - 1) / a.cap; }
-    for (uint64_t q = blockIdx.x; q < nreg; q += gridDim.x) {
-        uint32_t cnt;
-        if (a.counts) cnt = min(a.counts[q], a.cap);
-        else cnt = (uint32_t)min((unsigned long long)a.cap, flat - q * a.cap);
-        if (cnt == 0) continue;
-        const uint2 *src = a.buf + q * (uint64_t)a.cap;
-        for (uint32_t i = tid; i < cnt; i += PP_THREADS) {
-            const uint2 it = src[i];
-            const uint64_t p = a.p0 + it.y;
-            const uint64_t w0 = a.words[p >> 5], w1 = a.words[(p >> 5) + 1];
-            const uint32_t s = 2 * ((uint32_t)p & 31);
-            const uint64_t x = (w0 << s) | ((w1 >> 1) >> (63 - s));
-            const uint64_t fwd = x >> (64 - 2 * a.k);
-            const uint64_t rc = pk_revcomp(fwd, a.k);
-            s_canon[i] = fwd < rc ? fwd : rc;
-            s_h[i] = it.x;
-            s_pos[i] = it.y;
-        }
-        __syncthreads();
-        const bool do_pf = a.prefetch && a.counts && a.pb;
-        // hash range of this partition: [q << (32-pb), ((q+1) << (32-pb)) - 1]
-        const uint32_t h_lo = do_pf ? (uint32_t)(q << (32 - a.pb)) : 0;
-        const uint32_t h_hi = do_pf ? (uint32_t)(((q + 1) << (32 - a.pb)) - 1) : 0;
-        if (do_pf && tid == 0) {
-            const PkTable t = a.tables[0];
-            const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
-            if (b1 - b0 < 8192) l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
-        }
-        for (uint32_t g0 = 0; g0 < a.n_local; g0 += 32) {
-            uint32_t bits[PP_IPT];
-#pragma unroll
-            for (int j = 0; j < PP_IPT; j++) bits[j] = 0;
-            const uint32_t ng = min(32u, a.n_local - g0);
-            for (uint32_t gg = 0; gg < ng; gg++) {
-                const PkTable t = a.tables[g0 + gg];
-                if (do_pf && tid == 0 && g0 + gg + 1 < a.n_local) {
-                    const PkTable tn = a.tables[g0 + gg + 1];
-                    const uint32_t b0 = __umulhi(h_lo, tn.n_buckets), b1 = __umulhi(h_hi, tn.n_buckets);
-                    if (b1 - b0 < 8192) l2_prefetch_bulk(tn.slots + 4ull * b0, (b1 - b0 + 1) * 32);   // windows <= 256 KB
-                }
-#pragma unroll
-                for (int j0 = 0; j0 < PP_IPT; j0 += PP_ILP) {
-                    u64x4 v[PP_ILP];
-                    uint32_t b[PP_ILP];
-#pragma unroll
-                    for (int u = 0; u < PP_ILP; u++) {
-                        const uint32_t i = tid + (j0 + u) * PP_THREADS;
-                        if (i < cnt) {
-                            b[u] = __umulhi(s_h[i], t.n_buckets);
-                            v[u] = pk_ld_bucket_ca(t.slots + 4ull * b[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < PP_ILP; u++) {
-                        const uint32_t i = tid + (j0 + u) * PP_THREADS;
-                        if (i < cnt) {
-                            const uint64_t key = s_canon[i];
-                            bool hit = v[u].a == key || v[u].b == key || v[u].c == key || v[u].d == key;
-                            if (!hit && v[u].a != PK_EMPTY && v[u].b != PK_EMPTY && v[u].c != PK_EMPTY && v[u].d != PK_EMPTY)
-                                hit = pk_probe_slow_ca(t, key, b[u]);
-                            bits[j0 + u] |= (uint32_t)hit << gg;
-                        }
-                    }
-                }
-            }
-            if (a.out_list) {
-                // append (pos, bits) to the list of bin = pos >> out_shift: rank inside the block by
-                // warp match, one atomicAdd per (block, bin) reserves the run
-                for (uint32_t q = tid; q < PP_WARPS * PP_OBINS; q += PP_THREADS) (&o_wc[0][0])[q] = 0;
-                __syncthreads();
-                uint16_t rank[PP_IPT];
-#pragma unroll
-                for (int j = 0; j < PP_IPT; j++) {
-                    const uint32_t i = tid + j * PP_THREADS;
-                    const bool v = i < cnt;
-                    const uint32_t bin = v ? s_pos[i] >> a.out_shift : 0xffffffffu;
-                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-                    const uint32_t leader = __ffs(peers) - 1;
-                    uint32_t old = 0;
-                    if (v && lane == leader) {
-                        old = o_wc[wid][bin];
-                        o_wc[wid][bin] = (uint16_t)(old + __popc(peers));
-                    }
-                    old = __shfl_sync(0xffffffffu, old, leader);
-                    rank[j] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
-                    __syncwarp();
-                }
-                __syncthreads();
-                for (uint32_t b = tid; b < PP_OBINS; b += PP_THREADS) {
-                    uint32_t run = 0;
-#pragma unroll
-                    for (int ww = 0; ww < PP_WARPS; ww++) {
-                        const uint32_t t = o_wc[ww][b];
-                        o_wc[ww][b] = (uint16_t)run;
-                        run += t;
-                    }
-                    if (run) o_gb[b] = atomicAdd(&a.out_cursor[(g0 / 32) * PP_OBINS + b], run);
-                }
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < PP_IPT; j++) {
-                    const uint32_t i = tid + j * PP_THREADS;
-                    if (i < cnt) {
-                        const uint32_t pos = s_pos[i], bin = pos >> a.out_shift;
-                        const uint64_t slot = (((uint64_t)(g0 / 32) * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + o_wc[wid][bin] + rank[j];
-                        a.out_list[slot] = make_uint2(pos, bits[j]);
-                    }
-                }
-                __syncthreads();
-            } else {
-                const uint32_t nb = min(4u, a.nbl - g0 / 8);
-                const bool al4 = nb == 4 && ((a.row_stride | a.col_offset) & 3) == 0;
-#pragma unroll
-                for (int j = 0; j < PP_IPT; j++) {
-                    const uint32_t i = tid + j * PP_THREADS;
-                    if (i < cnt) {
-                        uint8_t *dst = a.rows + (uint64_t)s_pos[i] * a.row_stride + a.col_offset + g0 / 8;
-                        if (al4) *(uint32_t *)dst = bits[j];
-                        else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(bits[j] >> (8 * qb));
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------ K3, item-major variant
-// One item per thread at a time, GILP genomes in flight for it: a block's round trips to memory drop
-// from (genomes x rounds) to (items-per-thread x genome-groups); the walk-on to the next bucket is
-// batched over the GILP genomes instead of serialised. Partitions are smaller (<= T*IPT items) so that
-// the GILP windows a block has live stay small (8 KB each at 2^18 partitions of a 2 GB table).
-template <int T, int IPT, int GILP, int MINB>
-__global__ void __launch_bounds__(T, MINB) probe_item_kernel(ProbeArgs a) {
-    __shared__ uint16_t o_wc[T / 32][PP_OBINS];
-    __shared__ uint32_t o_gb[PP_OBINS];
-    __shared__ PkTable s_tb[32];
-    constexpr int QCAP = T * IPT;
-    __shared__ uint32_t s_bits[QCAP];              // results of the deferred walk-ons, by item
-    __shared__ unsigned long long q_key[QCAP];     // deferred walk-on queue
-    __shared__ uint32_t q_h[QCAP], q_meta[QCAP];
-    __shared__ uint32_t q_n;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint64_t nreg = a.n_regions;
-    unsigned long long flat = 0;
-    if (!a.counts) { flat = *a.flat_total; nreg = (flat + a.cap - 1) / a.cap; }
-    for (uint64_t q = blockIdx.x; q < nreg; q += gridDim.x) {
-        uint32_t cnt;
-        if (a.counts) cnt = min(a.counts[q], a.cap);
-        else cnt = (uint32_t)min((unsigned long long)a.cap, flat - q * a.cap);
-        if (cnt == 0) continue;
-        const bool do_pf = a.prefetch && a.counts && a.pb;
-        const uint32_t h_lo = do_pf ? (uint32_t)(q << (32 - a.pb)) : 0;
-        const uint32_t h_hi = do_pf ? (uint32_t)(((q + 1) << (32 - a.pb)) - 1) : 0;
-        if (do_pf && tid < min((uint32_t)GILP, a.n_local)) {
-            const PkTable t = a.tables[tid];
-            const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
-            if (b1 - b0 < 8192) l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
-        }
-        const uint2 *src = a.buf + q * (uint64_t)a.cap;
-        uint64_t canon[IPT];
-        uint32_t h[IPT], pos[IPT];
-#pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            const uint32_t i = tid + j * T;
-            canon[j] = 0; h[j] = 0; pos[j] = 0;
-            if (i < cnt) {
-                const uint2 it = src[i];
-                const uint64_t p = a.p0 + it.y;
-                const uint64_t w0 = a.words[p >> 5], w1 = a.words[(p >> 5) + 1];
-                const uint32_t s = 2 * ((uint32_t)p & 31);
-                const uint64_t x = (w0 << s) | ((w1 >> 1) >> (63 - s));
-                const uint64_t fwd = x >> (64 - 2 * a.k);
-                const uint64_t rc = pk_revcomp(fwd, a.k);
-                canon[j] = fwd < rc ? fwd : rc;
-                h[j] = it.x; pos[j] = it.y;
-            }
-        }
-        for (uint32_t g0 = 0; g0 < a.n_local; g0 += 32) {
-            uint32_t bits[IPT];
-#pragma unroll
-            for (int j = 0; j < IPT; j++) bits[j] = 0;
-            const uint32_t ng = min(32u, a.n_local - g0);
-            __syncthreads();
-            if (tid < 32) s_tb[tid] = a.tables[min(g0 + tid, a.n_local - 1)];
-            if (tid == 0) q_n = 0;
-            for (uint32_t qq = tid; qq < (uint32_t)QCAP; qq += T) s_bits[qq] = 0;
-            __syncthreads();
-            for (uint32_t gs = 0; gs < ng; gs += GILP) {
-                if (do_pf && tid < GILP && g0 + gs + GILP + tid < a.n_local) {      // next group's windows
-                    const PkTable t = a.tables[g0 + gs + GILP + tid];
-                    const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
-                    if (b1 - b0 < 8192) l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
-                }
-                const PkTable *tb = s_tb + gs;            // descriptors stay in shared memory (uniform LDS)
-                const uint32_t nu = min((uint32_t)GILP, ng - gs);
-#pragma unroll
-                for (int j = 0; j < IPT; j++) {
-                    const uint32_t i = tid + j * T;
-                    if (i < cnt) {
-                        u64x4 v[GILP];
-                        const uint64_t key = canon[j];
-#pragma unroll
-                        for (int u = 0; u < GILP; u++) {
-                            if ((uint32_t)u < nu)
-                                v[u] = pk_ld_bucket_ca(tb[u].slots + 4ull * __umulhi(h[j], tb[u].n_buckets));
-                        }
-#pragma unroll
-                        for (int u = 0; u < GILP; u++) {
-                            if ((uint32_t)u < nu) {
-                                const bool hit = v[u].a == key || v[u].b == key || v[u].c == key || v[u].d == key;
-                                bits[j] |= (uint32_t)hit << (gs + u);
-                                // slots fill in order, so the bucket is full iff its last slot is taken. A full
-                                // bucket without the key means the key may sit in a later bucket: that rare
-                                // walk-on is queued and resolved densely below instead of diverging here.
-                                if (!hit && v[u].d != PK_EMPTY) {
-                                    const uint32_t slot = atomicAdd(&q_n, 1u);
-                                    if (slot < QCAP) {
-                                        q_key[slot] = key;
-                                        q_h[slot] = h[j];
-                                        q_meta[slot] = (i << 5) | (gs + u);
-                                    } else {            // queue full (pathological): walk here
-                                        const uint32_t nbk = tb[u].n_buckets;
-                                        uint32_t bb = __umulhi(h[j], nbk);
-                                        for (uint32_t r = 1; r < nbk; r++) {
-                                            bb = bb + 1 == nbk ? 0 : bb + 1;
-                                            const u64x4 w = pk_ld_bucket_ca(tb[u].slots + 4ull * bb);
-                                            if (w.a == key || w.b == key || w.c == key || w.d == key) { bits[j] |= 1u << (gs + u); break; }
-                                            if (w.d == PK_EMPTY) break;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            {   // deferred walk-ons, one per thread, all lanes busy
-                const uint32_t nq = min(q_n, (uint32_t)QCAP);
-                for (uint32_t e = tid; e < nq; e += T) {
-                    const uint64_t key = q_key[e];
-                    const uint32_t meta = q_meta[e], g = meta & 31;
-                    const PkTable t = s_tb[g];
-                    const uint32_t b0 = __umulhi(q_h[e], t.n_buckets);
-                    uint32_t bb = b0;
-                    for (uint32_t r = 1; r < t.n_buckets; r++) {
-                        bb = bb + 1 == t.n_buckets ? 0 : bb + 1;
-                        const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * bb);
-                        if (v.a == key || v.b == key || v.c == key || v.d == key) { atomicOr(&s_bits[meta >> 5], 1u << g); break; }
-                        if (v.d == PK_EMPTY) break;
-                    }
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < IPT; j++)
-                if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
-            if (a.out_list) {
-                for (uint32_t qq = tid; qq < (T / 32) * PP_OBINS; qq += T) (&o_wc[0][0])[qq] = 0;
-                __syncthreads();
-                uint16_t rank[IPT];
-#pragma unroll
-                for (int j = 0; j < IPT; j++) {
-                    const bool v = tid + j * T < cnt;
-                    const uint32_t bin = v ? pos[j] >> a.out_shift : 0xffffffffu;
-                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-                    const uint32_t leader = __ffs(peers) - 1;
-                    uint32_t old = 0;
-                    if (v && lane == leader) {
-                        old = o_wc[wid][bin];
-                        o_wc[wid][bin] = (uint16_t)(old + __popc(peers));
-                    }
-                    old = __shfl_sync(0xffffffffu, old, leader);
-                    rank[j] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
-                    __syncwarp();
-                }
-                __syncthreads();
-                for (uint32_t b = tid; b < PP_OBINS; b += T) {
-                    uint32_t run = 0;
-#pragma unroll
-                    for (int ww = 0; ww < T / 32; ww++) {
-                        const uint32_t t = o_wc[ww][b];
-                        o_wc[ww][b] = (uint16_t)run;
-                        run += t;
-                    }
-                    if (run) o_gb[b] = atomicAdd(&a.out_cursor[(g0 / 32) * PP_OBINS + b], run);
-                }
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < IPT; j++) {
-                    if (tid + j * T < cnt) {
-                        const uint32_t bin = pos[j] >> a.out_shift;
-                        const uint64_t slot = (((uint64_t)(g0 / 32) * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + o_wc[wid][bin] + rank[j];
-                        a.out_list[slot] = make_uint2(pos[j], bits[j]);
-                    }
-                }
-                __syncthreads();
-            } else {
-                const uint32_t nb = min(4u, a.nbl - g0 / 8);
-                const bool al4 = nb == 4 && ((a.row_stride | a.col_offset) & 3) == 0;
-#pragma unroll
-                for (int j = 0; j < IPT; j++) {
-                    if (tid + j * T < cnt) {
-                        uint8_t *dst = a.rows + (uint64_t)pos[j] * a.row_stride + a.col_offset + g0 / 8;
-                        if (al4) *(uint32_t *)dst = bits[j];
-                        else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(bits[j] >> (8 * qb));
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------ K3, bucket-sorted variant
-// The L1TEX tag stage handles ~1 sector per clock per SM, and with one 32 B bucket per lane every probe is
-// a sector of its own (profiles/r1_k3_*.md: l1tex 87 % busy). Here the block first counting-sorts its
-// <= T*IPT items by the hash bits just below the partition bits (shared memory), so the 32 lanes of a warp
-// probe ~16 neighbouring buckets: half the tag lookups, more L1 hits, and DRAM sees 512 B runs.
-// One launch covers one group of <= 32 genomes whose table descriptors travel as kernel parameters
-// (constant bank: no LDS/LDG per probe).
-struct ProbeArgs2 {
-    const uint2 *buf;
-    const uint32_t *counts;
-    const unsigned long long *flat_total;
-    uint32_t cap, n_regions, pb;
-    const uint64_t *words;
-    uint64_t p0;
-    uint32_t k, ng, grp;
-    uint8_t *rows;
-    uint32_t row_stride, col_offset, nbl;
-    int prefetch;
-    uint2 *out_list;
-    uint32_t *out_cursor;
     uint32_t out_shift;
     PkTable tabs[32];
 };
 
-#define PS_BINS 1024
-template <int T, int IPT, int MINB>
-__global__ void __launch_bounds__(T, MINB) probe_sorted_kernel(const __grid_constant__ ProbeArgs2 a) {
+// K3. One block per fine partition (<= T*IPT items). Items go to registers (k-mer re-derived from the
+// L2-resident packed sequence); genome by genome every probe of the block lands in that partition's
+// window of the table (8 KB at 2^18 partitions of a 2 GB table) while a TMA bulk prefetch pulls the
+// window of the genome after next into L2. One load in flight per thread and many warps beat ILP here
+// (measured: 8/4/2/1 loads in flight -> 15.9/9.7/8.4/6.9 ms). A full home bucket without the key (the
+// key may sit in a later bucket) is rare; those walk-ons are queued in shared memory and resolved by all
+// lanes together instead of diverging inside the probe loop (-40 % issued instructions).
+// SORT = 1 first counting-sorts the items by the hash bits below the partition bits, so that the lanes of
+// a warp probe neighbouring buckets (half the L1 tag lookups; pays off once the tables are small enough
+// for the kernel to be L1-bound rather than DRAM-bound).
+template <int T, int IPT, int FMT, int SORT, int MINB>
+__global__ void __launch_bounds__(T, MINB) probe_part_kernel(const __grid_constant__ ProbeArgs a) {
     constexpr int CAP = T * IPT;
-    __shared__ unsigned long long s_canon[CAP];
-    __shared__ uint32_t s_h[CAP], s_pos[CAP], s_bits[CAP];
-    __shared__ uint32_t s_cnt[PS_BINS];
-    __shared__ unsigned long long q_key[CAP];
-    __shared__ uint32_t q_meta[CAP], q_h[CAP];
+    __shared__ uint32_t s_bits[CAP];               // results of the deferred walk-ons, by item
+    __shared__ unsigned long long q_key[CAP];      // deferred walk-on queue: canonical k-mer,
+    __shared__ uint32_t q_meta[CAP], q_h[CAP];     //   (item << 5 | genome), hash
     __shared__ uint32_t q_n, s_ws[T / 32];
     __shared__ uint16_t o_wc[T / 32][PP_OBINS];
     __shared__ uint32_t o_gb[PP_OBINS];
+    __shared__ unsigned long long s_canon[SORT ? CAP : 1];
+    __shared__ uint32_t s_h[SORT ? CAP : 1], s_pos[SORT ? CAP : 1], s_cnt[SORT ? PS_BINS : 1];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint64_t nreg = a.n_regions;
     unsigned long long flat = 0;
@@ -632,9 +280,9 @@ __global__ void __launch_bounds__(T, MINB) probe_sorted_kernel(const __grid_cons
             const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
             if (b1 - b0 < 8192) l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
         }
-        // ---- load items, derive canonical k-mers, counting sort by the next 10 hash bits
-        for (uint32_t i = tid; i < PS_BINS; i += T) s_cnt[i] = 0;
+        if (SORT) for (uint32_t i = tid; i < PS_BINS; i += T) s_cnt[i] = 0;
         for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
+        for (uint32_t i = tid; i < (T / 32) * PP_OBINS; i += T) (&o_wc[0][0])[i] = 0;
         if (tid == 0) q_n = 0;
         __syncthreads();
         const uint2 *src = a.buf + q * (uint64_t)a.cap;
@@ -646,54 +294,51 @@ __global__ void __launch_bounds__(T, MINB) probe_sorted_kernel(const __grid_cons
             canon[j] = 0; h[j] = 0; pos[j] = 0; rnk[j] = 0;
             if (i < cnt) {
                 const uint2 it = src[i];
-                const uint64_t p = a.p0 + it.y;
-                const uint64_t w0 = a.words[p >> 5], w1 = a.words[(p >> 5) + 1];
-                const uint32_t sh = 2 * ((uint32_t)p & 31);
-                const uint64_t x = (w0 << sh) | ((w1 >> 1) >> (63 - sh));
-                const uint64_t fwd = x >> (64 - 2 * a.k);
-                const uint64_t rc = pk_revcomp(fwd, a.k);
-                canon[j] = fwd < rc ? fwd : rc;
+                canon[j] = pk_canon_at(a.words, a.p0 + it.y, a.ks.k);
                 h[j] = it.x; pos[j] = it.y;
-                rnk[j] = atomicAdd(&s_cnt[(it.x >> sshift) & (PS_BINS - 1)], 1u);
+                if (SORT) rnk[j] = atomicAdd(&s_cnt[(it.x >> sshift) & (PS_BINS - 1)], 1u);
             }
         }
-        __syncthreads();
-        {   // exclusive scan of s_cnt[PS_BINS], PS_BINS / T bins per thread
-            constexpr int BPT = PS_BINS / T;
-            uint32_t c[BPT], sum = 0;
-#pragma unroll
-            for (int b = 0; b < BPT; b++) { c[b] = s_cnt[tid * BPT + b]; sum += c[b]; }
-            uint32_t inc = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= (uint32_t)o) inc += y;
-            }
-            if (lane == 31) s_ws[wid] = inc;
+        if (SORT) {
             __syncthreads();
-            uint32_t off = inc - sum;
+            {   // exclusive scan of s_cnt[PS_BINS], PS_BINS / T bins per thread
+                constexpr int BPT = PS_BINS / T;
+                uint32_t c[BPT], sum = 0;
 #pragma unroll
-            for (int ww = 0; ww < T / 32; ww++) off += ww < (int)wid ? s_ws[ww] : 0;
+                for (int b = 0; b < BPT; b++) { c[b] = s_cnt[tid * BPT + b]; sum += c[b]; }
+                uint32_t inc = sum;
 #pragma unroll
-            for (int b = 0; b < BPT; b++) { s_cnt[tid * BPT + b] = off; off += c[b]; }
-        }
-        __syncthreads();
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= (uint32_t)o) inc += y;
+                }
+                if (lane == 31) s_ws[wid] = inc;
+                __syncthreads();
+                uint32_t off = inc - sum;
 #pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            if (tid + j * T < cnt) {
-                const uint32_t d = s_cnt[(h[j] >> sshift) & (PS_BINS - 1)] + rnk[j];
-                s_canon[d] = canon[j]; s_h[d] = h[j]; s_pos[d] = pos[j];
+                for (int ww = 0; ww < T / 32; ww++) off += ww < (int)wid ? s_ws[ww] : 0;
+#pragma unroll
+                for (int b = 0; b < BPT; b++) { s_cnt[tid * BPT + b] = off; off += c[b]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                if (tid + j * T < cnt) {
+                    const uint32_t d = s_cnt[(h[j] >> sshift) & (PS_BINS - 1)] + rnk[j];
+                    s_canon[d] = canon[j]; s_h[d] = h[j]; s_pos[d] = pos[j];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                const uint32_t i = tid + j * T;
+                if (i < cnt) { canon[j] = s_canon[i]; h[j] = s_h[i]; pos[j] = s_pos[i]; }
             }
         }
-        __syncthreads();
         uint32_t bits[IPT];
 #pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            const uint32_t i = tid + j * T;
-            bits[j] = 0;
-            if (i < cnt) { canon[j] = s_canon[i]; h[j] = s_h[i]; }
-        }
-        // ---- probe: genome by genome, neighbouring lanes hit neighbouring buckets
+        for (int j = 0; j < IPT; j++) bits[j] = 0;
+        // ---- probe, genome by genome
         for (uint32_t g = 0; g < a.ng; g++) {
             const PkTable t = a.tabs[g];
             if (do_pf && tid == 0 && g + 2 < a.ng) {
@@ -706,21 +351,14 @@ __global__ void __launch_bounds__(T, MINB) probe_sorted_kernel(const __grid_cons
                 const uint32_t i = tid + j * T;
                 if (i < cnt) {
                     const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
-                    const uint64_t key = canon[j];
-                    const bool hit = v.a == key || v.b == key || v.c == key || v.d == key;
+                    const bool hit = pk_bucket_hit<FMT>(v, pk_target<FMT>(canon[j], 0));
                     bits[j] |= (uint32_t)hit << g;
-                    if (!hit && v.d != PK_EMPTY) {          // full bucket without the key: deferred walk-on
+                    if (!hit && pk_bucket_full<FMT>(v)) {          // deferred walk-on
                         const uint32_t slot = atomicAdd(&q_n, 1u);
                         if (slot < (uint32_t)CAP) {
-                            q_key[slot] = key; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
-                        } else {
-                            uint32_t bb = __umulhi(h[j], t.n_buckets);
-                            for (uint32_t r = 1; r < t.n_buckets; r++) {
-                                bb = bb + 1 == t.n_buckets ? 0 : bb + 1;
-                                const u64x4 w = pk_ld_bucket_ca(t.slots + 4ull * bb);
-                                if (w.a == key || w.b == key || w.c == key || w.d == key) { bits[j] |= 1u << g; break; }
-                                if (w.d == PK_EMPTY) break;
-                            }
+                            q_key[slot] = canon[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
+                        } else if (pk_lookup<FMT>(t, canon[j], h[j], 32 * a.grp + g, a.ks)) {      // queue full (pathological)
+                            bits[j] |= 1u << g;
                         }
                     }
                 }
@@ -730,26 +368,17 @@ __global__ void __launch_bounds__(T, MINB) probe_sorted_kernel(const __grid_cons
         {
             const uint32_t nq = min(q_n, (uint32_t)CAP);
             for (uint32_t e = tid; e < nq; e += T) {
-                const uint64_t key = q_key[e];
                 const uint32_t meta = q_meta[e], g = meta & 31;
-                const PkTable t = a.tabs[g];
-                uint32_t bb = __umulhi(q_h[e], t.n_buckets);
-                for (uint32_t r = 1; r < t.n_buckets; r++) {
-                    bb = bb + 1 == t.n_buckets ? 0 : bb + 1;
-                    const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * bb);
-                    if (v.a == key || v.b == key || v.c == key || v.d == key) { atomicOr(&s_bits[meta >> 5], 1u << g); break; }
-                    if (v.d == PK_EMPTY) break;
-                }
+                if (pk_lookup<FMT>(a.tabs[g], q_key[e], q_h[e], 32 * a.grp + g, a.ks)) atomicOr(&s_bits[meta >> 5], 1u << g);
             }
         }
-        for (uint32_t qq = tid; qq < (T / 32) * PP_OBINS; qq += T) (&o_wc[0][0])[qq] = 0;
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            const uint32_t i = tid + j * T;
-            if (i < cnt) { bits[j] |= s_bits[i]; pos[j] = s_pos[i]; }
-        }
+        for (int j = 0; j < IPT; j++)
+            if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
         if (a.out_list) {
+            // append (pos, bits) to the list of bin = pos >> out_shift: rank inside the block by warp match,
+            // one atomicAdd per (block, bin) reserves the run
             uint16_t rank[IPT];
 #pragma unroll
             for (int j = 0; j < IPT; j++) {
@@ -803,34 +432,27 @@ __global__ void __launch_bounds__(T, MINB) probe_sorted_kernel(const __grid_cons
 }
 
 // variants of K3 selectable at run time (PK_K3_VARIANT) while the design is being tuned
-struct K3Variant { int threads, cap; size_t shmem; void (*fn)(ProbeArgs); void (*fn2)(ProbeArgs2); };
+struct K3Variant { int threads, cap; void (*fn[2])(ProbeArgs); };   // fn[fmt]
+#define K3V(T, IPT, SORT, MINB) {T, T * IPT, {probe_part_kernel<T, IPT, PK_FMT_S64, SORT, MINB>, probe_part_kernel<T, IPT, PK_FMT_S32, SORT, MINB>}}
 static const K3Variant k3_variants[] = {
-    {PP_THREADS, PP_CAP, (size_t)PP_CAP * 16, probe_part_kernel},          // 0: genome-sequential, items in smem
-    {256, 768, 0, probe_item_kernel<256, 3, 8, 2>},                         // 1
-    {256, 768, 0, probe_item_kernel<256, 3, 8, 3>},                         // 2
-    {256, 768, 0, probe_item_kernel<256, 3, 4, 4>},                         // 3
-    {128, 768, 0, probe_item_kernel<128, 6, 4, 8>},                         // 4
-    {512, 1536, 0, probe_item_kernel<512, 3, 4, 2>},                        // 5
-    {256, 1536, 0, probe_item_kernel<256, 6, 4, 4>},                        // 6
-    {256, 768, 0, probe_item_kernel<256, 3, 2, 5>},                         // 7
-    {256, 768, 0, probe_item_kernel<256, 3, 2, 4>},                         // 8
-    {256, 768, 0, probe_item_kernel<256, 3, 4, 3>},                         // 9
-    {256, 768, 0, probe_item_kernel<256, 3, 1, 6>},                         // 10
-    {256, 768, 0, nullptr, probe_sorted_kernel<256, 3, 5>},                 // 11
-    {256, 768, 0, nullptr, probe_sorted_kernel<256, 3, 4>},                 // 12
-    {256, 512, 0, nullptr, probe_sorted_kernel<256, 2, 6>},                 // 13
-    {128, 768, 0, nullptr, probe_sorted_kernel<128, 6, 8>},                 // 14
+    K3V(256, 3, 0, 6),   // 0: unsorted, 6 blocks/SM
+    K3V(256, 3, 1, 5),   // 1: bucket-sorted
+    K3V(256, 3, 0, 5),   // 2
+    K3V(256, 3, 1, 4),   // 3
+    K3V(512, 2, 0, 3),   // 4: cap 1024
+    K3V(512, 2, 1, 2),   // 5
+    K3V(256, 6, 0, 4),   // 6: cap 1536 (2^17 partitions)
 };
-static int g_k3_variant = 10;
+static int g_k3_variant = 0;
 void pk_part_set_variant(int v) { if (v >= 0 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
 
 // K4: scatter the (pos, bits) lists into rows. All blocks of one bin write inside a slice of
 // 2^out_shift rows, which stays in L2 until its sectors are complete.
 #define UP_TILE 4096
 __global__ void __launch_bounds__(256) unpermute_kernel(const uint2 *__restrict__ list, const uint32_t *__restrict__ cursor,
-                                                        uint32_t out_shift, uint8_t *__restrict__ rows, uint32_t row_stride,
-                                                        uint32_t col_offset, uint32_t nbl) {
-    const uint32_t bin = blockIdx.y, grp = blockIdx.z;
+                                                        uint32_t out_shift, uint32_t bin0, uint8_t *__restrict__ rows,
+                                                        uint32_t row_stride, uint32_t col_offset, uint32_t nbl) {
+    const uint32_t bin = bin0 + blockIdx.y, grp = blockIdx.z;
     const uint32_t cnt = cursor[grp * PP_OBINS + bin];
     const uint32_t t0 = blockIdx.x * UP_TILE;
     if (t0 >= cnt) return;
@@ -872,39 +494,55 @@ void pk_part_plan(uint64_t n, PkPartPlan *pl) {
 }
 uint32_t pk_part_obins(void) { return PP_OBINS; }
 
-int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, uint32_t k,
-                                const PkTable *d_tables, const PkTable *h_tables, uint32_t n_local, uint8_t *d_rows,
-                                uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
-                                int prefetch, pk_stream_t s, cudaEvent_t *evs) {
-    if (!n) return 0;
-    static bool attr_set = false;
-    const K3Variant &kv = k3_variants[g_k3_variant];
-    const size_t shmem = kv.shmem;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(probe_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)PP_CAP * 16)) != cudaSuccess) return -1;
-        attr_set = true;
-    }
-    cudaMemsetAsync(sc.cursor1, 0, sizeof(uint32_t) * pl.n_regions1, s);
-    if (pl.n_regions2) cudaMemsetAsync(sc.cursor2, 0, sizeof(uint32_t) * pl.n_regions2, s);
-    cudaMemsetAsync(sc.spill_cursor, 0, sizeof(unsigned long long), s);
-    const uint32_t n_groups = (n_local + 31) / 32;
-    const bool unperm = sc.out_list != nullptr;
-    if (unperm) cudaMemsetAsync(sc.out_cursor, 0, sizeof(uint32_t) * n_groups * PP_OBINS, s);
+// The stages of one partitioned batch. A batch may be fed in pieces (pk_part_append per chromosome, as
+// its bytes arrive) and drained in pieces (pk_part_unpermute per range of position bins).
+static PartArgs make_part_args(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, uint32_t n_local,
+                               uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                               const PkPartScratch &sc) {
     PartArgs a{};
-    a.words = d_words; a.mask64 = (const uint64_t *)d_mask; a.p0 = p0; a.n = n; a.k = k;
+    a.words = d_words; a.mask64 = (const uint64_t *)d_mask; a.p0 = p0; a.ks = ks;
     a.pb1 = pl.pb1; a.pb2 = pl.pb2; a.cap1 = pl.cap1; a.cap2 = pl.cap2;
     a.buf1 = (uint2 *)sc.buf1; a.buf2 = (uint2 *)sc.buf2; a.spill = (uint2 *)sc.spill;
     a.cursor1 = sc.cursor1; a.cursor2 = sc.cursor2; a.spill_cursor = sc.spill_cursor; a.spill_cap = pl.spill_items;
     a.err = sc.err;
     a.rows = d_rows; a.row_stride = row_stride; a.col_offset = col_offset; a.nbl = (n_local + 7) / 8;
-    if (evs) cudaEventRecord(evs[0], s);
-    static const int rank_mode = getenv("PK_PART_RANK") ? atoi(getenv("PK_PART_RANK")) : 1;
-    if (rank_mode) partition_seq_kernel<1><<<(unsigned)((n + PT_TILE - 1) / PT_TILE), PT_THREADS, 0, s>>>(a);
-    else partition_seq_kernel<0><<<(unsigned)((n + PT_TILE - 1) / PT_TILE), PT_THREADS, 0, s>>>(a);
-    if (evs) cudaEventRecord(evs[1], s);
+    return a;
+}
+static int rank_mode() {
+    static const int m = getenv("PK_PART_RANK") ? atoi(getenv("PK_PART_RANK")) : 1;
+    return m;
+}
+
+void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s) {
+    cudaMemsetAsync(sc.cursor1, 0, sizeof(uint32_t) * pl.n_regions1, s);
+    if (pl.n_regions2) cudaMemsetAsync(sc.cursor2, 0, sizeof(uint32_t) * pl.n_regions2, s);
+    cudaMemsetAsync(sc.spill_cursor, 0, sizeof(unsigned long long), s);
+    if (sc.out_list) cudaMemsetAsync(sc.out_cursor, 0, sizeof(uint32_t) * ((n_local + 31) / 32) * PP_OBINS, s);
+}
+
+// K1 over positions [p0 + off, p0 + off + n) of the batch that starts at p0 (pos = off + i)
+void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t off, uint64_t n, PkKeySpec ks,
+                    uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                    const PkPartScratch &sc, pk_stream_t s) {
+    if (!n) return;
+    PartArgs a = make_part_args(d_words, d_mask, p0, ks, n_local, d_rows, row_stride, col_offset, pl, sc);
+    a.off = off; a.n = n;
+    const unsigned grid = (unsigned)((n + PT_TILE - 1) / PT_TILE);
+    if (rank_mode()) partition_seq_kernel<1><<<grid, PT_THREADS, 0, s>>>(a);
+    else partition_seq_kernel<0><<<grid, PT_THREADS, 0, s>>>(a);
+}
+
+// K2 + K3 (+ spill drain) over everything appended so far
+void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, const PkTable *h_tables,
+                   uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                   const PkPartScratch &sc, int prefetch, pk_stream_t s, cudaEvent_t *evs) {
+    const K3Variant &kv = k3_variants[g_k3_variant];
+    void (*k3)(ProbeArgs) = kv.fn[ks.fmt == PK_FMT_S32 ? 1 : 0];
+    const uint32_t n_groups = (n_local + 31) / 32;
+    PartArgs a = make_part_args(d_words, d_mask, p0, ks, n_local, d_rows, row_stride, col_offset, pl, sc);
     if (pl.pb2) {
         dim3 grid((pl.cap1 + PT_TILE - 1) / PT_TILE, pl.n_regions1);
-        if (rank_mode) partition_fine_kernel<1><<<grid, PT_THREADS, 0, s>>>(a);
+        if (rank_mode()) partition_fine_kernel<1><<<grid, PT_THREADS, 0, s>>>(a);
         else partition_fine_kernel<0><<<grid, PT_THREADS, 0, s>>>(a);
     }
     ProbeArgs p{};
@@ -913,45 +551,50 @@ int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask,
     p.cap = pl.pb2 ? pl.cap2 : pl.cap1;
     p.n_regions = pl.pb2 ? pl.n_regions2 : pl.n_regions1;
     p.pb = pl.pb1 + pl.pb2;
-    p.words = d_words; p.p0 = p0; p.k = k; p.tables = d_tables; p.n_local = n_local;
+    p.words = d_words; p.p0 = p0; p.ks = ks;
     p.rows = d_rows; p.row_stride = row_stride; p.col_offset = col_offset; p.nbl = a.nbl;
     p.prefetch = prefetch;
-    p.out_list = unperm ? (uint2 *)sc.out_list : nullptr;
+    p.out_list = (uint2 *)sc.out_list;
     p.out_cursor = sc.out_cursor;
     p.out_shift = pl.out_shift;
     if (evs) cudaEventRecord(evs[2], s);
-    if (kv.fn) {
-        kv.fn<<<p.n_regions, kv.threads, shmem, s>>>(p);
-        if (evs) cudaEventRecord(evs[3], s);
-        ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)
-        sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
-        kv.fn<<<148 * 2, kv.threads, shmem, s>>>(sp);
-    } else {
-        ProbeArgs2 p2{};
-        p2.buf = p.buf; p2.counts = p.counts; p2.cap = p.cap; p2.n_regions = p.n_regions; p2.pb = p.pb;
-        p2.words = d_words; p2.p0 = p0; p2.k = k;
-        p2.rows = d_rows; p2.row_stride = row_stride; p2.col_offset = col_offset; p2.nbl = a.nbl;
-        p2.prefetch = prefetch; p2.out_list = p.out_list; p2.out_cursor = p.out_cursor; p2.out_shift = p.out_shift;
-        for (uint32_t grp = 0; grp < n_groups; grp++) {       // one launch per group of 32 genomes
-            p2.grp = grp; p2.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
-            for (uint32_t g = 0; g < p2.ng; g++) p2.tabs[g] = h_tables[32 * grp + g];
-            kv.fn2<<<p2.n_regions, kv.threads, 0, s>>>(p2);
-        }
-        if (evs) cudaEventRecord(evs[3], s);
-        ProbeArgs2 sp = p2;
-        sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
-        for (uint32_t grp = 0; grp < n_groups; grp++) {
-            sp.grp = grp; sp.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
-            for (uint32_t g = 0; g < sp.ng; g++) sp.tabs[g] = h_tables[32 * grp + g];
-            kv.fn2<<<148 * 2, kv.threads, 0, s>>>(sp);
-        }
+    for (uint32_t grp = 0; grp < n_groups; grp++) {       // one launch per group of 32 genomes
+        p.grp = grp; p.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
+        for (uint32_t g = 0; g < p.ng; g++) p.tabs[g] = h_tables[32 * grp + g];
+        k3<<<p.n_regions, kv.threads, 0, s>>>(p);
+    }
+    if (evs) cudaEventRecord(evs[3], s);
+    ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)
+    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
+    for (uint32_t grp = 0; grp < n_groups; grp++) {
+        sp.grp = grp; sp.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
+        for (uint32_t g = 0; g < sp.ng; g++) sp.tabs[g] = h_tables[32 * grp + g];
+        k3<<<148 * 2, kv.threads, 0, s>>>(sp);
     }
     if (evs) cudaEventRecord(evs[4], s);
-    if (unperm) {
-        dim3 grid((unsigned)(((1ull << pl.out_shift) + UP_TILE - 1) / UP_TILE), pl.out_bins, n_groups);
-        unpermute_kernel<<<grid, 256, 0, s>>>((const uint2 *)sc.out_list, sc.out_cursor, pl.out_shift, d_rows, row_stride,
-                                              col_offset, a.nbl);
-    }
+}
+
+// K4 for position bins [bin0, bin1)
+void pk_part_unpermute(uint32_t bin0, uint32_t bin1, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
+                       uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s) {
+    if (!sc.out_list || bin1 <= bin0) return;
+    dim3 grid((unsigned)(((1ull << pl.out_shift) + UP_TILE - 1) / UP_TILE), bin1 - bin0, (n_local + 31) / 32);
+    unpermute_kernel<<<grid, 256, 0, s>>>((const uint2 *)sc.out_list, sc.out_cursor, pl.out_shift, bin0, d_rows, row_stride,
+                                          col_offset, (n_local + 7) / 8);
+}
+
+int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
+                                const PkTable *d_tables, const PkTable *h_tables, uint32_t n_local, uint8_t *d_rows,
+                                uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
+                                int prefetch, pk_stream_t s, cudaEvent_t *evs) {
+    if (!n) return 0;
+    (void)d_tables;
+    pk_part_begin(n_local, pl, sc, s);
+    if (evs) cudaEventRecord(evs[0], s);
+    pk_part_append(d_words, d_mask, p0, 0, n, ks, n_local, d_rows, row_stride, col_offset, pl, sc, s);
+    if (evs) cudaEventRecord(evs[1], s);
+    pk_part_probe(d_words, d_mask, p0, ks, h_tables, n_local, d_rows, row_stride, col_offset, pl, sc, prefetch, s, evs);
+    pk_part_unpermute(0, pl.out_bins, n_local, d_rows, row_stride, col_offset, pl, sc, s);
     if (evs) cudaEventRecord(evs[5], s);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

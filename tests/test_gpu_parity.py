@@ -110,7 +110,8 @@ def random_case(rng, n_genomes, k, length, p_member=0.6):
 
 
 @pytest.mark.parametrize("n_genomes,k,load", [(1, 21, 0.5), (2, 5, 0.5), (8, 31, 0.9), (9, 32, 0.75), (33, 21, 0.9),
-                                              (64, 17, 0.5), (70, 6, 0.5)])
+                                              (64, 17, 0.5), (70, 6, 0.5), (8, 24, 0.6), (3, 25, 0.6), (4, 14, 0.5),
+                                              (2, 15, 0.9)])
 def test_random_sets_vs_oracle(n_genomes, k, load):
     rng = np.random.default_rng(1000 * n_genomes + k)
     sb, ints, member, extra = random_case(rng, n_genomes, k, 6000)
