@@ -251,7 +251,7 @@ struct ProbeArgs {
 // SORT = 1 first counting-sorts the items by the hash bits below the partition bits, so that the lanes of
 // a warp probe neighbouring buckets (half the L1 tag lookups; pays off once the tables are small enough
 // for the kernel to be L1-bound rather than DRAM-bound).
-template <int T, int IPT, int FMT, int SORT, int MINB>
+template <int T, int IPT, int FMT, int SORT, int MINB, int GU>
 __global__ void __launch_bounds__(T, MINB) probe_part_kernel(const __grid_constant__ ProbeArgs a) {
     constexpr int CAP = T * IPT;
     __shared__ uint32_t s_bits[CAP];               // results of the deferred walk-ons, by item
@@ -338,30 +338,65 @@ __global__ void __launch_bounds__(T, MINB) probe_part_kernel(const __grid_consta
         uint32_t bits[IPT];
 #pragma unroll
         for (int j = 0; j < IPT; j++) bits[j] = 0;
-        // ---- probe, genome by genome
-        for (uint32_t g = 0; g < a.ng; g++) {
-            const PkTable t = a.tabs[g];
-            if (do_pf && tid == 0 && g + 2 < a.ng) {
-                const PkTable tn = a.tabs[g + 2];
+        // ---- probe, genome by genome (GU genomes' loads in flight per item)
+        for (uint32_t g0 = 0; g0 < a.ng; g0 += GU) {
+            if (do_pf && tid < GU && g0 + GU + 1 + tid < a.ng) {
+                const PkTable tn = a.tabs[g0 + GU + 1 + tid];
                 const uint32_t b0 = __umulhi(h_lo, tn.n_buckets), b1 = __umulhi(h_hi, tn.n_buckets);
                 if (b1 - b0 < 8192) l2_prefetch_bulk(tn.slots + 4ull * b0, (b1 - b0 + 1) * 32);
             }
+            if constexpr (GU == 1) {
+                const PkTable t = a.tabs[g0];
 #pragma unroll
-            for (int j = 0; j < IPT; j++) {
-                const uint32_t i = tid + j * T;
-                if (i < cnt) {
-                    const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
-                    const bool hit = pk_bucket_hit<FMT>(v, pk_target<FMT>(canon[j], 0));
-                    bits[j] |= (uint32_t)hit << g;
-                    if (!hit && pk_bucket_full<FMT>(v)) {          // deferred walk-on
-                        const uint32_t slot = atomicAdd(&q_n, 1u);
-                        if (slot < (uint32_t)CAP) {
-                            q_key[slot] = canon[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
-                        } else if (pk_lookup<FMT>(t, canon[j], h[j], 32 * a.grp + g, a.ks)) {      // queue full (pathological)
-                            bits[j] |= 1u << g;
+                for (int j = 0; j < IPT; j++) {
+                    const uint32_t i = tid + j * T;
+                    if (i < cnt) {
+                        const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
+                        const bool hit = pk_bucket_hit<FMT>(v, pk_target<FMT>(canon[j], 0));
+                        bits[j] |= (uint32_t)hit << g0;
+                        if (!hit && pk_bucket_full<FMT>(v)) {          // deferred walk-on
+                            const uint32_t slot = atomicAdd(&q_n, 1u);
+                            if (slot < (uint32_t)CAP) {
+                                q_key[slot] = canon[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g0;
+                            } else if (pk_lookup<FMT>(t, canon[j], h[j], 32 * a.grp + g0, a.ks)) {      // queue full (pathological)
+                                bits[j] |= 1u << g0;
+                            }
                         }
                     }
                 }
+            } else {
+            u64x4 v[GU][IPT];
+#pragma unroll
+            for (int u = 0; u < GU; u++) {
+                if (g0 + u < a.ng) {
+                    const PkTable t = a.tabs[g0 + u];
+#pragma unroll
+                    for (int j = 0; j < IPT; j++)
+                        if (tid + j * T < cnt) v[u][j] = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GU; u++) {
+                const uint32_t g = g0 + u;
+                if (g < a.ng) {
+#pragma unroll
+                    for (int j = 0; j < IPT; j++) {
+                        const uint32_t i = tid + j * T;
+                        if (i < cnt) {
+                            const bool hit = pk_bucket_hit<FMT>(v[u][j], pk_target<FMT>(canon[j], 0));
+                            bits[j] |= (uint32_t)hit << g;
+                            if (!hit && pk_bucket_full<FMT>(v[u][j])) {          // deferred walk-on
+                                const uint32_t slot = atomicAdd(&q_n, 1u);
+                                if (slot < (uint32_t)CAP) {
+                                    q_key[slot] = canon[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
+                                } else if (pk_lookup<FMT>(a.tabs[g], canon[j], h[j], 32 * a.grp + g, a.ks)) {      // queue full (pathological)
+                                    bits[j] |= 1u << g;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
             }
         }
         __syncthreads();
@@ -433,15 +468,17 @@ __global__ void __launch_bounds__(T, MINB) probe_part_kernel(const __grid_consta
 
 // variants of K3 selectable at run time (PK_K3_VARIANT) while the design is being tuned
 struct K3Variant { int threads, cap; void (*fn[2])(ProbeArgs); };   // fn[fmt]
-#define K3V(T, IPT, SORT, MINB) {T, T * IPT, {probe_part_kernel<T, IPT, PK_FMT_S64, SORT, MINB>, probe_part_kernel<T, IPT, PK_FMT_S32, SORT, MINB>}}
+#define K3V(T, IPT, SORT, MINB, GU) {T, T * IPT, {probe_part_kernel<T, IPT, PK_FMT_S64, SORT, MINB, GU>, probe_part_kernel<T, IPT, PK_FMT_S32, SORT, MINB, GU>}}
 static const K3Variant k3_variants[] = {
-    K3V(256, 3, 0, 6),   // 0: unsorted, 6 blocks/SM
-    K3V(256, 3, 1, 5),   // 1: bucket-sorted
-    K3V(256, 3, 0, 5),   // 2
-    K3V(256, 3, 1, 4),   // 3
-    K3V(512, 2, 0, 3),   // 4: cap 1024
-    K3V(512, 2, 1, 2),   // 5
-    K3V(256, 6, 0, 4),   // 6: cap 1536 (2^17 partitions)
+    K3V(256, 3, 0, 6, 1),   // 0: unsorted, 6 blocks/SM, one genome in flight
+    K3V(256, 3, 1, 5, 1),   // 1: bucket-sorted
+    K3V(256, 3, 0, 8, 1),   // 2: 8 blocks/SM (32 registers)
+    K3V(256, 3, 0, 5, 2),   // 3: two genomes in flight
+    K3V(256, 3, 0, 4, 2),   // 4
+    K3V(128, 6, 0, 12, 1),  // 5: 128-thread blocks
+    K3V(256, 6, 0, 4, 1),   // 6: cap 1536 (2^17 partitions)
+    K3V(256, 4, 0, 5, 1),   // 7: cap 1024
+    K3V(256, 3, 0, 7, 1),   // 8
 };
 static int g_k3_variant = 0;
 void pk_part_set_variant(int v) { if (v >= 0 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
