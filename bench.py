@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--probe-mode", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: assemble rows with the fused peer-memory gather+interleave kernel or NCCL all-gather + interleave")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -244,11 +246,47 @@ def main():
         d_rows = torch.empty((npos, rb_full), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
+    p2p = None
+    if world > 1 and args.exchange == "p2p":
+        # fused exchange over peer memory: each rank's planes (two, ping-pong) are IPC-mapped into every peer;
+        # stream-ordered barriers (1-element NCCL all-reduce) order the ranks, the data itself never goes
+        # through NCCL. The gather+interleave of step i runs on a side stream under the probe of step i+1
+        # (consecutive steps = consecutive anchor genomes).
+        planes, peers = [], []
+        for b in range(2):
+            pl = eng.device_alloc(npos * rb_local)
+            handles = [None] * world
+            dist.all_gather_object(handles, eng.ipc_export(pl))
+            planes.append(pl)
+            peers.append([pl if r == rank else eng.ipc_open(handles[r]) for r in range(world)])
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        d_rows2 = [d_rows, torch.empty_like(d_rows)]
+        p2p = {"i": 0, "probed": [torch.cuda.Event() for _ in range(2)], "gathered": [torch.cuda.Event() for _ in range(2)]}
+
     def device_step():
+        if p2p:
+            i = p2p["i"]; b = i & 1
+            if i >= 2:
+                tstream.wait_event(p2p["gathered"][b])      # own gather of step i-2 done (rows/plane b free)
+            dist.all_reduce(flag)                            # ... on every rank: plane b may be overwritten
+            eng.probe_device(d_words.data_ptr(), d_mask.data_ptr(), 0, npos, planes[b], rb_local, 0, st)
+            dist.all_reduce(flag)                            # every rank's plane b is complete
+            p2p["probed"][b].record(tstream)
+            side.wait_event(p2p["probed"][b])
+            eng.gather_interleave_device(peers[b], npos, rb_local, d_rows2[b].data_ptr(), rb_full, side.cuda_stream)
+            p2p["gathered"][b].record(side)
+            p2p["i"] = i + 1
+            return
         eng.probe_device(d_words.data_ptr(), d_mask.data_ptr(), 0, npos, d_local.data_ptr(), rb_local, 0, st)
         if world > 1:
             dist.all_gather_into_tensor(d_planes.view(-1), d_local.view(-1))
             eng.interleave_device(d_planes.data_ptr(), world, npos, rb_local, d_rows.data_ptr(), rb_full, st)
+
+    def drain():
+        if p2p:
+            for ev_ in p2p["gathered"]:
+                tstream.wait_event(ev_)
 
     def barrier():
         if world > 1:
@@ -257,6 +295,7 @@ def main():
 
     for _ in range(args.warmup):
         device_step()
+    drain()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -267,6 +306,8 @@ def main():
     ev[0].record()
     for i in range(args.steps):
         device_step()
+        if i == args.steps - 1:
+            drain()                  # the last step's exchange is inside the timed region
         ev[i + 1].record()
     barrier()
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -311,8 +352,9 @@ def main():
             d_ascii.copy_(t_cat, non_blocking=True)
             eng.pack_device(d_ascii.data_ptr(), ltot, d_words.data_ptr(), d_mask.data_ptr(), st)
             device_step()
+            drain()
             if rank == 0:
-                h_out.copy_(d_rows, non_blocking=True)
+                h_out.copy_(d_rows2[(p2p["i"] - 1) & 1] if p2p else d_rows, non_blocking=True)
         e2e_step(); barrier()
         t1 = time.perf_counter()
         for _ in range(args.steps):
@@ -360,7 +402,9 @@ def main():
                            "load_factor": args.load_factor, "probe_mode": args.probe_mode,
                            "l2": "inputs (per-genome tables, %.1f GB/GPU) are far larger than L2; no flush needed"
                                  % (sum(t["bytes"] for t in tstats) / 1e9),
-                           "parallelism": f"genome-sharded x{world}" if world > 1 else "1 GPU",
+                           "parallelism": (f"genome-sharded x{world}, exchange=" +
+                                           ("fused peer-memory gather+interleave kernel" if p2p else "NCCL all-gather + interleave"))
+                           if world > 1 else "1 GPU",
                            "setup_s": round(setup_s, 1)},
                 "e2e": {"value": positions * n_total / (e2e_ms / 1e3), "unit": unit, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

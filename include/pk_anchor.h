@@ -190,6 +190,24 @@ int pk_reduce_device(pk_engine *e, const void *d_rows, uint32_t row_stride, uint
 int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w,
                          void *d_rows, uint32_t row_stride, void *stream);
 
+/* ---- peer memory: the fused exchange step of the genome-sharded path ------------
+ * One process per GPU. Each rank allocates its plane ([n][w] bytes: its shard's columns of every row) with
+ * pk_device_alloc, exports it (cudaIpc handle, 64 bytes, exchanged by the host over any channel), and maps
+ * its peers' planes with pk_ipc_open. pk_gather_interleave_device then assembles full rows
+ *   rows[i][r*w .. r*w+w) = planes[r][i][0..w)
+ * in ONE kernel that reads the peers' planes in place over NVLink (coalesced 16-byte loads), transposes
+ * through shared memory and writes whole rows: no NCCL all-gather, no [R][n][w] staging buffer, no separate
+ * interleave pass. d_planes is a HOST array of n_ranks device pointers (own plane included, any order the
+ * caller wants as column order). The caller orders the ranks (a stream-ordered barrier before the call,
+ * another before the planes are overwritten). n_ranks <= 16. */
+int pk_device_alloc(pk_engine *e, void **d_ptr, size_t bytes);   /* zero-filled */
+int pk_device_free(pk_engine *e, void *d_ptr);
+int pk_ipc_export(pk_engine *e, const void *d_ptr, uint8_t handle[64]);
+int pk_ipc_open(pk_engine *e, const uint8_t handle[64], void **d_ptr);
+int pk_ipc_close(pk_engine *e, void *d_ptr);
+int pk_gather_interleave_device(pk_engine *e, const void *const *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w,
+                                void *d_rows, uint32_t row_stride, void *stream);
+
 /* timing / accounting of the last pk_anchor_chrom or pk_get_counters_for_read */
 typedef struct pk_stats {
     float h2d_ms, pack_ms, probe_ms, reduce_ms, d2h_ms, total_ms;

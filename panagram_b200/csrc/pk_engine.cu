@@ -435,6 +435,57 @@ extern "C" int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t
     return PK_OK;
 }
 
+// ------------------------------------------------------------------ peer memory (multi-GPU, process per GPU)
+extern "C" int pk_device_alloc(pk_engine *e, void **d_ptr, size_t bytes) {
+    if (!e || !d_ptr) { pk_set_error("null argument"); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    CU(cudaMemset(*d_ptr, 0, bytes ? bytes : 1));
+    return PK_OK;
+}
+extern "C" int pk_device_free(pk_engine *e, void *d_ptr) {
+    if (!e) { pk_set_error("null argument"); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    if (d_ptr) CU(cudaFree(d_ptr));
+    return PK_OK;
+}
+extern "C" int pk_ipc_export(pk_engine *e, const void *d_ptr, uint8_t handle[64]) {
+    if (!e || !d_ptr || !handle) { pk_set_error("null argument"); return PK_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    int rc = set_device(e); if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle, &h, 64);
+    return PK_OK;
+}
+extern "C" int pk_ipc_open(pk_engine *e, const uint8_t handle[64], void **d_ptr) {
+    if (!e || !d_ptr || !handle) { pk_set_error("null argument"); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PK_OK;
+}
+extern "C" int pk_ipc_close(pk_engine *e, void *d_ptr) {
+    if (!e) { pk_set_error("null argument"); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr));
+    return PK_OK;
+}
+extern "C" int pk_gather_interleave_device(pk_engine *e, const void *const *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w,
+                                           void *d_rows, uint32_t row_stride, void *stream) {
+    if (!e || !d_planes || !d_rows) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (n_ranks == 0 || n_ranks > 16 || w == 0) { pk_set_error("n_ranks %u / w %u out of range (<= 16 ranks)", n_ranks, w); return PK_EINVAL; }
+    if ((uint64_t)n_ranks * w > row_stride) { pk_set_error("row_stride %u < n_ranks*w", row_stride); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    if (pk_launch_gather_interleave(d_planes, n_ranks, n, w, (uint8_t *)d_rows, row_stride,
+                                    stream ? (pk_stream_t)stream : e->stream)) {
+        pk_set_error("gather_interleave launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return PK_ECUDA;
+    }
+    return PK_OK;
+}
+
 // ------------------------------------------------------------------ probe dispatch
 static void free_scratch(pk_engine *e) {
     cudaFree(e->sc.buf1); cudaFree(e->sc.buf2); cudaFree(e->sc.spill);

@@ -94,6 +94,8 @@ void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_col
                       uint8_t *d_rows_low, uint32_t step, pk_stream_t s);
 void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,
                           uint32_t row_stride, pk_stream_t s);
+int pk_launch_gather_interleave(const void *const *planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,
+                                uint32_t row_stride, pk_stream_t s);
 void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
                            uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
 

@@ -392,6 +392,100 @@ void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n,
     interleave_kernel<<<grid_for(n * n_ranks), 256, 0, s>>>(d_planes, n_ranks, n, w, d_rows, row_stride);
 }
 
+// Fused exchange: the rows of R genome shards are assembled by reading every rank's plane IN PLACE over
+// NVLink (peer-mapped pointers), transposing through shared memory and writing whole interleaved rows:
+// rows[i][r*w .. r*w+w) = planes[r][i][0..w). One kernel replaces the NCCL all-gather, the [R][n][w]
+// staging buffer and the interleave pass. Loads from a peer are 16-byte, coalesced; stores are 16-byte.
+#define GI_MAX_RANKS 16
+struct GatherArgs {
+    const uint8_t *planes[GI_MAX_RANKS];
+    uint32_t n_ranks, w, row_stride, tile_rows;
+    uint64_t n;
+    uint8_t *rows;
+};
+__global__ void __launch_bounds__(256) gather_interleave_kernel(const __grid_constant__ GatherArgs a) {
+    extern __shared__ __align__(16) uint8_t g_tile[];          // [n_ranks][tile_rows * w]
+    const uint32_t plane_bytes = a.tile_rows * a.w;
+    for (uint64_t t0 = (uint64_t)blockIdx.x * a.tile_rows; t0 < a.n; t0 += (uint64_t)gridDim.x * a.tile_rows) {
+        const uint32_t nrows = (uint32_t)min((uint64_t)a.tile_rows, a.n - t0);
+        const uint32_t nbytes = nrows * a.w;
+        for (uint32_t r = 0; r < a.n_ranks; r++) {
+            const uint8_t *src = a.planes[r] + t0 * a.w;
+            uint8_t *dst = g_tile + r * plane_bytes;
+            if ((((uintptr_t)src) & 15) == 0) {
+                for (uint32_t o = threadIdx.x * 16; o + 16 <= nbytes; o += 256 * 16)
+                    *(uint4 *)(dst + o) = *(const uint4 *)(src + o);
+                for (uint32_t o = (nbytes & ~15u) + threadIdx.x; o < nbytes; o += 256) dst[o] = src[o];
+            } else {
+                for (uint32_t o = threadIdx.x; o < nbytes; o += 256) dst[o] = src[o];
+            }
+        }
+        __syncthreads();
+        const uint32_t rw = a.n_ranks * a.w;
+        uint8_t *out = a.rows + t0 * a.row_stride;
+        if (a.w == 1 && (a.n_ranks & 3) == 0 && a.row_stride == rw && (((uintptr_t)out) & 15) == 0) {
+            // 1 byte per rank and row (8 genomes per GPU): 4 rows per thread, one 32-bit shared load per rank,
+            // byte transpose in registers, rows written as 32-bit words (consecutive lanes -> consecutive rows)
+            for (uint32_t r4 = threadIdx.x * 4; r4 < nrows; r4 += 256 * 4) {
+                uint32_t x[GI_MAX_RANKS];
+#pragma unroll
+                for (int r = 0; r < GI_MAX_RANKS; r++)
+                    if ((uint32_t)r < a.n_ranks) x[r] = *(const uint32_t *)(g_tile + r * plane_bytes + r4);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (r4 + j < nrows) {
+                        uint32_t *orow = (uint32_t *)(out + (uint64_t)(r4 + j) * rw);
+#pragma unroll
+                        for (int q = 0; q < GI_MAX_RANKS / 4; q++) {
+                            if ((uint32_t)(4 * q) < a.n_ranks) {
+                                const uint32_t lo = __byte_perm(x[4 * q], x[4 * q + 1], 0x0040 + j * 0x0011);
+                                const uint32_t hi = __byte_perm(x[4 * q + 2], x[4 * q + 3], 0x0040 + j * 0x0011);
+                                orow[q] = (lo & 0xffffu) | (hi << 16);
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (a.row_stride == rw && (((uintptr_t)out) & 15) == 0) {
+            const uint32_t total = nrows * rw;
+            for (uint32_t o = threadIdx.x * 16; o < total; o += 256 * 16) {
+                uint8_t tmp[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const uint32_t oo = o + q;
+                    const uint32_t row = oo / rw, within = oo - row * rw, r = within / a.w, b = within - r * a.w;
+                    tmp[q] = oo < total ? g_tile[r * plane_bytes + row * a.w + b] : 0;
+                }
+                if (o + 16 <= total) *(uint4 *)(out + o) = *(const uint4 *)tmp;
+                else for (uint32_t q = 0; o + q < total; q++) out[o + q] = tmp[q];
+            }
+        } else {
+            for (uint32_t e = threadIdx.x; e < nrows * rw; e += 256) {
+                const uint32_t row = e / rw, within = e - row * rw, r = within / a.w, b = within - r * a.w;
+                out[(uint64_t)row * a.row_stride + within] = g_tile[r * plane_bytes + row * a.w + b];
+            }
+        }
+        __syncthreads();
+    }
+}
+int pk_launch_gather_interleave(const void *const *planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,
+                                uint32_t row_stride, pk_stream_t s) {
+    if (!n) return 0;
+    if (n_ranks > GI_MAX_RANKS) return -1;
+    GatherArgs a{};
+    for (uint32_t r = 0; r < n_ranks; r++) a.planes[r] = (const uint8_t *)planes[r];
+    a.n_ranks = n_ranks; a.w = w; a.row_stride = row_stride; a.n = n; a.rows = d_rows;
+    uint32_t tile = 32768 / (n_ranks * w);            // 32 KB of shared memory per block
+    tile = tile / 16 * 16;
+    if (tile < 16) tile = 16;
+    a.tile_rows = tile;
+    const size_t shmem = (size_t)n_ranks * tile * w;
+    const uint64_t ntiles = (n + tile - 1) / tile;
+    const unsigned grid = (unsigned)(ntiles < 148ull * 6 ? ntiles : 148ull * 6);
+    gather_interleave_kernel<<<grid, 256, shmem, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 __global__ void __launch_bounds__(256) rows_to_u32_kernel(const uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t byte_off,
                                                           uint32_t n_bytes, uint32_t bit_mask, uint64_t n, uint32_t *__restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

@@ -480,8 +480,15 @@ static const K3Variant k3_variants[] = {
     K3V(256, 4, 0, 5, 1),   // 7: cap 1024
     K3V(256, 3, 0, 7, 1),   // 8
 };
-static int g_k3_variant = 0;
-void pk_part_set_variant(int v) { if (v >= 0 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
+// -1 = auto: per launch (group of <= 32 genomes), bucket-sorted blocks once the sort is amortised over
+// >= 16 genomes (configs[2]: 18.9 vs 19.9 ms), unsorted below (configs[1]: 5.5 vs 6.3 ms). Variants 0 and 1
+// share the block capacity, hence the partition plan.
+static int g_k3_variant = -1;
+void pk_part_set_variant(int v) { if (v >= -1 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
+static const K3Variant &k3_pick(uint32_t n_genomes_in_launch) {
+    if (g_k3_variant >= 0) return k3_variants[g_k3_variant];
+    return k3_variants[n_genomes_in_launch >= 16 ? 1 : 0];
+}
 
 // K4: scatter the (pos, bits) lists into rows. All blocks of one bin write inside a slice of
 // 2^out_shift rows, which stays in L2 until its sectors are complete.
@@ -510,7 +517,7 @@ static uint32_t ceil_log2(uint64_t v) { uint32_t b = 0; while ((1ull << b) < v) 
 
 void pk_part_plan(uint64_t n, PkPartPlan *pl) {
     // mean fill <= 5/6 of the K3 block capacity (>= 20% head-room for the Poisson spread)
-    const uint32_t cap = (uint32_t)k3_variants[g_k3_variant].cap;
+    const uint32_t cap = (uint32_t)k3_pick(1).cap;
     const uint64_t fill = (uint64_t)cap * 5 / 6;
     uint32_t pb = ceil_log2((n + fill - 1) / fill);
     if (pb > 18) pb = 18;
@@ -573,8 +580,7 @@ void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0
 void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, const PkTable *h_tables,
                    uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
                    const PkPartScratch &sc, int prefetch, pk_stream_t s, cudaEvent_t *evs) {
-    const K3Variant &kv = k3_variants[g_k3_variant];
-    void (*k3)(ProbeArgs) = kv.fn[ks.fmt == PK_FMT_S32 ? 1 : 0];
+    const int fi = ks.fmt == PK_FMT_S32 ? 1 : 0;
     const uint32_t n_groups = (n_local + 31) / 32;
     PartArgs a = make_part_args(d_words, d_mask, p0, ks, n_local, d_rows, row_stride, col_offset, pl, sc);
     if (pl.pb2) {
@@ -598,15 +604,17 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     for (uint32_t grp = 0; grp < n_groups; grp++) {       // one launch per group of 32 genomes
         p.grp = grp; p.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         for (uint32_t g = 0; g < p.ng; g++) p.tabs[g] = h_tables[32 * grp + g];
-        k3<<<p.n_regions, kv.threads, 0, s>>>(p);
+        const K3Variant &kv = k3_pick(p.ng);
+        kv.fn[fi]<<<p.n_regions, kv.threads, 0, s>>>(p);
     }
     if (evs) cudaEventRecord(evs[3], s);
     ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)
-    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = kv.cap; sp.pb = 0;
+    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = k3_pick(1).cap; sp.pb = 0;
     for (uint32_t grp = 0; grp < n_groups; grp++) {
         sp.grp = grp; sp.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         for (uint32_t g = 0; g < sp.ng; g++) sp.tabs[g] = h_tables[32 * grp + g];
-        k3<<<148 * 2, kv.threads, 0, s>>>(sp);
+        const K3Variant &kv = k3_pick(sp.ng);
+        kv.fn[fi]<<<148 * 2, kv.threads, 0, s>>>(sp);
     }
     if (evs) cudaEventRecord(evs[4], s);
 }

@@ -216,6 +216,35 @@ class Engine:
                                        d_hist or None, d_colsums or None, d_low or None,
                                        self.lowres_step, stream or None))
 
+    # ---- peer memory (genome-sharded exchange without NCCL) ---------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(self._L.pk_device_alloc(self._h, C.byref(p), nbytes))
+        return p.value
+
+    def device_free(self, d_ptr: int):
+        check(self._L.pk_device_free(self._h, d_ptr))
+
+    def ipc_export(self, d_ptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        check(self._L.pk_ipc_export(self._h, d_ptr, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        check(self._L.pk_ipc_open(self._h, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, d_ptr: int):
+        check(self._L.pk_ipc_close(self._h, d_ptr))
+
+    def gather_interleave_device(self, plane_ptrs: list[int], n: int, w: int, d_rows: int, row_stride: int,
+                                 stream: int = 0):
+        arr = (C.c_void_p * len(plane_ptrs))(*plane_ptrs)
+        check(self._L.pk_gather_interleave_device(self._h, arr, len(plane_ptrs), n, w, d_rows, row_stride,
+                                                  stream or None))
+
     def interleave_device(self, d_planes: int, n_ranks: int, n: int, w: int, d_rows: int, row_stride: int,
                           stream: int = 0):
         check(self._L.pk_interleave_device(self._h, d_planes, n_ranks, n, w, d_rows, row_stride,

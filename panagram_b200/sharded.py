@@ -62,6 +62,41 @@ class ShardedAnchorer:
     def owns(self, genome: int) -> bool:
         return self.begin <= genome < self.end
 
+    # ---- exchange over peer memory: one fused kernel instead of all-gather + interleave ----
+    def setup_p2p(self, npos: int):
+        """Allocate this rank's plane [npos, w], exchange IPC handles, map the peers' planes."""
+        import torch
+        import torch.distributed as dist
+        eng = self.engine
+        self.p2p_npos = npos
+        self.plane = eng.device_alloc(npos * self.w)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, eng.ipc_export(self.plane))
+        self.peer_planes = [self.plane if r == self.rank else eng.ipc_open(handles[r]) for r in range(self.world)]
+        self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{eng.cfg.device}")
+
+    def close_p2p(self):
+        import torch.distributed as dist
+        dist.barrier()
+        for r, p in enumerate(self.peer_planes):
+            if r != self.rank:
+                self.engine.ipc_close(p)
+        dist.barrier()
+        self.engine.device_free(self.plane)
+
+    def probe_rows_p2p(self, d_words: int, d_mask: int, npos: int, stream: int, d_rows):
+        """local probe into this rank's plane -> barrier -> gather_interleave reading every peer's plane over
+        NVLink. The all-reduces are stream-ordered barriers: peers' planes are complete before they are read,
+        and nobody overwrites a plane that a peer may still be reading (barrier at entry)."""
+        import torch.distributed as dist
+        assert npos == self.p2p_npos
+        eng = self.engine
+        dist.all_reduce(self._flag)
+        eng.probe_device(d_words, d_mask, 0, npos, self.plane, self.w, 0, stream)
+        dist.all_reduce(self._flag)
+        eng.gather_interleave_device(self.peer_planes, npos, self.w, d_rows.data_ptr(), self.world * self.w, stream)
+        return d_rows
+
     def probe_rows(self, d_words: int, d_mask: int, npos: int, stream: int, d_local, d_planes, d_rows):
         """local probe -> all-gather -> interleave. d_local [npos, w], d_planes [world, npos, w],
         d_rows [npos, world*w] are torch uint8 tensors on this rank's device."""

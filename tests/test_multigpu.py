@@ -62,7 +62,16 @@ def _worker(rank, world, port, q):
         d_rows = torch.empty((npos, world * sa.w), dtype=torch.uint8, device=dev)
         rows = sa.probe_rows(d_words.data_ptr(), d_mask.data_ptr(), npos, st, d_local, d_planes, d_rows)
         torch.cuda.synchronize()
-        q.put((rank, rows.cpu().numpy()))
+        nccl_rows = rows.cpu().numpy()
+        # the same exchange through peer memory (one fused kernel, no NCCL in the data path)
+        sa.setup_p2p(npos)
+        d_rows2 = torch.zeros((npos, world * sa.w), dtype=torch.uint8, device=dev)
+        for _ in range(2):          # twice: the entry barrier protects planes that are still being read
+            sa.probe_rows_p2p(d_words.data_ptr(), d_mask.data_ptr(), npos, st, d_rows2)
+        torch.cuda.synchronize()
+        p2p_rows = d_rows2.cpu().numpy()
+        sa.close_p2p()
+        q.put((rank, nccl_rows, bool((p2p_rows == nccl_rows).all())))
     finally:
         dist.destroy_process_group()
 
@@ -77,7 +86,9 @@ def test_two_rank_sharded_equals_single_engine():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=600) for _ in procs)
+    got = [q.get(timeout=600) for _ in procs]
+    assert all(ok for _, _, ok in got), "peer-memory exchange differs from the NCCL exchange"
+    res = {r: rows for r, rows, _ in got}
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
