@@ -114,15 +114,25 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
         if (2 * tid + 1 < nb) S.dstart[2 * tid + 1] = excl + a;
         if (tid == PT_THREADS - 1) S.tile_total = woff + s;
     }
-    for (uint32_t d = tid; d < nb; d += PT_THREADS)
-        if (S.tot[d]) S.gbase[d] = atomicAdd(&cursor[region0 + d], S.tot[d]);
-    __syncthreads();
+    // reserve the runs (one global atomic per digit of the tile); the round trip overlaps with the staging
+    uint32_t gb[PT_MAXB / PT_THREADS];
+#pragma unroll
+    for (int q = 0; q < PT_MAXB / PT_THREADS; q++) {
+        const uint32_t d = tid + q * PT_THREADS;
+        gb[q] = (d < nb && S.tot[d]) ? atomicAdd(&cursor[region0 + d], S.tot[d]) : 0;
+    }
+    __syncthreads();            // dstart / tile_total visible
 #pragma unroll
     for (int j = 0; j < PT_IPT; j++) {
         if ((validmask >> j) & 1) {
             const uint32_t d = (h[j] >> shift) & (nb - 1);
             S.stage[S.dstart[d] + S.warp_cnt[w][d] + rank[j]] = make_uint2(h[j], pos[j]);
         }
+    }
+#pragma unroll
+    for (int q = 0; q < PT_MAXB / PT_THREADS; q++) {
+        const uint32_t d = tid + q * PT_THREADS;
+        if (d < nb) S.gbase[d] = gb[q];
     }
     __syncthreads();
     const uint32_t total = S.tile_total;

@@ -351,3 +351,79 @@ def test_panagram_index_cli_end_to_end(pan3, tmp_path, capsys):
     assert main(["index", str(tsv), "-k", "21", "-o", str(tmp_path / "idx2"), "--anchor_genomes", "g2"]) == 0
     assert layout.read_bgzf(tmp_path / "idx2" / "anchor" / "g2" / "bitmap.1.gz") == pan3["expected"]["g2"]["bitmap.1"]
     assert not (tmp_path / "idx2" / "anchor" / "g0").exists()
+
+
+# ---- S32 slot format: quotienting must stay exact -------------------------------------------------
+def _kmer_str(v: int, k: int) -> bytes:
+    return bytes(b"ACGT"[(v >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def _s32_hash(canon: np.ndarray, k: int) -> np.ndarray:
+    """numpy restatement of pk_key_hash (S32) for building adversarial key sets."""
+    eb = max(0, 2 * k - 28)
+    lo = (canon & np.uint64(0x0FFFFFFF)).astype(np.uint32)
+    m = lo.copy()
+    m ^= m >> np.uint32(16); m *= np.uint32(0x7FEB352D); m ^= m >> np.uint32(15); m *= np.uint32(0x846CA68B); m ^= m >> np.uint32(16)
+    if eb == 0:
+        return m
+    hi = (canon >> np.uint64(28)).astype(np.uint32)
+    f = (m * np.uint32(0x9E3779B1)) >> np.uint32(32 - eb)
+    return ((hi ^ f) << np.uint32(32 - eb)) | (m >> np.uint32(eb))
+
+
+def _canonical_keys(rng, k, n):
+    """random k-mers that start and end with A: fwd < revcomp, so the integer is its own canonical form"""
+    v = rng.integers(0, 1 << (2 * k - 4), size=n, dtype=np.uint64) << np.uint64(2)     # ...A at the end, A.. at the top
+    return np.unique(v)
+
+
+@pytest.mark.parametrize("k", [21, 24, 16])
+def test_s32_same_low_bits_never_alias(k):
+    """k-mers that agree in the 28 stored bits and differ only in the bits implied by the home bucket:
+    present ones are found, absent ones are not (no false positives from quotienting)."""
+    rng = np.random.default_rng(k)
+    lo = _canonical_keys(rng, 14, 300) & np.uint64(0x0FFFFFFC)
+    hi_bits = 2 * k - 28
+    his = rng.integers(0, 1 << (hi_bits - 2), size=(lo.size, 6), dtype=np.uint64)       # top base A
+    keys = np.unique((his << np.uint64(28)) | lo[:, None])
+    member = rng.random(keys.size) < 0.5
+    eng = Engine(k, 1, probe_mode="direct")
+    eng.add_keys(0, keys[member])
+    eng.finalize()
+    assert eng.table_stats(0)["n_keys"] == int(member.sum())
+    got = np.array([int(eng.get_counters_for_read(0, _kmer_str(int(v), k))[0]) for v in keys])
+    assert (got == member.astype(int)).all()
+
+
+def test_s32_overfull_neighbourhood_goes_to_the_stash():
+    """> 15 buckets' worth of k-mers with one home bucket: the surplus lands in the stash and is still found,
+    while colliding k-mers that were never inserted are not."""
+    k = 21
+    rng = np.random.default_rng(3)
+    cand = _canonical_keys(rng, k, 3_000_000)
+    nb = (1 << 14)                                    # the minimum table: n_buckets = 2^eb for k=21
+    h = _s32_hash(cand, k)
+    bucket = ((h.astype(np.uint64) * np.uint64(nb)) >> np.uint64(32)).astype(np.int64)
+    target = np.bincount(bucket, minlength=nb).argmax()
+    coll = cand[bucket == target]
+    assert coll.size >= 170, coll.size
+    ins, absent = coll[:150], coll[150:170]
+    eng = Engine(k, 1, probe_mode="direct")
+    eng.reserve(0, 1000)                              # -> n_buckets = 2^14 exactly
+    eng.add_keys(0, ins)
+    eng.finalize()
+    st = eng.table_stats(0)
+    assert st["n_buckets"] == nb and st["n_keys"] == ins.size
+    for v in ins:
+        assert eng.get_counters_for_read(0, _kmer_str(int(v), k))[0] == 1
+    for v in absent:
+        assert eng.get_counters_for_read(0, _kmer_str(int(v), k))[0] == 0
+    # the same through the partitioned path: one long sequence holding all of them, N-separated
+    seq = b"N".join(_kmer_str(int(v), k) for v in np.concatenate([ins, absent]))
+    engp = Engine(k, 1, probe_mode="partitioned")
+    engp.reserve(0, 1000)
+    engp.add_keys(0, ins)
+    engp.finalize()
+    rows = engp.anchor_chrom(seq, hist=False)["bitmap1"][:, 0]
+    starts = np.arange(ins.size + absent.size) * (k + 1)
+    assert (rows[starts[:ins.size]] == 1).all() and (rows[starts[ins.size:]] == 0).all()
