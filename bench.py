@@ -374,9 +374,16 @@ def main():
         alg_bytes = positions * (npg * 32 + 0.375 + nbytes_local * 1.01)
         k3_ms = ks["k_probe_ms"] if ks["k_probe_ms"] > 0 else ms_per_step
         stage_ms = statistics.median(step_ms)
+        traffic = None
+        try:
+            tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(args.workload)
+            if tj and world == 1 and ks["k_probe_ms"] > 0:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": "probe_part_kernel" if ks["k_probe_ms"] > 0 else "probe_kernel",
                 "achieved": alg_bytes / (k3_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / (k3_ms / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                "frac": alg_bytes / (k3_ms / 1e3) / 1e9 / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k3_ms,
                 "stage": {"what": "all kernels of the probe stage (partition_seq + partition_fine + probe_part + spill + unpermute)",
                           "ms": stage_ms, "achieved": alg_bytes / (stage_ms / 1e3) / 1e9,
