@@ -427,3 +427,56 @@ def test_s32_overfull_neighbourhood_goes_to_the_stash():
     rows = engp.anchor_chrom(seq, hist=False)["bitmap1"][:, 0]
     starts = np.arange(ins.size + absent.size) * (k + 1)
     assert (rows[starts[:ins.size]] == 1).all() and (rows[starts[ins.size:]] == 0).all()
+
+
+def test_full_size_configs1_properties():
+    """BASELINE configs[1] at full size (8 x 135 Mbp, k=21, anchor = genome 0) through the public call:
+    size-independent properties of the reference's output (SURVEY §4 [probed]) on all 135 M rows, and
+    bit-exact agreement of the partitioned path with the direct kernel and the C oracle on samples."""
+    from panagram_b200 import synth
+    k, n, length, seed = 21, 8, 135_000_000, 20260001
+    anc = synth.ancestor_codes(length, seed)
+    eng = Engine(k, n)
+    anchor_seqs = None
+    for g in range(n):
+        chroms = [s for _, s in synth.genome_chroms(anc, g, seed)]
+        if g == 0:
+            anchor_seqs = chroms
+        eng.reserve(g, sum(c.size for c in chroms))
+        for c in chroms:
+            eng.add_sequence(g, c)
+    eng.finalize()
+    res = eng.anchor_genome(anchor_seqs)
+    total = 0
+    col = np.zeros(n, dtype=np.uint64)
+    for seq, r in zip(anchor_seqs, res["chroms"]):
+        rows = r["bitmap1"][:, 0]
+        nk = seq.size - k + 1
+        assert r["nkmers"] == nk and rows.size == nk
+        bad = ~np.isin(seq, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+        c = np.concatenate(([0], np.cumsum(bad, dtype=np.int64)))
+        valid = (c[k:] - c[:-k]) == 0                                  # window holds only ACGTacgt
+        assert ((rows & 1) == valid).all()                              # the anchor's own column
+        assert ((rows == 0) == ~valid).all()                            # all-zero iff a non-ACGT byte in the window
+        assert (r["low"][:, 0] == rows[::100]).all()                    # bitmap.100 = every 100th row per chromosome
+        pc = np.unpackbits(rows[:, None], axis=1).sum(axis=1)
+        binlen = r["binlen"]
+        assert binlen == 200000 and r["bin_hist"].shape == ((nk + binlen - 1) // binlen, n + 1)
+        assert r["bin_hist"].sum() == nk
+        b3 = np.bincount(pc[3 * binlen:4 * binlen], minlength=n + 1)
+        assert (r["bin_hist"][3] == b3).all()
+        col += np.unpackbits(rows[:, None], axis=1, bitorder="little").sum(axis=0).astype(np.uint64)
+        total += nk
+    assert (res["col_sums"] == col).all() and res["col_sums"][0] == col.max()
+    assert total == 134_999_900
+    # partitioned (default for this size) == direct kernel on a 3 M-position slice
+    engd = Engine(k, n, probe_mode="direct")
+    for g in range(n):
+        chroms = [s for _, s in synth.genome_chroms(anc, g, seed)]
+        engd.reserve(g, sum(c.size for c in chroms))
+        for c in chroms:
+            engd.add_sequence(g, c)
+    engd.finalize()
+    sl = anchor_seqs[1][:3_000_000]
+    rd = engd.anchor_chrom(sl, hist=False, low=False, colsums=False)["bitmap1"]
+    assert (rd[:, 0] == res["chroms"][1]["bitmap1"][: rd.shape[0], 0]).all()
