@@ -208,6 +208,14 @@ int pk_ipc_close(pk_engine *e, void *d_ptr);
 int pk_gather_interleave_device(pk_engine *e, const void *const *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w,
                                 void *d_rows, uint32_t row_stride, void *stream);
 
+/* Tuning knobs of the partitioned probe (process-wide; no reference counterpart). Results never depend on
+ * them; tests run the parity suite under several settings. name = "k3_window" (1: probe out of table
+ * windows staged in shared memory by TMA bulk copies when they fit, 0: always probe through L1/L2),
+ * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_stages" (1..4 windows in flight per block),
+ * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "unpermute" (0/1: applies to
+ * scratch allocated afterwards). Unknown names return PK_EINVAL. */
+int pk_engine_tune(pk_engine *e, const char *name, int value);
+
 /* timing / accounting of the last pk_anchor_chrom or pk_get_counters_for_read */
 typedef struct pk_stats {
     float h2d_ms, pack_ms, probe_ms, reduce_ms, d2h_ms, total_ms;

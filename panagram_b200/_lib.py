@@ -85,6 +85,7 @@ SIGNATURES = {
     "pk_reduce_device": (C.c_int, [_vp, _vp, _u32, _u32, _u64, _u64, _u64, _vp, _vp, _vp, _u32, _vp]),
     "pk_interleave_device": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _vp, _u32, _vp]),
     "pk_engine_stats": (C.c_int, [_vp, C.POINTER(PkStats)]),
+    "pk_engine_tune": (C.c_int, [_vp, _cp, C.c_int]),
     "pk_device_alloc": (C.c_int, [_vp, _pp, _sz]),
     "pk_device_free": (C.c_int, [_vp, _vp]),
     "pk_ipc_export": (C.c_int, [_vp, _vp, _vp]),

@@ -29,6 +29,9 @@ void pk_set_error(const char *fmt, ...) {
         }                                                                                          \
     } while (0)
 
+// process-wide tuning state of the partitioned probe (pk_engine_tune / PK_K3* environment variables)
+static int g_tune_window = 0, g_tune_wvariant = -1, g_tune_wstages = 3;   // window kernel off by default until measured
+
 // ------------------------------------------------------------------ engine
 struct HostTable {
     PkTable dev{nullptr, 0, 0};
@@ -136,6 +139,13 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (const char *pf = getenv("PK_L2_PREFETCH")) e->l2_prefetch = atoi(pf);
     if (const char *up = getenv("PK_UNPERMUTE")) e->unpermute = atoi(up);
     if (const char *kv = getenv("PK_K3_VARIANT")) pk_part_set_variant(atoi(kv));
+    {
+        const char *we = getenv("PK_K3_WINDOW"), *wv = getenv("PK_K3W_VARIANT"), *ws = getenv("PK_K3W_STAGES");
+        if (we) g_tune_window = atoi(we);
+        if (wv) g_tune_wvariant = atoi(wv);
+        if (ws && atoi(ws) >= 1 && atoi(ws) <= 4) g_tune_wstages = atoi(ws);
+        pk_part_set_window(g_tune_window, g_tune_wvariant, g_tune_wstages);
+    }
     e->n_local = cfg->genome_end - cfg->genome_begin;
     e->row_bytes = (e->n_local + 7) / 8;
     e->tabs.resize(e->n_local);
@@ -769,6 +779,28 @@ extern "C" int pk_get_counters_for_read(pk_engine *e, uint32_t dbi, const char *
     rc = check_part_error(e); if (rc) return rc;
     if (shift) for (uint64_t i = 0; i < nk; i++) counters[i] <<= shift;
     *n_out = nk;
+    return PK_OK;
+}
+
+extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
+    if (!e || !name) { pk_set_error("null argument"); return PK_EINVAL; }
+    const std::string n(name);
+    if (n == "k3_window") g_tune_window = value;
+    else if (n == "k3w_variant") g_tune_wvariant = value;
+    else if (n == "k3w_stages") { if (value < 1 || value > 4) { pk_set_error("k3w_stages %d out of 1..4", value); return PK_EINVAL; } g_tune_wstages = value; }
+    else if (n == "k3_variant") { pk_part_set_variant(value); return PK_OK; }
+    else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
+    else if (n == "unpermute") {
+        if (e->unpermute != value) {       // the scratch layout depends on it: drop it, the next launch re-allocates
+            int rc = set_device(e); if (rc) return rc;
+            CU(cudaDeviceSynchronize());
+            free_scratch(e);
+            e->unpermute = value;
+        }
+        return PK_OK;
+    }
+    else { pk_set_error("unknown tuning knob '%s'", name); return PK_EINVAL; }
+    pk_part_set_window(g_tune_window, g_tune_wvariant, g_tune_wstages);
     return PK_OK;
 }
 

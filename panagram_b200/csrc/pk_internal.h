@@ -117,6 +117,7 @@ struct PkPartScratch {
 };
 uint32_t pk_part_obins(void);
 void pk_part_set_variant(int v);
+void pk_part_set_window(int enable, int variant, int stages);   // TMA-staged K3 (PK_K3_WINDOW / PK_K3W_VARIANT / PK_K3W_STAGES)
 void pk_part_plan(uint64_t n, PkPartPlan *pl);
 void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
 void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t off, uint64_t n, PkKeySpec ks,

@@ -437,6 +437,279 @@ __global__ void __launch_bounds__(T, MINB) probe_part_kernel(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------ K3w: table windows staged in shared memory by TMA
+// The L1TEX tag stage bounds probe_part_kernel (one 32 B sector per lane and probe: 1.29 G tag lookups, 86 %
+// busy on configs[1]). Every probe of a block falls inside one contiguous window of each table (the
+// partition's hash range), and with ~4 probes per bucket nearly every sector of that window is needed anyway:
+// so one elected thread streams the whole window of genome g into shared memory with a TMA bulk copy
+// (cp.async.bulk.shared.global, completion on an mbarrier, a ring of n_stages windows in flight ahead of the
+// probes) and the lanes probe shared memory. DRAM sees purely sequential 4-8 KB reads, the L1 tag stage sees
+// nothing, and a walk-on into the next bucket is one more shared-memory read instead of a deferred global one.
+// Only a walk-on past the end of the window (or a table whose window does not fit a stage) takes the old
+// global path.
+#define PW_MAX_STAGES 4
+#define PW_QCAP 256
+#define PW_MAX_STAGE_BYTES 16384u
+
+__device__ __forceinline__ uint32_t pw_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pw_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pw_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void pw_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pw_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// bounded wait: a copy that never lands (which would be a bug) traps instead of hanging the GPU
+__device__ __forceinline__ void pw_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 22)) __trap();
+    }
+}
+
+// one LDS.128 (the compiler otherwise splits the bucket into lazily evaluated 32-bit loads)
+__device__ __forceinline__ uint4 pw_lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// a bucket read as its two 16-byte halves (in either order); `last` is the half that holds the last slot
+template <int FMT> __device__ __forceinline__ bool pw_hit(const uint4 &A, const uint4 &B, uint64_t target) {
+    if (FMT == PK_FMT_S32) {
+        const uint32_t t = (uint32_t)target;
+        return (A.x == t) | (A.y == t) | (A.z == t) | (A.w == t) | (B.x == t) | (B.y == t) | (B.z == t) | (B.w == t);
+    }
+    const uint32_t lo = (uint32_t)target, hi = (uint32_t)(target >> 32);
+    return ((A.x == lo) & (A.y == hi)) | ((A.z == lo) & (A.w == hi)) | ((B.x == lo) & (B.y == hi)) | ((B.z == lo) & (B.w == hi));
+}
+template <int FMT> __device__ __forceinline__ bool pw_full(const uint4 &last) {
+    return FMT == PK_FMT_S32 ? last.w != PK_EMPTY32 : !(last.z == 0xFFFFFFFFu && last.w == 0xFFFFFFFFu);
+}
+
+template <int T, int IPT, int FMT, int SORT, int MINB>
+__global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constant__ ProbeArgs a, const uint32_t stage_bytes,
+                                                            const uint32_t n_stages) {
+    constexpr int CAP = T * IPT;
+    extern __shared__ __align__(128) uint8_t s_win[];          // [n_stages][stage_bytes]
+    __shared__ __align__(8) unsigned long long s_bar[PW_MAX_STAGES];
+    __shared__ uint32_t s_bits[CAP];               // results of the deferred (global) walk-ons, by item
+    __shared__ unsigned long long q_key[PW_QCAP];  // deferred queue: canonical k-mer,
+    __shared__ uint32_t q_meta[PW_QCAP], q_h[PW_QCAP];     //   (item << 5 | genome), hash
+    __shared__ uint32_t q_n, s_ws[T / 32];
+    __shared__ uint16_t o_wc[T / 32][PP_OBINS];
+    __shared__ uint32_t o_gb[PP_OBINS];
+    __shared__ unsigned long long s_canon[SORT ? CAP : 1];
+    __shared__ uint32_t s_h[SORT ? CAP : 1], s_pos[SORT ? CAP : 1], s_cnt[SORT ? PS_BINS : 1];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t sshift = a.pb + 10 <= 32 ? 32 - a.pb - 10 : 0;
+    const uint32_t win0 = pw_smem(s_win), bar0 = pw_smem(s_bar);
+    if (tid == 0) {
+        for (uint32_t s = 0; s < n_stages; s++) pw_mbar_init(bar0 + 8 * s, 1);
+        pw_mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t par = 0;            // bit s: the phase parity the next wait on stage s expects
+    for (uint64_t q = blockIdx.x; q < a.n_regions; q += gridDim.x) {
+        const uint32_t cnt = min(a.counts[q], a.cap);
+        if (cnt == 0) continue;
+        const uint32_t h_lo = (uint32_t)(q << (32 - a.pb));
+        const uint32_t h_hi = (uint32_t)(((q + 1) << (32 - a.pb)) - 1);
+        // window of genome g = buckets [b0, b1] of its table; streamed into stage g % n_stages when it fits
+        auto issue = [&](uint32_t g) {
+            const PkTable t = a.tabs[g];
+            const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
+            const uint32_t bytes = (b1 - b0 + 1) * 32;
+            if (bytes <= stage_bytes) {
+                const uint32_t s = g % n_stages;
+                pw_mbar_expect_tx(bar0 + 8 * s, bytes);
+                pw_bulk_g2s(win0 + s * stage_bytes, t.slots + 4ull * b0, bytes, bar0 + 8 * s);
+            }
+        };
+        if (tid == 0)
+            for (uint32_t g = 0; g < n_stages && g < a.ng; g++) issue(g);
+        if (SORT) for (uint32_t i = tid; i < PS_BINS; i += T) s_cnt[i] = 0;
+        for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
+        for (uint32_t i = tid; i < (T / 32) * PP_OBINS; i += T) (&o_wc[0][0])[i] = 0;
+        if (tid == 0) q_n = 0;
+        __syncthreads();
+        const uint2 *src = a.buf + q * (uint64_t)a.cap;
+        uint64_t canon[IPT];
+        uint32_t h[IPT], pos[IPT], rnk[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const uint32_t i = tid + j * T;
+            canon[j] = 0; h[j] = 0; pos[j] = 0; rnk[j] = 0;
+            if (i < cnt) {
+                const uint2 it = src[i];
+                canon[j] = pk_canon_at(a.words, a.p0 + it.y, a.ks.k);
+                h[j] = it.x; pos[j] = it.y;
+                if (SORT) rnk[j] = atomicAdd(&s_cnt[(it.x >> sshift) & (PS_BINS - 1)], 1u);
+            }
+        }
+        if (SORT) {
+            __syncthreads();
+            {   // exclusive scan of s_cnt[PS_BINS], PS_BINS / T bins per thread
+                constexpr int BPT = PS_BINS / T;
+                uint32_t c[BPT], sum = 0;
+#pragma unroll
+                for (int b = 0; b < BPT; b++) { c[b] = s_cnt[tid * BPT + b]; sum += c[b]; }
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= (uint32_t)o) inc += y;
+                }
+                if (lane == 31) s_ws[wid] = inc;
+                __syncthreads();
+                uint32_t off = inc - sum;
+#pragma unroll
+                for (int ww = 0; ww < T / 32; ww++) off += ww < (int)wid ? s_ws[ww] : 0;
+#pragma unroll
+                for (int b = 0; b < BPT; b++) { s_cnt[tid * BPT + b] = off; off += c[b]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                if (tid + j * T < cnt) {
+                    const uint32_t d = s_cnt[(h[j] >> sshift) & (PS_BINS - 1)] + rnk[j];
+                    s_canon[d] = canon[j]; s_h[d] = h[j]; s_pos[d] = pos[j];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                const uint32_t i = tid + j * T;
+                if (i < cnt) { canon[j] = s_canon[i]; h[j] = s_h[i]; pos[j] = s_pos[i]; }
+            }
+        }
+        uint32_t bits[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) bits[j] = 0;
+        // ---- probe, genome by genome, out of the staged windows
+        for (uint32_t g = 0; g < a.ng; g++) {
+            const PkTable t = a.tabs[g];
+            const uint32_t s = g % n_stages;
+            const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
+            const uint32_t nbk = b1 - b0 + 1;
+            const bool wok = nbk * 32 <= stage_bytes;
+            const uint32_t maxd = pk_max_disp<FMT>(t.n_buckets);
+            if (wok) {
+                pw_mbar_wait(bar0 + 8 * s, (par >> s) & 1);
+                par ^= 1u << s;
+            }
+            const uint32_t win = win0 + s * stage_bytes;
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                const uint32_t i = tid + j * T;
+                if (i < cnt) {
+                    int res = 0;            // 0 absent, 1 present, 2 undecided: resolve through global memory
+                    if (wok) {
+                        const uint32_t off = __umulhi(h[j], t.n_buckets) - b0;
+                        const uint32_t x = lane & 1;          // odd lanes read the halves in the other order: spreads the banks
+                        for (uint32_t r = 0;; r++) {
+                            const uint32_t wa = win + (off + r) * 32 + x * 16;
+                            const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
+                            if (pw_hit<FMT>(A, B, pk_target<FMT>(canon[j], r))) { res = 1; break; }
+                            if (!pw_full<FMT>(x ? A : B)) break;
+                            if (r == maxd || off + r + 1 >= nbk) { res = 2; break; }
+                        }
+                    } else {
+                        const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
+                        if (pk_bucket_hit<FMT>(v, pk_target<FMT>(canon[j], 0))) res = 1;
+                        else if (pk_bucket_full<FMT>(v)) res = 2;
+                    }
+                    if (res == 1) {
+                        bits[j] |= 1u << g;
+                    } else if (res == 2) {
+                        const uint32_t slot = atomicAdd(&q_n, 1u);
+                        if (slot < (uint32_t)PW_QCAP) {
+                            q_key[slot] = canon[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
+                        } else if (pk_lookup<FMT>(t, canon[j], h[j], 32 * a.grp + g, a.ks)) {
+                            bits[j] |= 1u << g;
+                        }
+                    }
+                }
+            }
+            if (g + n_stages < a.ng) {
+                __syncthreads();            // every lane is done with stage s: refill it
+                if (tid == 0) issue(g + n_stages);
+            }
+        }
+        __syncthreads();
+        {
+            const uint32_t nq = min(q_n, (uint32_t)PW_QCAP);
+            for (uint32_t e = tid; e < nq; e += T) {
+                const uint32_t meta = q_meta[e], g = meta & 31;
+                if (pk_lookup<FMT>(a.tabs[g], q_key[e], q_h[e], 32 * a.grp + g, a.ks)) atomicOr(&s_bits[meta >> 5], 1u << g);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < IPT; j++)
+            if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
+        if (a.out_list) {
+            uint16_t rank[IPT];
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                const bool v = tid + j * T < cnt;
+                const uint32_t bin = v ? pos[j] >> a.out_shift : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (v && lane == leader) {
+                    old = o_wc[wid][bin];
+                    o_wc[wid][bin] = (uint16_t)(old + __popc(peers));
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rank[j] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1)));
+                __syncwarp();
+            }
+            __syncthreads();
+            for (uint32_t b = tid; b < PP_OBINS; b += T) {
+                uint32_t run = 0;
+#pragma unroll
+                for (int ww = 0; ww < T / 32; ww++) {
+                    const uint32_t tt = o_wc[ww][b];
+                    o_wc[ww][b] = (uint16_t)run;
+                    run += tt;
+                }
+                if (run) o_gb[b] = atomicAdd(&a.out_cursor[a.grp * PP_OBINS + b], run);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                if (tid + j * T < cnt) {
+                    const uint32_t bin = pos[j] >> a.out_shift;
+                    const uint64_t slot = (((uint64_t)a.grp * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + o_wc[wid][bin] + rank[j];
+                    a.out_list[slot] = make_uint2(pos[j], bits[j]);
+                }
+            }
+        } else {
+            const uint32_t nb = min(4u, a.nbl - 4 * a.grp);
+            const bool al4 = nb == 4 && ((a.row_stride | a.col_offset) & 3) == 0;
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                if (tid + j * T < cnt) {
+                    uint8_t *dst = a.rows + (uint64_t)pos[j] * a.row_stride + a.col_offset + 4 * a.grp;
+                    if (al4) *(uint32_t *)dst = bits[j];
+                    else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(bits[j] >> (8 * qb));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // variants of K3 selectable at run time (PK_K3_VARIANT) while the design is being tuned
 struct K3Variant { int threads, cap; void (*fn[2])(ProbeArgs); };   // fn[fmt]
 #define K3V(T, IPT, SORT, MINB, GU) {T, T * IPT, {probe_part_kernel<T, IPT, PK_FMT_S64, SORT, MINB, GU>, probe_part_kernel<T, IPT, PK_FMT_S32, SORT, MINB, GU>}}
@@ -459,6 +732,38 @@ void pk_part_set_variant(int v) { if (v >= -1 && v < (int)(sizeof k3_variants / 
 static const K3Variant &k3_pick(uint32_t n_genomes_in_launch) {
     if (g_k3_variant >= 0) return k3_variants[g_k3_variant];
     return k3_variants[n_genomes_in_launch >= 16 ? 1 : 0];
+}
+
+// window (TMA-staged) variants of K3; same block capacity as variants 0/1, so the partition plan is shared
+struct K3WinVariant { int threads, cap, static_smem; void (*fn[2])(ProbeArgs, uint32_t, uint32_t); };
+#define K3W(T, IPT, SORT, MINB) {T, T * IPT, 0, {probe_win_kernel<T, IPT, PK_FMT_S64, SORT, MINB>, probe_win_kernel<T, IPT, PK_FMT_S32, SORT, MINB>}}
+static const K3WinVariant k3w_variants[] = {
+    K3W(256, 3, 0, 6),      // 0: unsorted
+    K3W(256, 3, 1, 4),      // 1: bucket-sorted (lanes of a warp read neighbouring buckets: fewer bank conflicts)
+    K3W(256, 3, 0, 8),      // 2: 8 blocks/SM (32 registers)
+    K3W(256, 3, 0, 4),      // 3
+};
+static int g_k3_window = 1;          // 0: never use the window kernels
+static int g_k3w_variant = -1;       // -1 auto
+static int g_k3w_stages = 3;
+void pk_part_set_window(int enable, int variant, int stages) {
+    g_k3_window = enable;
+    if (variant >= -1 && variant < (int)(sizeof k3w_variants / sizeof k3w_variants[0])) g_k3w_variant = variant;
+    if (stages >= 1 && stages <= PW_MAX_STAGES) g_k3w_stages = stages;
+}
+static const K3WinVariant &k3w_pick(uint32_t n_genomes_in_launch) {
+    if (g_k3w_variant >= 0) return k3w_variants[g_k3w_variant];
+    return k3w_variants[n_genomes_in_launch >= 16 ? 1 : 0];
+}
+// bytes one stage must hold for every table of the launch, or 0 when some window does not fit a stage
+static uint32_t k3w_stage_bytes(const PkTable *tabs, uint32_t ng, uint32_t pb) {
+    uint64_t mx = 0;
+    for (uint32_t g = 0; g < ng; g++) {
+        const uint64_t nbk = ((uint64_t)tabs[g].n_buckets >> pb) + 2;       // b1 - b0 + 1 <= ceil(nb / 2^pb) + 1
+        mx = nbk > mx ? nbk : mx;
+    }
+    const uint64_t bytes = (mx * 32 + 127) & ~127ull;
+    return bytes <= PW_MAX_STAGE_BYTES ? (uint32_t)bytes : 0;
 }
 
 // K4: scatter the (pos, bits) lists into rows. All blocks of one bin write inside a slice of
@@ -569,8 +874,17 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     for (uint32_t grp = 0; grp < n_groups; grp++) {       // one launch per group of 32 genomes
         p.grp = grp; p.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         for (uint32_t g = 0; g < p.ng; g++) p.tabs[g] = h_tables[32 * grp + g];
-        const K3Variant &kv = k3_pick(p.ng);
-        kv.fn[fi]<<<p.n_regions, kv.threads, 0, s>>>(p);
+        const uint32_t stage_bytes = g_k3_window && k3_pick(p.ng).cap == k3w_pick(p.ng).cap ? k3w_stage_bytes(p.tabs, p.ng, p.pb) : 0;
+        if (stage_bytes) {
+            const K3WinVariant &wv = k3w_pick(p.ng);
+            const uint32_t stages = g_k3w_stages;
+            const size_t dyn = (size_t)stages * stage_bytes;
+            cudaFuncSetAttribute(wv.fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
+            wv.fn[fi]<<<p.n_regions, wv.threads, dyn, s>>>(p, stage_bytes, stages);
+        } else {
+            const K3Variant &kv = k3_pick(p.ng);
+            kv.fn[fi]<<<p.n_regions, kv.threads, 0, s>>>(p);
+        }
     }
     if (evs) cudaEventRecord(evs[3], s);
     ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)

@@ -198,6 +198,11 @@ class Engine:
         check(self._L.pk_engine_stats(self._h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in s._fields_}
 
+    def tune(self, **knobs):
+        """Tuning knobs of the partitioned probe (pk_engine_tune); results never depend on them."""
+        for name, value in knobs.items():
+            check(self._L.pk_engine_tune(self._h, name.encode(), int(value)))
+
     # ---- hot path, device pointers (ints; e.g. torch.Tensor.data_ptr()) ------
     def packed_words(self, length: int) -> int:
         return int(self._L.pk_packed_words(length))

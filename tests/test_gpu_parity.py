@@ -315,6 +315,43 @@ def test_partitioned_path_large_vs_oracle_and_direct(n_genomes, k, repeats, load
     assert (rp["chroms"][0]["bin_hist"] == want["bin_hist"]).all()
 
 
+@pytest.mark.parametrize("n_genomes,k,load", [(8, 21, 0.5), (20, 31, 0.7)])
+def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
+    """The TMA-staged window kernel (every variant / stage count), the L1/L2 kernel and the direct kernel
+    give identical rows; so does a batch whose table windows are too large for a shared-memory stage."""
+    genomes = big_case(n_genomes, k, 1_400_000, 77 + n_genomes)
+    eng = Engine(k, n_genomes, load_factor=load, probe_mode="partitioned")
+    engd = Engine(k, n_genomes, load_factor=load, probe_mode="direct")
+    for g, chroms in enumerate(genomes):
+        for e in (eng, engd):
+            e.reserve(g, sum(s.size for _, s in chroms))
+            for _, s in chroms:
+                e.add_sequence(g, s)
+    eng.finalize(); engd.finalize()
+    seqs = [s for _, s in genomes[2]]
+    want = engd.anchor_genome(seqs)
+    try:
+        for knobs in (dict(k3_window=1, k3w_variant=-1, k3w_stages=3), dict(k3w_variant=0, k3w_stages=1),
+                      dict(k3w_variant=1, k3w_stages=2), dict(k3w_variant=2, k3w_stages=4), dict(k3w_variant=3),
+                      dict(k3_window=0), dict(k3_window=1, k3w_variant=-1, k3w_stages=3, unpermute=0)):
+            eng.tune(**knobs)
+            got = eng.anchor_genome(seqs)
+            assert (got["col_sums"] == want["col_sums"]).all(), knobs
+            for a, b in zip(got["chroms"], want["chroms"]):
+                assert (a["bitmap1"] == b["bitmap1"]).all(), knobs
+                assert (a["bin_hist"] == b["bin_hist"]).all(), knobs
+        # a short anchor against the same (large) tables: few partitions -> windows of > 16 KB -> L1/L2 kernel
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_stages=3, unpermute=1)
+        short = seqs[0][:30_000]
+        a = eng.anchor_chrom(short, hist=False)["bitmap1"]
+        b = engd.anchor_chrom(short, hist=False)["bitmap1"]
+        assert (a == b).all()
+    finally:
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_stages=3, unpermute=1)
+    with pytest.raises(_lib.PkError):
+        eng.tune(no_such_knob=1)
+
+
 def test_panagram_index_cli_end_to_end(pan3, tmp_path, capsys):
     """`panagram index` from a samples TSV: k-mer sets built on the GPU from the FASTAs, every anchor
     directory byte-compatible with the reference's run_anchor output; bitdump reads it back."""
