@@ -327,6 +327,8 @@ def main():
         h[:] = c
         h_chroms.append(h)
     e2e_ms = None
+    e2e_files = None
+    e2e_timeline = None
     if world == 1:
         res = eng.anchor_genome(h_chroms, pinned=True)          # allocates the pinned output buffers once
         for _ in range(max(1, args.warmup - 1)):
@@ -339,9 +341,27 @@ def main():
             ts.append((time.perf_counter() - t1) * 1e3)
         e2e_ms = sum(ts) / len(ts)
         e2e_stats = eng.stats()
+        # CUDA events of the last call on the engine's streams: H2D + pack + K1 (overlapped) | K2 + K3 | K4 + reduce per
+        # chromosome | tail of the D2H copies
+        e2e_timeline = {"h2d_pack_partition": e2e_stats["h2d_ms"], "probe": e2e_stats["probe_ms"],
+                        "unpermute_reduce": e2e_stats["reduce_ms"], "d2h_tail": e2e_stats["d2h_ms"], "total": e2e_stats["total_ms"]}
         h2d = sum(lens)
         d2h = sum(r["bitmap1"].nbytes + r["low"].nbytes + r["bin_hist"].nbytes for r in res["chroms"]) + 8 * npg
         e2e_launches = e2e_stats["kernel_launches"]
+        # the same call delivering bitmap.1.gz/.gzi + bitmap.100.gz/.gzi as file images compressed on the GPU
+        rz = eng.anchor_genome_bgzf(h_chroms)
+        rz = eng.anchor_genome_bgzf(h_chroms, out=rz)
+        ts = []
+        for _ in range(args.steps):
+            t1 = time.perf_counter()
+            rz = eng.anchor_genome_bgzf(h_chroms, out=rz)
+            ts.append((time.perf_counter() - t1) * 1e3)
+        e2e_files = {"what": "pk_anchor_genome_bgzf: ASCII in (pinned host) -> bitmap.1.gz/.gzi + bitmap.100.gz/.gzi file "
+                             "images (BGZF deflated on the GPU) + histograms + column sums out",
+                     "ms_per_step": sum(ts) / len(ts), "value": positions * n_total / (sum(ts) / len(ts) / 1e3), "unit": unit,
+                     "h2d_bytes_per_step": int(h2d),
+                     "d2h_bytes_per_step": int(rz["gz"].size + rz["gzi"].size + rz["gz_low"].size + rz["gzi_low"].size),
+                     "raw_bitmap_bytes": int(positions * rb_local), "gz_bytes": int(rz["gz"].size)}
     else:
         # rank r: H2D of the anchor, pack, probe its shard, all-gather, interleave; rank 0 reads the rows back
         h_cat = pinned_empty(ltot); h_cat[:] = cat
@@ -381,7 +401,7 @@ def main():
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
             traffic = None
-        roof = {"bound": "hbm", "kernel": "probe_part_kernel" if ks["k_probe_ms"] > 0 else "probe_kernel",
+        roof = {"bound": "hbm", "kernel": ("probe_win_kernel" if ks.get("k_probe_window") else "probe_part_kernel") if ks["k_probe_ms"] > 0 else "probe_kernel",
                 "achieved": alg_bytes / (k3_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (k3_ms / 1e3) / 1e9 / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k3_ms,
@@ -414,8 +434,9 @@ def main():
                            if world > 1 else "1 GPU",
                            "setup_s": round(setup_s, 1)},
                 "e2e": {"value": positions * n_total / (e2e_ms / 1e3), "unit": unit, "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "device_timeline_ms": e2e_timeline},
+                "e2e_files": e2e_files, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "tables": {"keys": [t["n_keys"] for t in tstats], "overflow_frac": sum(t["n_overflow"] for t in tstats) /
                            max(1, sum(t["n_keys"] for t in tstats))}}
         print(json.dumps(line))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Sweep the tuning knobs of the partitioned probe on one workload with the tables built ONCE.
 
-  python bench/k3_sweep.py [--workload configs1] [--steps 3] "k3_window=0" "k3w_variant=0,k3w_stages=3" ...
+  python bench/k3_sweep.py [--workload configs1] [--steps 3] "k3_window=0" "k3w_variant=0,k3w_group=3" ...
 
 For every setting: CUDA-event times of K1..K4 (pk_engine_stats) of the last of `steps` launches, the stage
 time over all steps, and a checksum of the rows (all settings must agree with the first)."""

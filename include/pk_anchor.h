@@ -208,10 +208,34 @@ int pk_ipc_close(pk_engine *e, void *d_ptr);
 int pk_gather_interleave_device(pk_engine *e, const void *const *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w,
                                 void *d_rows, uint32_t row_stride, void *stream);
 
+/* ---- BGZF output on the GPU ------------------------------------------------------
+ * Replaces bgzf_open/bgzf_index_build_init/bgzf_write/bgzf_index_dump/bgzf_close as KMCdb::anchor_fasta and
+ * write_bits use them (cpp/anchor.cpp:46-54,102-106,167,177; Python path: bgzip.BGZipWriter + `bgzip -rI`,
+ * panagram/index.py:1035-1037,1089-1094): device bytes in, the complete image of the .gz (BGZF: gzip members of
+ * <= 0xff00 payload bytes + the 28-byte EOF member) and of its .gzi (uint64 n, then n x (compressed offset,
+ * uncompressed offset) of every member after the first — what Genome.load_bgz_blocks reads, index.py:793-799)
+ * out. The deflate streams differ from zlib's (one warp per member, fixed Huffman codes, matches at
+ * `match_dist` = the row width only); the DECOMPRESSED bytes, which is what parity is defined on, are identical.
+ *   pk_bgzf_bound / pk_bgzf_gzi_bound: capacity the two images need for n_bytes of payload.
+ *   pk_bgzf_compress_device: d_gz / d_gzi device buffers of at least those sizes; d_totals: 2 x uint64 on
+ *     the device = bytes of the .gz image, bytes of the .gzi image. Asynchronous on `stream`.
+ *   pk_anchor_genome_bgzf: pk_anchor_genome with the step-1 and low-res bitmaps delivered as file images
+ *     (all chromosomes of the anchor form ONE stream, as in the reference) into caller-owned HOST buffers
+ *     gz[2] / gzi[2] (index 0: step 1, index 1: lowres_step) of capacities gz_cap[2] / gzi_cap[2]
+ *     (>= the bounds above for sum(nkmers) * row_bytes and sum(ceil(nkmers/step)) * row_bytes);
+ *     sizes[4] receives gz bytes, gzi bytes (step 1), gz bytes, gzi bytes (low-res). */
+uint64_t pk_bgzf_bound(uint64_t n_bytes);
+uint64_t pk_bgzf_gzi_bound(uint64_t n_bytes);
+int pk_bgzf_compress_device(pk_engine *e, const void *d_in, uint64_t n_bytes, uint32_t match_dist, void *d_gz,
+                            void *d_gzi, void *d_totals, void *stream);
+int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                          uint8_t *const *gz, const uint64_t *gz_cap, uint8_t *const *gzi, const uint64_t *gzi_cap,
+                          uint64_t *sizes, uint64_t *const *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out);
+
 /* Tuning knobs of the partitioned probe (process-wide; no reference counterpart). Results never depend on
  * them; tests run the parity suite under several settings. name = "k3_window" (1: probe out of table
  * windows staged in shared memory by TMA bulk copies when they fit, 0: always probe through L1/L2),
- * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_stages" (1..4 windows in flight per block),
+ * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_group" (1, 2 or 4 genomes per window group; two groups of windows are staged per block),
  * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "unpermute" (0/1: applies to
  * scratch allocated afterwards). Unknown names return PK_EINVAL. */
 int pk_engine_tune(pk_engine *e, const char *name, int value);
@@ -222,7 +246,8 @@ typedef struct pk_stats {
     /* CUDA-event durations of the kernels of the last partitioned probe launch, on the stream
      * they ran on: K1 partition_seq, K2 partition_fine, K3 probe_part, K3 over the spill list,
      * K4 unpermute */
-    float k_partition_ms, k_fine_ms, k_probe_ms, k_spill_ms, k_unpermute_ms, _pad;
+    float k_partition_ms, k_fine_ms, k_probe_ms, k_spill_ms, k_unpermute_ms;
+    float k_probe_window;    /* 1 when K3 ran as probe_win_kernel (windows staged by TMA), 0 for probe_part_kernel */
     uint64_t positions, probes, probe_launches, kernel_launches;
 } pk_stats;
 int pk_engine_stats(const pk_engine *e, pk_stats *out);

@@ -47,7 +47,7 @@ class PkStats(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("probe_ms", C.c_float),
                 ("reduce_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("k_partition_ms", C.c_float), ("k_fine_ms", C.c_float), ("k_probe_ms", C.c_float),
-                ("k_spill_ms", C.c_float), ("k_unpermute_ms", C.c_float), ("_pad", C.c_float),
+                ("k_spill_ms", C.c_float), ("k_unpermute_ms", C.c_float), ("k_probe_window", C.c_float),
                 ("positions", C.c_uint64), ("probes", C.c_uint64), ("probe_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64)]
 
@@ -86,6 +86,10 @@ SIGNATURES = {
     "pk_interleave_device": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _vp, _u32, _vp]),
     "pk_engine_stats": (C.c_int, [_vp, C.POINTER(PkStats)]),
     "pk_engine_tune": (C.c_int, [_vp, _cp, C.c_int]),
+    "pk_bgzf_bound": (_u64, [_u64]),
+    "pk_bgzf_gzi_bound": (_u64, [_u64]),
+    "pk_bgzf_compress_device": (C.c_int, [_vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "pk_anchor_genome_bgzf": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pk_device_alloc": (C.c_int, [_vp, _pp, _sz]),
     "pk_device_free": (C.c_int, [_vp, _vp]),
     "pk_ipc_export": (C.c_int, [_vp, _vp, _vp]),

@@ -59,37 +59,51 @@ def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
 
 
 def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[str] | None = None,
-                 bgzf_level: int = 6, threads: int | None = None, strip_cr: bool = False) -> dict:
+                 bgzf_level: int = 6, threads: int | None = None, strip_cr: bool = False,
+                 bgzf: str = "gpu") -> dict:
     """Anchor one genome and write its directory. Returns summary numbers.
 
     The engine must hold all N genomes (single-GPU layout). Chromosomes shorter
     than k + min_bin_count - 1 have no defined bins in the reference
     (cpp/anchor.cpp:116-120 divides by zero): they raise ValueError here.
+    bgzf="gpu": the .gz/.gzi files are compressed on the GPU (pk_anchor_genome_bgzf) and arrive as file
+    images; bgzf="zlib": raw rows come back and are deflated by zlib on a host thread pool
+    (`bgzf_level`, `threads`). Both decompress to the same bytes.
     """
     outdir = Path(outdir)
     outdir.mkdir(parents=True, exist_ok=True)
     threads = threads or min(32, os.cpu_count() or 1)
     step = engine.lowres_step
-    w1 = layout.BgzfWriter(outdir / "bitmap.1.gz", bgzf_level, threads)
-    wl = layout.BgzfWriter(outdir / f"bitmap.{step}.gz", bgzf_level, threads)
-    chroms, bins = [], []
-    positions = 0
     recs = parse_fasta(fasta, strip_cr=strip_cr)
     for cname, seq in recs:
         nk = seq.size - engine.k + 1
         if nk < 1 or engine.bin_len(nk) == 0:
             raise ValueError(f"{fasta}: chromosome {cname!r} has {max(nk, 0)} k-mers; the reference "
                              "needs at least min_bin_count (cpp/anchor.cpp:116-120)")
-    res = engine.anchor_genome([s for _, s in recs], pinned=True)     # the whole genome in one batch
+    chroms, bins = [], []
+    positions = 0
+    if bgzf == "gpu":
+        res = engine.anchor_genome_bgzf([s for _, s in recs])             # the whole genome in one batch
+        for key, fn in (("gz", "bitmap.1.gz"), ("gzi", "bitmap.1.gzi"), ("gz_low", f"bitmap.{step}.gz"),
+                        ("gzi_low", f"bitmap.{step}.gzi")):
+            with open(outdir / fn, "wb") as fh:
+                fh.write(res[key].data)
+    elif bgzf == "zlib":
+        w1 = layout.BgzfWriter(outdir / "bitmap.1.gz", bgzf_level, threads)
+        wl = layout.BgzfWriter(outdir / f"bitmap.{step}.gz", bgzf_level, threads)
+        res = engine.anchor_genome([s for _, s in recs], pinned=True)
+        for r in res["chroms"]:
+            w1.write(r["bitmap1"])
+            wl.write(r["low"])
+        w1.close(outdir / "bitmap.1.gzi")
+        wl.close(outdir / f"bitmap.{step}.gzi")
+    else:
+        raise ValueError(f"bgzf={bgzf!r}: expected 'gpu' or 'zlib'")
     col = res["col_sums"]
     for (cname, _), r in zip(recs, res["chroms"]):
-        w1.write(r["bitmap1"])
-        wl.write(r["low"])
         chroms.append((cname, r["nkmers"]))
         bins.append((r["binlen"], r["bin_hist"]))
         positions += r["nkmers"]
-    w1.close(outdir / "bitmap.1.gzi")
-    wl.close(outdir / f"bitmap.{step}.gzi")
     (outdir / "chrs.tsv").write_text(layout.chrs_tsv(chroms))
     (outdir / "bitsum.bins.tsv").write_text(layout.bins_tsv(engine.n_local, bins))
     if genome_names is not None and name in genome_names:

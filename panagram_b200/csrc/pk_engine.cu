@@ -30,7 +30,7 @@ void pk_set_error(const char *fmt, ...) {
     } while (0)
 
 // process-wide tuning state of the partitioned probe (pk_engine_tune / PK_K3* environment variables)
-static int g_tune_window = 0, g_tune_wvariant = -1, g_tune_wstages = 3;   // window kernel off by default until measured
+static int g_tune_window = 1, g_tune_wvariant = -1, g_tune_wstages = 4;
 
 // ------------------------------------------------------------------ engine
 struct HostTable {
@@ -72,6 +72,13 @@ struct pk_engine {
     // staging for KMC ingestion
     uint8_t *h_stage = nullptr, *d_stage = nullptr;
     size_t stage_bytes = 0;
+    // on-GPU BGZF writer: CRC tables, scratch, the contiguous row stream and the two file images (grow-only)
+    uint32_t *z_tables = nullptr;
+    uint8_t *z_scratch = nullptr; uint64_t z_scratch_cap = 0;
+    uint8_t *z_cat = nullptr; uint64_t z_cat_cap = 0;
+    uint8_t *z_gz[2] = {nullptr, nullptr}; uint64_t z_gz_cap[2] = {0, 0};
+    unsigned long long *z_gzi[2] = {nullptr, nullptr}; uint64_t z_gzi_cap[2] = {0, 0};
+    unsigned long long *z_totals = nullptr;     // [4]
     pk_stats stats{};
 };
 
@@ -140,10 +147,10 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (const char *up = getenv("PK_UNPERMUTE")) e->unpermute = atoi(up);
     if (const char *kv = getenv("PK_K3_VARIANT")) pk_part_set_variant(atoi(kv));
     {
-        const char *we = getenv("PK_K3_WINDOW"), *wv = getenv("PK_K3W_VARIANT"), *ws = getenv("PK_K3W_STAGES");
+        const char *we = getenv("PK_K3_WINDOW"), *wv = getenv("PK_K3W_VARIANT"), *ws = getenv("PK_K3W_GROUP");
         if (we) g_tune_window = atoi(we);
         if (wv) g_tune_wvariant = atoi(wv);
-        if (ws && atoi(ws) >= 1 && atoi(ws) <= 4) g_tune_wstages = atoi(ws);
+        if (ws && (atoi(ws) == 1 || atoi(ws) == 2 || atoi(ws) == 4)) g_tune_wstages = atoi(ws);
         pk_part_set_window(g_tune_window, g_tune_wvariant, g_tune_wstages);
     }
     e->n_local = cfg->genome_end - cfg->genome_begin;
@@ -180,6 +187,9 @@ extern "C" void pk_engine_destroy(pk_engine *e) {
     cudaFree(e->ks.stash); cudaFree(e->ks.stash_n);
     cudaFree(e->d_tables); cudaFree(e->d_counters); cudaFree(e->d_colsums); cudaFree(e->d_hist);
     cudaFree(e->d_stage);
+    cudaFree(e->z_tables); cudaFree(e->z_scratch); cudaFree(e->z_cat); cudaFree(e->z_totals);
+    for (int i = 0; i < 2; i++) { cudaFree(e->z_gz[i]); cudaFree(e->z_gzi[i]); }
+    cudaFree(e->sc.out_list); cudaFree(e->sc.out_cursor);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -591,9 +601,23 @@ template <typename T> static int grow(T *&p, uint64_t &cap, uint64_t need) {
     return PK_OK;
 }
 
-extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
-                                uint8_t *const *bitmap1, uint8_t *const *bitmap_low, uint64_t *const *bin_hist,
-                                uint64_t *col_sums, uint64_t *nkmers_out) {
+// file images requested from anchor_genome_impl (pk_anchor_genome_bgzf): [0] step 1, [1] low-res
+struct BgzfOut {
+    uint8_t *const *gz; const uint64_t *gz_cap; uint8_t *const *gzi; const uint64_t *gzi_cap; uint64_t *sizes;
+};
+static int ensure_bgzf_tables(pk_engine *e) {
+    if (e->z_tables) return PK_OK;
+    std::vector<uint32_t> h(PK_BGZF_TABLE_WORDS);
+    pk_bgzf_tables_host(h.data());
+    CU(cudaMalloc(&e->z_tables, h.size() * 4));
+    CU(cudaMemcpy(e->z_tables, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&e->z_totals, 4 * sizeof(unsigned long long)));
+    return PK_OK;
+}
+
+static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                              uint8_t *const *bitmap1, uint8_t *const *bitmap_low, uint64_t *const *bin_hist,
+                              uint64_t *col_sums, uint64_t *nkmers_out, const BgzfOut *z) {
     NEED_FINAL(e);
     if (n_chroms && (!seqs || !lens)) { pk_set_error("null argument"); return PK_EINVAL; }
     const uint32_t k = e->cfg.k, step = e->cfg.lowres_step, rb = e->row_bytes, N = e->n_local;
@@ -620,8 +644,41 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
         postot += nk[c];
         if (nkmers_out) nkmers_out[c] = nk[c];
     }
-    if (postot == 0) return PK_OK;
+    if (z) {
+        if (!z->gz || !z->gzi || !z->gz_cap || !z->gzi_cap || !z->sizes) { pk_set_error("null argument"); return PK_EINVAL; }
+        const uint64_t nbytes[2] = {postot * rb, lowtot * rb};
+        for (int i = 0; i < 2; i++) {
+            if (!z->gz[i] || !z->gzi[i]) { pk_set_error("null argument"); return PK_EINVAL; }
+            if (z->gz_cap[i] < pk_bgzf_bound_impl(nbytes[i]) || z->gzi_cap[i] < pk_bgzf_gzi_bound_impl(nbytes[i])) {
+                pk_set_error("BGZF output %d: capacity %llu / %llu below pk_bgzf_bound %llu / pk_bgzf_gzi_bound %llu", i,
+                             (unsigned long long)z->gz_cap[i], (unsigned long long)z->gzi_cap[i],
+                             (unsigned long long)pk_bgzf_bound_impl(nbytes[i]), (unsigned long long)pk_bgzf_gzi_bound_impl(nbytes[i]));
+                return PK_EINVAL;
+            }
+        }
+    }
+    if (postot == 0) {
+        if (z) {       // nothing to write: both files are the bare EOF member, both indexes hold zero entries
+            static const uint8_t eof[28] = {0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 0x42, 0x43, 2, 0, 0x1B, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 2; i++) {
+                memcpy(z->gz[i], eof, sizeof eof);
+                memset(z->gzi[i], 0, 8);
+                z->sizes[2 * i] = sizeof eof; z->sizes[2 * i + 1] = 8;
+            }
+        }
+        return PK_OK;
+    }
     int rc = set_device(e); if (rc) return rc;
+    if (z) {
+        rc = ensure_bgzf_tables(e); if (rc) return rc;
+        const uint64_t nbytes[2] = {postot * rb, lowtot * rb};
+        rc = grow(e->z_cat, e->z_cat_cap, nbytes[0] + 16); if (rc) return rc;
+        rc = grow(e->z_scratch, e->z_scratch_cap, pk_bgzf_scratch_bytes(nbytes[0])); if (rc) return rc;
+        for (int i = 0; i < 2; i++) {
+            rc = grow(e->z_gz[i], e->z_gz_cap[i], pk_bgzf_bound_impl(nbytes[i])); if (rc) return rc;
+            rc = grow(e->z_gzi[i], e->z_gzi_cap[i], pk_bgzf_gzi_bound_impl(nbytes[i]) / 8 + 1); if (rc) return rc;
+        }
+    }
     const uint64_t nw = pk_packed_words(ltot);
     const uint64_t npos = ltot >= k ? ltot - k + 1 : 0;
     rc = grow(e->g_ascii, e->g_ascii_cap, ltot + 64); if (rc) return rc;
@@ -691,7 +748,7 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
         }
         const uint8_t *rows_c = e->g_rows + off[c] * rb;
         uint8_t *low_c = e->g_low + lowoff[c] * rb;
-        const bool want_low = bitmap_low && bitmap_low[c];
+        const bool want_low = (bitmap_low && bitmap_low[c]) || z;
         if (nbins[c] || col_sums || want_low) {
             pk_launch_reduce(rows_c, rb, N, 0, nk[c], nbins[c] ? binlen[c] : 0, nbins[c] ? e->d_hist + histoff[c] : nullptr,
                              col_sums ? e->d_colsums : nullptr, want_low ? low_c : nullptr, step, s);
@@ -701,7 +758,29 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
         CU(cudaEventRecord(done[c], s));
         CU(cudaStreamWaitEvent(cs, done[c], 0));
         if (bitmap1 && bitmap1[c]) CU(cudaMemcpyAsync(bitmap1[c], rows_c, nk[c] * rb, cudaMemcpyDeviceToHost, cs));
-        if (want_low) CU(cudaMemcpyAsync(bitmap_low[c], low_c, ((nk[c] + step - 1) / step) * rb, cudaMemcpyDeviceToHost, cs));
+        if (bitmap_low && bitmap_low[c]) CU(cudaMemcpyAsync(bitmap_low[c], low_c, ((nk[c] + step - 1) / step) * rb, cudaMemcpyDeviceToHost, cs));
+    }
+    if (z) {
+        // one stream per anchor, chromosomes back to back (cpp/anchor.cpp:167: bgzf_write appends chunk after chunk)
+        uint64_t so = 0;
+        for (uint32_t c = 0; c < n_chroms; c++) {
+            if (!nk[c]) continue;
+            CU(cudaMemcpyAsync(e->z_cat + so * rb, e->g_rows + off[c] * rb, nk[c] * rb, cudaMemcpyDeviceToDevice, s));
+            so += nk[c];
+        }
+        pk_launch_bgzf(e->z_cat, postot * rb, rb, e->z_gz[0], e->z_gzi[0], e->z_totals, e->z_scratch, e->z_tables, s);
+        pk_launch_bgzf(e->g_low, lowtot * rb, rb, e->z_gz[1], e->z_gzi[1], e->z_totals + 2, e->z_scratch, e->z_tables, s);
+        e->stats.kernel_launches += 6;
+        CU(cudaGetLastError());
+        unsigned long long tot[4];
+        CU(cudaMemcpyAsync(tot, e->z_totals, sizeof tot, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        for (int i = 0; i < 2; i++) {
+            if (tot[2 * i] > z->gz_cap[i] || tot[2 * i + 1] > z->gzi_cap[i]) { cleanup(); pk_set_error("BGZF image larger than its bound (internal error)"); return PK_ECUDA; }
+            CU(cudaMemcpyAsync(z->gz[i], e->z_gz[i], tot[2 * i], cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(z->gzi[i], e->z_gzi[i], tot[2 * i + 1], cudaMemcpyDeviceToHost, s));
+            z->sizes[2 * i] = tot[2 * i]; z->sizes[2 * i + 1] = tot[2 * i + 1];
+        }
     }
     CU(cudaEventRecord(e->ev[4], s));
     std::vector<unsigned long long> hist_h, col_h;
@@ -730,6 +809,35 @@ extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *con
     CU(cudaEventElapsedTime(&e->stats.total_ms, e->ev[0], e->ev[5]));
     e->stats.positions = postot;
     e->stats.probes = postot * N;
+    return PK_OK;
+}
+
+extern "C" int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                                uint8_t *const *bitmap1, uint8_t *const *bitmap_low, uint64_t *const *bin_hist,
+                                uint64_t *col_sums, uint64_t *nkmers_out) {
+    return anchor_genome_impl(e, n_chroms, seqs, lens, bitmap1, bitmap_low, bin_hist, col_sums, nkmers_out, nullptr);
+}
+
+extern "C" int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                                     uint8_t *const *gz, const uint64_t *gz_cap, uint8_t *const *gzi, const uint64_t *gzi_cap,
+                                     uint64_t *sizes, uint64_t *const *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out) {
+    const BgzfOut z{gz, gz_cap, gzi, gzi_cap, sizes};
+    return anchor_genome_impl(e, n_chroms, seqs, lens, nullptr, nullptr, bin_hist, col_sums, nkmers_out, &z);
+}
+
+extern "C" uint64_t pk_bgzf_bound(uint64_t n_bytes) { return pk_bgzf_bound_impl(n_bytes); }
+extern "C" uint64_t pk_bgzf_gzi_bound(uint64_t n_bytes) { return pk_bgzf_gzi_bound_impl(n_bytes); }
+extern "C" int pk_bgzf_compress_device(pk_engine *e, const void *d_in, uint64_t n_bytes, uint32_t match_dist, void *d_gz,
+                                       void *d_gzi, void *d_totals, void *stream) {
+    if (!e || (!d_in && n_bytes) || !d_gz || !d_gzi || !d_totals) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (match_dist < 1 || match_dist > 32768) { pk_set_error("match_dist %u out of 1..32768", match_dist); return PK_EINVAL; }
+    if ((uintptr_t)d_gzi & 7 || (uintptr_t)d_totals & 7) { pk_set_error("d_gzi / d_totals must be 8-byte aligned"); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    rc = ensure_bgzf_tables(e); if (rc) return rc;
+    rc = grow(e->z_scratch, e->z_scratch_cap, pk_bgzf_scratch_bytes(n_bytes)); if (rc) return rc;
+    pk_launch_bgzf((const uint8_t *)d_in, n_bytes, match_dist, (uint8_t *)d_gz, (unsigned long long *)d_gzi,
+                   (unsigned long long *)d_totals, e->z_scratch, e->z_tables, stream ? (pk_stream_t)stream : e->stream);
+    CU(cudaGetLastError());
     return PK_OK;
 }
 
@@ -787,7 +895,7 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     const std::string n(name);
     if (n == "k3_window") g_tune_window = value;
     else if (n == "k3w_variant") g_tune_wvariant = value;
-    else if (n == "k3w_stages") { if (value < 1 || value > 4) { pk_set_error("k3w_stages %d out of 1..4", value); return PK_EINVAL; } g_tune_wstages = value; }
+    else if (n == "k3w_group") { if (value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 1, 2 or 4", value); return PK_EINVAL; } g_tune_wstages = value; }
     else if (n == "k3_variant") { pk_part_set_variant(value); return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
     else if (n == "unpermute") {
@@ -808,6 +916,7 @@ extern "C" int pk_engine_stats(const pk_engine *e, pk_stats *out) {
     if (!e || !out) { pk_set_error("null argument"); return PK_EINVAL; }
     *out = e->stats;
     out->k_partition_ms = out->k_fine_ms = out->k_probe_ms = out->k_spill_ms = out->k_unpermute_ms = 0.f;
+    out->k_probe_window = (float)pk_part_last_window();
     if (e->pev_valid) {      // kernels of the last partitioned launch, timed on their own stream
         CU(cudaEventSynchronize(e->pev[5]));
         CU(cudaEventElapsedTime(&out->k_unpermute_ms, e->pev[4], e->pev[5]));

@@ -99,6 +99,16 @@ int pk_launch_gather_interleave(const void *const *planes, uint32_t n_ranks, uin
 void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
                            uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
 
+// ---- on-GPU BGZF writer (pk_bgzf.cu) ----
+#define PK_BGZF_TABLE_WORDS (256 + 17 * 32)      // CRC byte table + "append 2^j zero bytes" operators
+uint64_t pk_bgzf_blocks_impl(uint64_t n);
+uint64_t pk_bgzf_bound_impl(uint64_t n);
+uint64_t pk_bgzf_gzi_bound_impl(uint64_t n);
+uint64_t pk_bgzf_scratch_bytes(uint64_t n);
+void pk_bgzf_tables_host(uint32_t *dst /*[PK_BGZF_TABLE_WORDS]*/);
+void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_out, unsigned long long *d_gzi,
+                    unsigned long long *d_totals, uint8_t *d_scratch, const uint32_t *d_tables, pk_stream_t s);
+
 // ---- partitioned probe (pk_partition.cu) ----
 #define PK_PART_MAX_N (512ull << 20)   // positions per partitioned launch (2^18 partitions of <= 2560 mean fill)
 struct PkPartPlan {
@@ -117,6 +127,7 @@ struct PkPartScratch {
 };
 uint32_t pk_part_obins(void);
 void pk_part_set_variant(int v);
+int pk_part_last_window(void);
 void pk_part_set_window(int enable, int variant, int stages);   // TMA-staged K3 (PK_K3_WINDOW / PK_K3W_VARIANT / PK_K3W_STAGES)
 void pk_part_plan(uint64_t n, PkPartPlan *pl);
 void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);

@@ -442,14 +442,23 @@ __global__ void __launch_bounds__(T, MINB) probe_part_kernel(const __grid_consta
 // busy on configs[1]). Every probe of a block falls inside one contiguous window of each table (the
 // partition's hash range), and with ~4 probes per bucket nearly every sector of that window is needed anyway:
 // so one elected thread streams the whole window of genome g into shared memory with a TMA bulk copy
-// (cp.async.bulk.shared.global, completion on an mbarrier, a ring of n_stages windows in flight ahead of the
-// probes) and the lanes probe shared memory. DRAM sees purely sequential 4-8 KB reads, the L1 tag stage sees
-// nothing, and a walk-on into the next bucket is one more shared-memory read instead of a deferred global one.
-// Only a walk-on past the end of the window (or a table whose window does not fit a stage) takes the old
-// global path.
-#define PW_MAX_STAGES 4
-#define PW_QCAP 256
-#define PW_MAX_STAGE_BYTES 16384u
+// (cp.async.bulk.shared.global, completion on an mbarrier) and the lanes probe shared memory. DRAM sees
+// purely sequential 4-8 KB reads and the L1 tag stage sees nothing.
+//
+// Windows are staged in two groups of `gsz` genomes (2 * gsz stage buffers): while the lanes probe the
+// windows of one group, the copies of the next group are in flight; with <= 2 * gsz genomes in the launch
+// everything is issued up front and nothing is recycled. The probe loop is straight-line: a full home
+// bucket without the key (the key may sit in a later bucket) is pushed to a small queue, and after the
+// group's last genome all lanes drain the queue together — still out of the staged windows, one more
+// shared-memory read per step. Only a walk-on past the end of the window (or a table whose window does
+// not fit a stage) takes the global path.
+// First version (inline walk-on loop, 3-4 single-genome stages, 6 blocks/SM): 5.59 ms on configs[1], issue-bound
+// (149 thread-instructions per probe: rematerialised window geometry under a 40-register cap, and a
+// second trip round the walk-on loop for 40 % of the warp-iterations) — profiles/r1c_*.
+#define PW_MAX_GROUP 4
+#define PW_MAX_STAGES (2 * PW_MAX_GROUP)
+#define PW_QCAP 384
+#define PW_MAX_STAGE_BYTES 12288u
 
 __device__ __forceinline__ uint32_t pw_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pw_mbar_init(uint32_t bar, uint32_t count) {
@@ -495,29 +504,33 @@ template <int FMT> __device__ __forceinline__ bool pw_hit(const uint4 &A, const 
 template <int FMT> __device__ __forceinline__ bool pw_full(const uint4 &last) {
     return FMT == PK_FMT_S32 ? last.w != PK_EMPTY32 : !(last.z == 0xFFFFFFFFu && last.w == 0xFFFFFFFFu);
 }
+template <int FMT> struct PwKey { typedef uint64_t type; };
+template <> struct PwKey<PK_FMT_S32> { typedef uint32_t type; };      // S32 compares 32-bit slots: keep 32 bits per item
 
-template <int T, int IPT, int FMT, int SORT, int MINB>
+template <int T, int IPT, int FMT, int MINB>
 __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constant__ ProbeArgs a, const uint32_t stage_bytes,
-                                                            const uint32_t n_stages) {
+                                                            const uint32_t gsz) {
     constexpr int CAP = T * IPT;
-    extern __shared__ __align__(128) uint8_t s_win[];          // [n_stages][stage_bytes]
+    typedef typename PwKey<FMT>::type key_t;
+    extern __shared__ __align__(128) uint8_t s_win[];          // [2 * gsz][stage_bytes]
     __shared__ __align__(8) unsigned long long s_bar[PW_MAX_STAGES];
-    __shared__ uint32_t s_bits[CAP];               // results of the deferred (global) walk-ons, by item
-    __shared__ unsigned long long q_key[PW_QCAP];  // deferred queue: canonical k-mer,
-    __shared__ uint32_t q_meta[PW_QCAP], q_h[PW_QCAP];     //   (item << 5 | genome), hash
-    __shared__ uint32_t q_n, s_ws[T / 32];
+    __shared__ uint32_t s_bits[CAP];               // results of the deferred walk-ons, by item
+    __shared__ key_t q_key[PW_QCAP];                                       // deferred queue: key (as in the home bucket),
+    __shared__ uint32_t q_pos[PW_QCAP], q_h[PW_QCAP], q_meta[PW_QCAP];   //   position, hash, (item << 5 | genome)
+    __shared__ uint32_t q_n[2];
     __shared__ uint16_t o_wc[T / 32][PP_OBINS];
     __shared__ uint32_t o_gb[PP_OBINS];
-    __shared__ unsigned long long s_canon[SORT ? CAP : 1];
-    __shared__ uint32_t s_h[SORT ? CAP : 1], s_pos[SORT ? CAP : 1], s_cnt[SORT ? PS_BINS : 1];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t sshift = a.pb + 10 <= 32 ? 32 - a.pb - 10 : 0;
+    const uint32_t n_stages = 2 * gsz;
     const uint32_t win0 = pw_smem(s_win), bar0 = pw_smem(s_bar);
-    if (tid == 0) {
-        for (uint32_t s = 0; s < n_stages; s++) pw_mbar_init(bar0 + 8 * s, 1);
+    const uint32_t xoff = (lane & 1) * 16;          // odd lanes read the bucket halves in the other order: spreads the banks
+    // thread s initialises the mbarrier of stage s and issues the first copy into it straight away (other threads
+    // first touch that barrier after a __syncthreads that follows); copies are issued by several threads in
+    // parallel: one thread issuing 8 windows back to back held the whole block at the first barrier for > 1 us
+    if (tid < n_stages) {
+        pw_mbar_init(bar0 + 8 * tid, 1);
         pw_mbar_fence_init();
     }
-    __syncthreads();
     uint32_t par = 0;            // bit s: the phase parity the next wait on stage s expects
     for (uint64_t q = blockIdx.x; q < a.n_regions; q += gridDim.x) {
         const uint32_t cnt = min(a.counts[q], a.cap);
@@ -530,130 +543,107 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
             const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
             const uint32_t bytes = (b1 - b0 + 1) * 32;
             if (bytes <= stage_bytes) {
-                const uint32_t s = g % n_stages;
+                const uint32_t s = g & (n_stages - 1);
                 pw_mbar_expect_tx(bar0 + 8 * s, bytes);
                 pw_bulk_g2s(win0 + s * stage_bytes, t.slots + 4ull * b0, bytes, bar0 + 8 * s);
             }
         };
-        if (tid == 0)
-            for (uint32_t g = 0; g < n_stages && g < a.ng; g++) issue(g);
-        if (SORT) for (uint32_t i = tid; i < PS_BINS; i += T) s_cnt[i] = 0;
-        for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
-        for (uint32_t i = tid; i < (T / 32) * PP_OBINS; i += T) (&o_wc[0][0])[i] = 0;
-        if (tid == 0) q_n = 0;
-        __syncthreads();
+        if (tid < n_stages && tid < a.ng) issue(tid);
         const uint2 *src = a.buf + q * (uint64_t)a.cap;
-        uint64_t canon[IPT];
-        uint32_t h[IPT], pos[IPT], rnk[IPT];
+        uint2 it[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) it[j] = tid + j * T < cnt ? src[tid + j * T] : make_uint2(0, 0);
+        if (tid == 0) { q_n[0] = 0; q_n[1] = 0; }
+        for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
+        for (uint32_t i = tid; i < (T / 32) * PP_OBINS / 2; i += T) ((uint32_t *)&o_wc[0][0])[i] = 0;
+        key_t key[IPT];          // S64: the canonical k-mer; S32: the slot value it has in its home bucket
+        uint32_t h[IPT], pos[IPT], bits[IPT];
 #pragma unroll
         for (int j = 0; j < IPT; j++) {
-            const uint32_t i = tid + j * T;
-            canon[j] = 0; h[j] = 0; pos[j] = 0; rnk[j] = 0;
-            if (i < cnt) {
-                const uint2 it = src[i];
-                canon[j] = pk_canon_at(a.words, a.p0 + it.y, a.ks.k);
-                h[j] = it.x; pos[j] = it.y;
-                if (SORT) rnk[j] = atomicAdd(&s_cnt[(it.x >> sshift) & (PS_BINS - 1)], 1u);
-            }
+            key[j] = 0; h[j] = it[j].x; pos[j] = it[j].y; bits[j] = 0;
+            if (tid + j * T < cnt) key[j] = (key_t)pk_target<FMT>(pk_canon_at(a.words, a.p0 + it[j].y, a.ks.k), 0);
         }
-        if (SORT) {
-            __syncthreads();
-            {   // exclusive scan of s_cnt[PS_BINS], PS_BINS / T bins per thread
-                constexpr int BPT = PS_BINS / T;
-                uint32_t c[BPT], sum = 0;
-#pragma unroll
-                for (int b = 0; b < BPT; b++) { c[b] = s_cnt[tid * BPT + b]; sum += c[b]; }
-                uint32_t inc = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= (uint32_t)o) inc += y;
+        __syncthreads();
+        // ---- probe, group by group, out of the staged windows
+        uint32_t grp_i = 0;
+        for (uint32_t g0 = 0; g0 < a.ng; g0 += gsz, grp_i++) {
+            const uint32_t g1 = min(g0 + gsz, a.ng);
+            uint32_t *qn = &q_n[grp_i & 1];
+            // a full home bucket without the key: the key may sit in a later bucket, decide after the group
+            auto defer = [&](int j, uint32_t i, uint32_t g, const PkTable &t) {
+                const uint32_t slot = atomicAdd(qn, 1u);
+                if (slot < (uint32_t)PW_QCAP) {
+                    q_key[slot] = key[j]; q_pos[slot] = pos[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
+                } else if (pk_lookup<FMT>(t, pk_canon_at(a.words, a.p0 + pos[j], a.ks.k), h[j], 32 * a.grp + g, a.ks)) {
+                    bits[j] |= 1u << g;     // queue full (pathological)
                 }
-                if (lane == 31) s_ws[wid] = inc;
-                __syncthreads();
-                uint32_t off = inc - sum;
+            };
+            for (uint32_t g = g0; g < g1; g++) {
+                const PkTable t = a.tabs[g];
+                const uint32_t s = g & (n_stages - 1);
+                const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
+                const uint32_t gbit = 1u << g;
+                if ((b1 - b0 + 1) * 32 <= stage_bytes) {
+                    pw_mbar_wait(bar0 + 8 * s, (par >> s) & 1);
+                    par ^= 1u << s;
+                    // + 32 * bucket = the bucket's first (even lanes) / second (odd lanes) half; kept opaque so that it
+                    // stays in a register instead of being re-derived per item
+                    uint32_t wbase = win0 + s * stage_bytes - b0 * 32 + xoff, nb = t.n_buckets;
+                    asm volatile("" : "+r"(wbase), "+r"(nb));
 #pragma unroll
-                for (int ww = 0; ww < T / 32; ww++) off += ww < (int)wid ? s_ws[ww] : 0;
-#pragma unroll
-                for (int b = 0; b < BPT; b++) { s_cnt[tid * BPT + b] = off; off += c[b]; }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < IPT; j++) {
-                if (tid + j * T < cnt) {
-                    const uint32_t d = s_cnt[(h[j] >> sshift) & (PS_BINS - 1)] + rnk[j];
-                    s_canon[d] = canon[j]; s_h[d] = h[j]; s_pos[d] = pos[j];
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < IPT; j++) {
-                const uint32_t i = tid + j * T;
-                if (i < cnt) { canon[j] = s_canon[i]; h[j] = s_h[i]; pos[j] = s_pos[i]; }
-            }
-        }
-        uint32_t bits[IPT];
-#pragma unroll
-        for (int j = 0; j < IPT; j++) bits[j] = 0;
-        // ---- probe, genome by genome, out of the staged windows
-        for (uint32_t g = 0; g < a.ng; g++) {
-            const PkTable t = a.tabs[g];
-            const uint32_t s = g % n_stages;
-            const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
-            const uint32_t nbk = b1 - b0 + 1;
-            const bool wok = nbk * 32 <= stage_bytes;
-            const uint32_t maxd = pk_max_disp<FMT>(t.n_buckets);
-            if (wok) {
-                pw_mbar_wait(bar0 + 8 * s, (par >> s) & 1);
-                par ^= 1u << s;
-            }
-            const uint32_t win = win0 + s * stage_bytes;
-#pragma unroll
-            for (int j = 0; j < IPT; j++) {
-                const uint32_t i = tid + j * T;
-                if (i < cnt) {
-                    int res = 0;            // 0 absent, 1 present, 2 undecided: resolve through global memory
-                    if (wok) {
-                        const uint32_t off = __umulhi(h[j], t.n_buckets) - b0;
-                        const uint32_t x = lane & 1;          // odd lanes read the halves in the other order: spreads the banks
-                        for (uint32_t r = 0;; r++) {
-                            const uint32_t wa = win + (off + r) * 32 + x * 16;
+                    for (int j = 0; j < IPT; j++) {
+                        const uint32_t i = tid + j * T;
+                        if (i < cnt) {
+                            const uint32_t wa = wbase + __umulhi(h[j], nb) * 32;
                             const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
-                            if (pw_hit<FMT>(A, B, pk_target<FMT>(canon[j], r))) { res = 1; break; }
-                            if (!pw_full<FMT>(x ? A : B)) break;
-                            if (r == maxd || off + r + 1 >= nbk) { res = 2; break; }
+                            const bool hit = pw_hit<FMT>(A, B, key[j]);
+                            if (hit) bits[j] |= gbit;
+                            else if (pw_full<FMT>(xoff ? A : B)) defer(j, i, g, t);
                         }
-                    } else {
-                        const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
-                        if (pk_bucket_hit<FMT>(v, pk_target<FMT>(canon[j], 0))) res = 1;
-                        else if (pk_bucket_full<FMT>(v)) res = 2;
                     }
-                    if (res == 1) {
-                        bits[j] |= 1u << g;
-                    } else if (res == 2) {
-                        const uint32_t slot = atomicAdd(&q_n, 1u);
-                        if (slot < (uint32_t)PW_QCAP) {
-                            q_key[slot] = canon[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
-                        } else if (pk_lookup<FMT>(t, canon[j], h[j], 32 * a.grp + g, a.ks)) {
-                            bits[j] |= 1u << g;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < IPT; j++) {
+                        const uint32_t i = tid + j * T;
+                        if (i < cnt) {
+                            const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
+                            if (pk_bucket_hit<FMT>(v, key[j])) bits[j] |= gbit;
+                            else if (pk_bucket_full<FMT>(v)) defer(j, i, g, t);
                         }
                     }
                 }
             }
-            if (g + n_stages < a.ng) {
-                __syncthreads();            // every lane is done with stage s: refill it
-                if (tid == 0) issue(g + n_stages);
+            __syncthreads();
+            {   // drain the queue: walk on through the staged window, bucket by bucket
+                const uint32_t nq = min(*qn, (uint32_t)PW_QCAP);
+                for (uint32_t e = tid; e < nq; e += T) {
+                    const uint32_t meta = q_meta[e], g = meta & 31, hh = q_h[e];
+                    const key_t kk = q_key[e];
+                    const PkTable t = a.tabs[g];
+                    const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
+                    const uint32_t nbk = b1 - b0 + 1, off = __umulhi(hh, t.n_buckets) - b0;
+                    const uint32_t maxd = pk_max_disp<FMT>(t.n_buckets);
+                    int res = 2;            // 0 absent, 1 present, 2 undecided: leave the window -> global lookup
+                    if (nbk * 32 <= stage_bytes) {
+                        const uint32_t wb = win0 + (g & (n_stages - 1)) * stage_bytes + xoff;
+                        for (uint32_t r = 1; r <= maxd && off + r < nbk; r++) {
+                            const uint32_t wa = wb + (off + r) * 32;
+                            const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
+                            // S32: the slot value at displacement r is the home value + r; S64: the k-mer itself
+                            if (pw_hit<FMT>(A, B, FMT == PK_FMT_S32 ? (uint64_t)kk + r : (uint64_t)kk)) { res = 1; break; }
+                            if (!pw_full<FMT>(xoff ? A : B)) { res = 0; break; }
+                        }
+                    }
+                    if (res == 2)       // rare: past the window's end, > 14 full buckets in a row (stash), or no window
+                        res = pk_lookup<FMT>(t, pk_canon_at(a.words, a.p0 + q_pos[e], a.ks.k), hh, 32 * a.grp + g, a.ks) ? 1 : 0;
+                    if (res) atomicOr(&s_bits[meta >> 5], 1u << g);
+                }
             }
+            __syncthreads();            // the group's windows and the queue are free again
+            if (tid == 0) *qn = 0;
+            if (tid < gsz && g0 + n_stages + tid < a.ng) issue(g0 + n_stages + tid);     // refill the group's stages in parallel
         }
-        __syncthreads();
-        {
-            const uint32_t nq = min(q_n, (uint32_t)PW_QCAP);
-            for (uint32_t e = tid; e < nq; e += T) {
-                const uint32_t meta = q_meta[e], g = meta & 31;
-                if (pk_lookup<FMT>(a.tabs[g], q_key[e], q_h[e], 32 * a.grp + g, a.ks)) atomicOr(&s_bits[meta >> 5], 1u << g);
-            }
-        }
-        __syncthreads();
+        // (the last group's second barrier also orders s_bits)
 #pragma unroll
         for (int j = 0; j < IPT; j++)
             if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
@@ -735,25 +725,27 @@ static const K3Variant &k3_pick(uint32_t n_genomes_in_launch) {
 }
 
 // window (TMA-staged) variants of K3; same block capacity as variants 0/1, so the partition plan is shared
-struct K3WinVariant { int threads, cap, static_smem; void (*fn[2])(ProbeArgs, uint32_t, uint32_t); };
-#define K3W(T, IPT, SORT, MINB) {T, T * IPT, 0, {probe_win_kernel<T, IPT, PK_FMT_S64, SORT, MINB>, probe_win_kernel<T, IPT, PK_FMT_S32, SORT, MINB>}}
+struct K3WinVariant { int threads, cap; void (*fn[2])(ProbeArgs, uint32_t, uint32_t); };
+#define K3W(T, IPT, MINB) {T, T * IPT, {probe_win_kernel<T, IPT, PK_FMT_S64, MINB>, probe_win_kernel<T, IPT, PK_FMT_S32, MINB>}}
 static const K3WinVariant k3w_variants[] = {
-    K3W(256, 3, 0, 6),      // 0: unsorted
-    K3W(256, 3, 1, 4),      // 1: bucket-sorted (lanes of a warp read neighbouring buckets: fewer bank conflicts)
-    K3W(256, 3, 0, 8),      // 2: 8 blocks/SM (32 registers)
-    K3W(256, 3, 0, 4),      // 3
+    K3W(256, 3, 4),      // 0: <= 64 registers
+    K3W(256, 3, 5),      // 1: <= 48 registers
+    K3W(256, 3, 3),      // 2: <= 80 registers
+    K3W(256, 3, 6),      // 3: <= 40 registers
 };
 static int g_k3_window = 1;          // 0: never use the window kernels
+static int g_k3_last_window = 0;     // did the last K3 launch use a window kernel?
+int pk_part_last_window(void) { return g_k3_last_window; }
 static int g_k3w_variant = -1;       // -1 auto
-static int g_k3w_stages = 3;
+static int g_k3w_group = 4;          // genomes per window group (2 * group stage buffers)
 void pk_part_set_window(int enable, int variant, int stages) {
     g_k3_window = enable;
     if (variant >= -1 && variant < (int)(sizeof k3w_variants / sizeof k3w_variants[0])) g_k3w_variant = variant;
-    if (stages >= 1 && stages <= PW_MAX_STAGES) g_k3w_stages = stages;
+    if (stages == 1 || stages == 2 || stages == 4) g_k3w_group = stages;      // 2 * group stages: a power of two
 }
 static const K3WinVariant &k3w_pick(uint32_t n_genomes_in_launch) {
-    if (g_k3w_variant >= 0) return k3w_variants[g_k3w_variant];
-    return k3w_variants[n_genomes_in_launch >= 16 ? 1 : 0];
+    (void)n_genomes_in_launch;
+    return k3w_variants[g_k3w_variant >= 0 ? g_k3w_variant : 0];
 }
 // bytes one stage must hold for every table of the launch, or 0 when some window does not fit a stage
 static uint32_t k3w_stage_bytes(const PkTable *tabs, uint32_t ng, uint32_t pb) {
@@ -875,12 +867,13 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
         p.grp = grp; p.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         for (uint32_t g = 0; g < p.ng; g++) p.tabs[g] = h_tables[32 * grp + g];
         const uint32_t stage_bytes = g_k3_window && k3_pick(p.ng).cap == k3w_pick(p.ng).cap ? k3w_stage_bytes(p.tabs, p.ng, p.pb) : 0;
+        g_k3_last_window = stage_bytes != 0;
         if (stage_bytes) {
             const K3WinVariant &wv = k3w_pick(p.ng);
-            const uint32_t stages = g_k3w_stages;
-            const size_t dyn = (size_t)stages * stage_bytes;
+            const uint32_t gsz = g_k3w_group;
+            const size_t dyn = (size_t)2 * gsz * stage_bytes;
             cudaFuncSetAttribute(wv.fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
-            wv.fn[fi]<<<p.n_regions, wv.threads, dyn, s>>>(p, stage_bytes, stages);
+            wv.fn[fi]<<<p.n_regions, wv.threads, dyn, s>>>(p, stage_bytes, gsz);
         } else {
             const K3Variant &kv = k3_pick(p.ng);
             kv.fn[fi]<<<p.n_regions, kv.threads, 0, s>>>(p);

@@ -181,6 +181,54 @@ class Engine:
                   for nk, x, y, z, b in zip(nks, b1, lo, hi, bl)]
         return {"chroms": chroms, "col_sums": cs}
 
+    def anchor_genome_bgzf(self, seqs, hist=True, colsums=True, out: dict | None = None) -> dict:
+        """All chromosomes of one anchor in one batch, the two bitmaps delivered as FILE IMAGES
+        (pk_anchor_genome_bgzf): 'gz'/'gzi' hold the bytes of bitmap.1.gz / bitmap.1.gzi and
+        'gz_low'/'gzi_low' those of bitmap.<step>.gz/.gzi, compressed on the GPU. `out` = a previous
+        result for the same chromosome lengths (its pinned buffers are reused)."""
+        arrs = [_u8(s) for s in seqs]
+        n = len(arrs)
+        rb, step = self.row_bytes, self.lowres_step
+        nks = [max(a.size - self.k + 1, 0) for a in arrs]
+        bl = [self.bin_len(nk) if nk else 0 for nk in nks]
+        nbytes = [sum(nks) * rb, sum((nk + step - 1) // step for nk in nks) * rb]
+        if out is not None:
+            assert [c["nkmers"] for c in out["chroms"]] == nks, "out= must come from the same chromosome lengths"
+            bufs, hi, cs = out["_bufs"], [c["bin_hist"] for c in out["chroms"]], out["col_sums"]
+            if cs is not None:
+                cs[:] = 0
+        else:
+            bufs = {"gz": [pinned_empty(int(self._L.pk_bgzf_bound(b))) for b in nbytes],
+                    "gzi": [pinned_empty(int(self._L.pk_bgzf_gzi_bound(b))) for b in nbytes]}
+            hi = [np.zeros(((nk + b - 1) // b, self.n_local + 1), dtype=np.uint64) if (hist and nk and b) else None
+                  for nk, b in zip(nks, bl)]
+            cs = np.zeros(self.n_local, dtype=np.uint64) if colsums else None
+
+        def ptrs(lst, m):
+            return (C.c_void_p * m)(*[None if x is None else x.ctypes.data for x in lst])
+
+        lens = (C.c_uint64 * n)(*[a.size for a in arrs])
+        nko = (C.c_uint64 * n)()
+        caps_gz = (C.c_uint64 * 2)(*[b.size for b in bufs["gz"]])
+        caps_gzi = (C.c_uint64 * 2)(*[b.size for b in bufs["gzi"]])
+        sizes = (C.c_uint64 * 4)()
+        check(self._L.pk_anchor_genome_bgzf(self._h, n, ptrs(arrs, n), lens, ptrs(bufs["gz"], 2), caps_gz,
+                                            ptrs(bufs["gzi"], 2), caps_gzi, sizes, ptrs(hi, n),
+                                            None if cs is None else cs.ctypes.data, nko))
+        assert list(nko) == nks
+        chroms = [{"nkmers": nk, "bin_hist": z, "binlen": b} for nk, z, b in zip(nks, hi, bl)]
+        return {"chroms": chroms, "col_sums": cs, "gz": bufs["gz"][0][:sizes[0]], "gzi": bufs["gzi"][0][:sizes[1]],
+                "gz_low": bufs["gz"][1][:sizes[2]], "gzi_low": bufs["gzi"][1][:sizes[3]], "_bufs": bufs}
+
+    def bgzf_bound(self, nbytes: int) -> tuple[int, int]:
+        return int(self._L.pk_bgzf_bound(nbytes)), int(self._L.pk_bgzf_gzi_bound(nbytes))
+
+    def bgzf_compress_device(self, d_in: int, nbytes: int, match_dist: int, d_gz: int, d_gzi: int, d_totals: int,
+                             stream: int = 0):
+        """Device bytes -> BGZF .gz image + .gzi image + totals (2 x uint64), all on the device."""
+        check(self._L.pk_bgzf_compress_device(self._h, d_in or None, nbytes, match_dist, d_gz, d_gzi, d_totals,
+                                              stream or None))
+
     def get_counters_for_read(self, dbi: int, read) -> np.ndarray | None:
         """uint32 counters of bitvec database `dbi` for every k-mer of `read`
         (CKMCFile::GetCountersForRead); None when len(read) < k."""

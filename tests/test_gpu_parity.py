@@ -196,6 +196,60 @@ def test_pinned_buffers_and_anchor_dir(pan3, tmp_path):
     assert s["positions"] == len(exp["bitmap.1"])
 
 
+@pytest.mark.parametrize("bgzf", ["gpu", "zlib"])
+def test_anchor_dir_both_bgzf_writers(pan3, tmp_path, bgzf):
+    """The GPU BGZF writer and the host zlib writer give files that decompress to the reference's bytes and
+    are seekable through their .gzi the way Genome._query_bytes seeks (index.py:827-845)."""
+    from test_bgzf_format import check_bgzf_image
+    eng = Engine(pan3["k"], 3)
+    eng.add_bitvec(0, pan3["dir"] / "kmc" / "bitvec0")
+    eng.finalize()
+    for a in pan3["anchors"]:
+        d = tmp_path / a
+        anchor.anchor_fasta(eng, a, pan3["fasta"][a], d, genome_names=pan3["names"], bgzf=bgzf)
+        exp = pan3["expected"][a]
+        for step in (1, 100):
+            raw, gzi = (d / f"bitmap.{step}.gz").read_bytes(), (d / f"bitmap.{step}.gzi").read_bytes()
+            if bgzf == "gpu":
+                check_bgzf_image(raw, gzi, exp[f"bitmap.{step}"])
+            assert layout.read_bgzf(d / f"bitmap.{step}.gz") == exp[f"bitmap.{step}"]
+        n = len(exp["bitmap.1"])
+        for off in (0, 1, n // 2, n - 60):
+            assert layout.query_bytes(d / "bitmap.1.gz", d / "bitmap.1.gzi", off, 60) == exp["bitmap.1"][off:off + 60]
+        assert (d / "chrs.tsv").read_text() == exp["chrs.tsv"]
+        assert (d / "bitsum.bins.tsv").read_text() == exp["bitsum.bins.tsv"]
+
+
+def test_bgzf_compress_device_formats():
+    """pk_bgzf_compress_device on device buffers: compressible rows of several widths, incompressible bytes
+    (stored members), empty and ragged sizes; images validated member by member against zlib."""
+    import torch
+    from test_bgzf_format import cases, check_bgzf_image
+    eng = Engine(21, 1)
+    eng.add_keys(0, np.array([1], dtype=np.uint64))
+    eng.finalize()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    big = np.repeat(np.random.default_rng(9).integers(0, 256, (400000, 2), dtype=np.uint8),
+                    np.random.default_rng(10).integers(1, 30, 400000), axis=0).tobytes()
+    for label, data, dist in cases() + [("12 MB of 2-byte rows", big, 2)]:
+        n = len(data)
+        cap_gz, cap_gzi = eng.bgzf_bound(n)
+        d_in = torch.frombuffer(bytearray(data) or bytearray(1), dtype=torch.uint8).to(dev)
+        d_gz = torch.zeros(cap_gz, dtype=torch.uint8, device=dev)
+        d_gzi = torch.zeros(cap_gzi // 8, dtype=torch.int64, device=dev)
+        d_tot = torch.zeros(2, dtype=torch.int64, device=dev)
+        eng.bgzf_compress_device(d_in.data_ptr(), n, dist, d_gz.data_ptr(), d_gzi.data_ptr(), d_tot.data_ptr(), st)
+        torch.cuda.synchronize()
+        tot = d_tot.cpu().numpy()
+        assert tot[0] <= cap_gz and tot[1] <= cap_gzi, label
+        raw = d_gz[: int(tot[0])].cpu().numpy().tobytes()
+        gzi = d_gzi.cpu().numpy().tobytes()[: int(tot[1])]
+        check_bgzf_image(raw, gzi, data)
+        if label.startswith("runs") or label.startswith("12 MB"):
+            assert len(raw) < n / 5, label
+
+
 def test_device_level_sharded_gather_equals_single_engine():
     """Two genome shards on one GPU stand in for two ranks: per-shard rows, gathered as planes,
     interleaved, reduced == one engine holding all 16 genomes."""
@@ -331,9 +385,9 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
     seqs = [s for _, s in genomes[2]]
     want = engd.anchor_genome(seqs)
     try:
-        for knobs in (dict(k3_window=1, k3w_variant=-1, k3w_stages=3), dict(k3w_variant=0, k3w_stages=1),
-                      dict(k3w_variant=1, k3w_stages=2), dict(k3w_variant=2, k3w_stages=4), dict(k3w_variant=3),
-                      dict(k3_window=0), dict(k3_window=1, k3w_variant=-1, k3w_stages=3, unpermute=0)):
+        for knobs in (dict(k3_window=1, k3w_variant=-1, k3w_group=4), dict(k3w_variant=0, k3w_group=1),
+                      dict(k3w_variant=1, k3w_group=2), dict(k3w_variant=2, k3w_group=4), dict(k3w_variant=3),
+                      dict(k3_window=0), dict(k3_window=1, k3w_variant=-1, k3w_group=4, unpermute=0)):
             eng.tune(**knobs)
             got = eng.anchor_genome(seqs)
             assert (got["col_sums"] == want["col_sums"]).all(), knobs
@@ -341,13 +395,13 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
                 assert (a["bitmap1"] == b["bitmap1"]).all(), knobs
                 assert (a["bin_hist"] == b["bin_hist"]).all(), knobs
         # a short anchor against the same (large) tables: few partitions -> windows of > 16 KB -> L1/L2 kernel
-        eng.tune(k3_window=1, k3w_variant=-1, k3w_stages=3, unpermute=1)
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=4, unpermute=1)
         short = seqs[0][:30_000]
         a = eng.anchor_chrom(short, hist=False)["bitmap1"]
         b = engd.anchor_chrom(short, hist=False)["bitmap1"]
         assert (a == b).all()
     finally:
-        eng.tune(k3_window=1, k3w_variant=-1, k3w_stages=3, unpermute=1)
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=4, unpermute=1)
     with pytest.raises(_lib.PkError):
         eng.tune(no_such_knob=1)
 
@@ -502,10 +556,24 @@ def test_full_size_configs1_properties():
         assert r["bin_hist"].sum() == nk
         b3 = np.bincount(pc[3 * binlen:4 * binlen], minlength=n + 1)
         assert (r["bin_hist"][3] == b3).all()
+        nbins = (nk + binlen - 1) // binlen                              # every bin, incl. the ragged last one
+        full = np.bincount((np.arange(nk, dtype=np.int64) // binlen) * (n + 1) + pc, minlength=nbins * (n + 1))
+        assert (r["bin_hist"].ravel() == full.astype(np.uint64)).all()
         col += np.unpackbits(rows[:, None], axis=1, bitorder="little").sum(axis=0).astype(np.uint64)
         total += nk
     assert (res["col_sums"] == col).all() and res["col_sums"][0] == col.max()
     assert total == 134_999_900
+    # the same genome through the GPU BGZF writer: the file images decompress to exactly these rows
+    import gzip
+    rz = eng.anchor_genome_bgzf(anchor_seqs)
+    assert (rz["col_sums"] == res["col_sums"]).all()
+    assert gzip.decompress(rz["gz"].tobytes()) == b"".join(r["bitmap1"].tobytes() for r in res["chroms"])
+    assert gzip.decompress(rz["gz_low"].tobytes()) == b"".join(r["low"].tobytes() for r in res["chroms"])
+    nblk = (total + 0xff00 - 1) // 0xff00
+    assert rz["gzi"].size == 8 + 16 * (nblk - 1) and int(rz["gzi"][:8].view(np.uint64)[0]) == nblk - 1
+    for a, b in zip(rz["chroms"], res["chroms"]):
+        assert (a["bin_hist"] == b["bin_hist"]).all()
+    print("configs[1] bitmap.1: %d bytes -> %d bytes of BGZF (GPU)" % (total, rz["gz"].size))
     # partitioned (default for this size) == direct kernel on a 3 M-position slice
     engd = Engine(k, n, probe_mode="direct")
     for g in range(n):
