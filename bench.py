@@ -45,6 +45,8 @@ WORKLOADS = {
                      name="configs[1]: 8 synthetic 135 Mbp genomes, k=21, 1 anchor"),
     "configs2": dict(n_per_gpu=32, length=150_000_000, k=21, seed=20260002,
                      name="configs[2]: 32 synthetic 150 Mbp genomes, k=21, 1 anchor"),
+    "configs3s": dict(n_per_gpu=8, length=150_000_000, k=31, seed=20260003,
+                      name="configs[3], one GPU's shard: 8 of 64 synthetic 150 Mbp genomes, k=31 (64-bit slots), 1 of 4 anchors"),
     "small": dict(n_per_gpu=8, length=8_000_000, k=21, seed=20260009,
                   name="small: 8 synthetic 8 Mbp genomes, k=21, 1 anchor"),
 }

@@ -235,7 +235,7 @@ int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *se
 /* Tuning knobs of the partitioned probe (process-wide; no reference counterpart). Results never depend on
  * them; tests run the parity suite under several settings. name = "k3_window" (1: probe out of table
  * windows staged in shared memory by TMA bulk copies when they fit, 0: always probe through L1/L2),
- * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_group" (1, 2 or 4 genomes per window group; two groups of windows are staged per block),
+ * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_group" (0 = by window size, or 1, 2, 4 genomes per window group; two groups of windows are staged per block),
  * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "unpermute" (0/1: applies to
  * scratch allocated afterwards). Unknown names return PK_EINVAL. */
 int pk_engine_tune(pk_engine *e, const char *name, int value);

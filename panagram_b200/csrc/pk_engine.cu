@@ -30,7 +30,7 @@ void pk_set_error(const char *fmt, ...) {
     } while (0)
 
 // process-wide tuning state of the partitioned probe (pk_engine_tune / PK_K3* environment variables)
-static int g_tune_window = 1, g_tune_wvariant = -1, g_tune_wstages = 4;
+static int g_tune_window = 1, g_tune_wvariant = -1, g_tune_wstages = 0;
 
 // ------------------------------------------------------------------ engine
 struct HostTable {
@@ -150,7 +150,7 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
         const char *we = getenv("PK_K3_WINDOW"), *wv = getenv("PK_K3W_VARIANT"), *ws = getenv("PK_K3W_GROUP");
         if (we) g_tune_window = atoi(we);
         if (wv) g_tune_wvariant = atoi(wv);
-        if (ws && (atoi(ws) == 1 || atoi(ws) == 2 || atoi(ws) == 4)) g_tune_wstages = atoi(ws);
+        if (ws && (atoi(ws) == 0 || atoi(ws) == 1 || atoi(ws) == 2 || atoi(ws) == 4)) g_tune_wstages = atoi(ws);
         pk_part_set_window(g_tune_window, g_tune_wvariant, g_tune_wstages);
     }
     e->n_local = cfg->genome_end - cfg->genome_begin;
@@ -895,7 +895,7 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     const std::string n(name);
     if (n == "k3_window") g_tune_window = value;
     else if (n == "k3w_variant") g_tune_wvariant = value;
-    else if (n == "k3w_group") { if (value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 1, 2 or 4", value); return PK_EINVAL; } g_tune_wstages = value; }
+    else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } g_tune_wstages = value; }
     else if (n == "k3_variant") { pk_part_set_variant(value); return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
     else if (n == "unpermute") {

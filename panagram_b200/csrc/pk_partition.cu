@@ -737,15 +737,15 @@ static int g_k3_window = 1;          // 0: never use the window kernels
 static int g_k3_last_window = 0;     // did the last K3 launch use a window kernel?
 int pk_part_last_window(void) { return g_k3_last_window; }
 static int g_k3w_variant = -1;       // -1 auto
-static int g_k3w_group = 4;          // genomes per window group (2 * group stage buffers)
+static int g_k3w_group = 0;          // genomes per window group (2 * group stage buffers); 0 = by window size
 void pk_part_set_window(int enable, int variant, int stages) {
     g_k3_window = enable;
     if (variant >= -1 && variant < (int)(sizeof k3w_variants / sizeof k3w_variants[0])) g_k3w_variant = variant;
-    if (stages == 1 || stages == 2 || stages == 4) g_k3w_group = stages;      // 2 * group stages: a power of two
+    if (stages == 0 || stages == 1 || stages == 2 || stages == 4) g_k3w_group = stages;      // 2 * group stages: a power of two
 }
 static const K3WinVariant &k3w_pick(uint32_t n_genomes_in_launch) {
     (void)n_genomes_in_launch;
-    return k3w_variants[g_k3w_variant >= 0 ? g_k3w_variant : 0];
+    return k3w_variants[g_k3w_variant >= 0 ? g_k3w_variant : 3];      // 6 blocks/SM: profiles/r1e_sweep.json
 }
 // bytes one stage must hold for every table of the launch, or 0 when some window does not fit a stage
 static uint32_t k3w_stage_bytes(const PkTable *tabs, uint32_t ng, uint32_t pb) {
@@ -870,7 +870,9 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
         g_k3_last_window = stage_bytes != 0;
         if (stage_bytes) {
             const K3WinVariant &wv = k3w_pick(p.ng);
-            const uint32_t gsz = g_k3w_group;
+            // two genomes per group while four windows stay under ~24 KB (6 blocks/SM), else one: measured on
+            // configs[1] (4.1 KB windows: 5.14 vs 5.81 ms) and on k=31 tables (9.2 KB windows: 9.42 vs 7.86 ms)
+            const uint32_t gsz = g_k3w_group ? g_k3w_group : (4 * stage_bytes <= 24576 ? 2 : 1);
             const size_t dyn = (size_t)2 * gsz * stage_bytes;
             cudaFuncSetAttribute(wv.fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
             wv.fn[fi]<<<p.n_regions, wv.threads, dyn, s>>>(p, stage_bytes, gsz);

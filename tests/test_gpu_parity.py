@@ -395,13 +395,13 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
                 assert (a["bitmap1"] == b["bitmap1"]).all(), knobs
                 assert (a["bin_hist"] == b["bin_hist"]).all(), knobs
         # a short anchor against the same (large) tables: few partitions -> windows of > 16 KB -> L1/L2 kernel
-        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=4, unpermute=1)
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1)
         short = seqs[0][:30_000]
         a = eng.anchor_chrom(short, hist=False)["bitmap1"]
         b = engd.anchor_chrom(short, hist=False)["bitmap1"]
         assert (a == b).all()
     finally:
-        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=4, unpermute=1)
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1)
     with pytest.raises(_lib.PkError):
         eng.tune(no_such_knob=1)
 
@@ -557,7 +557,7 @@ def test_full_size_configs1_properties():
         b3 = np.bincount(pc[3 * binlen:4 * binlen], minlength=n + 1)
         assert (r["bin_hist"][3] == b3).all()
         nbins = (nk + binlen - 1) // binlen                              # every bin, incl. the ragged last one
-        full = np.bincount((np.arange(nk, dtype=np.int64) // binlen) * (n + 1) + pc, minlength=nbins * (n + 1))
+        full = np.bincount((np.arange(nk, dtype=np.int64) // binlen) * (n + 1) + pc.astype(np.int64), minlength=nbins * (n + 1))
         assert (r["bin_hist"].ravel() == full.astype(np.uint64)).all()
         col += np.unpackbits(rows[:, None], axis=1, bitorder="little").sum(axis=0).astype(np.uint64)
         total += nk
