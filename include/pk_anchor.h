@@ -237,7 +237,9 @@ int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *se
  * windows staged in shared memory by TMA bulk copies when they fit, 0: always probe through L1/L2),
  * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_group" (0 = by window size, or 1, 2, 4 genomes per window group; two groups of windows are staged per block),
  * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "unpermute" (0/1: applies to
- * scratch allocated afterwards). Unknown names return PK_EINVAL. */
+ * scratch allocated afterwards), "e2e_batches" (1..8: batches of whole chromosomes per pk_anchor_genome call;
+ * copies of one batch overlap the kernels of the other), "e2e_batch_min" (positions from which a genome is
+ * split into batches; default 32 Mi). Unknown names return PK_EINVAL. */
 int pk_engine_tune(pk_engine *e, const char *name, int value);
 
 /* timing / accounting of the last pk_anchor_chrom or pk_get_counters_for_read */

@@ -64,6 +64,8 @@ struct pk_engine {
     uint64_t hist_cap = 0;
     cudaEvent_t pev[6] = {};                    // around K1 / K2 / K3 / spill / K4 of the last partitioned launch
     int unpermute = 1;
+    int e2e_batches = 2;                        // batches of whole chromosomes per pk_anchor_genome call (copy/compute overlap)
+    uint64_t e2e_batch_min = 32ull << 20;       // ... for genomes of at least this many positions
     bool pev_valid = false;
     PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
     PkPartPlan sc_plan{};
@@ -707,58 +709,93 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     }
     CU(cudaMemsetAsync(e->d_hist, 0, (histtot + 1) * 8, s));
     CU(cudaMemsetAsync(e->d_colsums, 0, N * 8, s));
-    PkPartPlan pl{};
-    if (pipelined) {
-        pk_part_plan(npos, &pl);
-        rc = ensure_scratch(e, pl); if (rc) { cleanup(); return rc; }
-        pk_part_begin(N, pl, e->sc, s);
-    }
-    // ---- pack (+ K1 of the partitioned probe) per chromosome as soon as its bytes are on the device
-    for (uint32_t c = 0; c < n_chroms; c++) {
-        CU(cudaStreamWaitEvent(s, in_done[c], 0));
-        const uint64_t w0 = off[c] / 32, w1 = c + 1 < n_chroms ? off[c + 1] / 32 : nw;
-        pk_launch_pack(e->g_ascii + off[c], ltot + 64 - off[c], w1 - w0, e->g_words + w0, e->g_mask + w0, s);
-        e->stats.kernel_launches += 1;
-        if (pipelined && nk[c]) {
-            pk_part_append(e->g_words, e->g_mask, 0, off[c], nk[c], e->ks, N, e->g_rows, rb, 0, pl, e->sc, s);
-            e->stats.kernel_launches += 1;
+    // ---- batches. The partitioned probe streams every table through L2 once per batch, so few batches are
+    // best for the kernels; but with ONE batch nothing overlaps the first H2D and the last D2H (2.7 + 1.3 ms of
+    // an 11.1 ms call on configs[1], profiles/r1f_bench.json). Two batches of whole chromosomes let the copy
+    // engines run under the other batch's kernels while the tables are still read only twice.
+    struct Batch { uint32_t c0, c1; uint64_t base, npos; PkPartPlan pl; };
+    std::vector<Batch> batches;
+    {
+        uint32_t nb = 1;
+        if (pipelined && e->e2e_batches > 1 && npos >= e->e2e_batch_min) nb = (uint32_t)e->e2e_batches;
+        uint32_t c = 0;
+        for (uint32_t b = 0; b < nb && c < n_chroms; b++) {
+            // cut after the chromosome at which the running length first reaches (b+1)/nb of the total
+            const uint64_t target = ltot * (b + 1) / nb;
+            Batch bt{};
+            bt.c0 = c;
+            while (c < n_chroms && (b + 1 == nb || c == bt.c0 || off[c] + lens[c] / 2 <= target)) c++;
+            bt.c1 = c;
+            bt.base = off[bt.c0];
+            const uint64_t end = (bt.c1 < n_chroms ? off[bt.c1] : ltot);
+            bt.npos = end > bt.base + k - 1 ? end - bt.base - (k - 1) : 0;
+            batches.push_back(bt);
         }
+        if (!batches.empty()) batches.back().c1 = n_chroms;
     }
-    CU(cudaEventRecord(e->ev[1], s));
-    CU(cudaEventRecord(e->ev[2], s));
     if (pipelined) {
-        pk_part_probe(e->g_words, e->g_mask, 0, e->ks, e->h_tables.data(), N, e->g_rows, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
-        e->stats.kernel_launches += (pl.pb2 ? 1 : 0) + 2 * ((N + 31) / 32);
-        e->stats.probe_launches += 1;
-    } else {
-        rc = probe_any(e, e->g_words, e->g_mask, 0, npos, e->g_rows, rb, 0, s); if (rc) { cleanup(); return rc; }
+        PkPartPlan mx{};
+        for (auto &bt : batches) {
+            pk_part_plan(bt.npos ? bt.npos : 1, &bt.pl);
+            mx.buf1_items = std::max(mx.buf1_items, bt.pl.buf1_items); mx.buf2_items = std::max(mx.buf2_items, bt.pl.buf2_items);
+            mx.spill_items = std::max(mx.spill_items, bt.pl.spill_items);
+            mx.n_regions1 = std::max(mx.n_regions1, bt.pl.n_regions1); mx.n_regions2 = std::max(mx.n_regions2, bt.pl.n_regions2);
+            mx.out_shift = std::max(mx.out_shift, bt.pl.out_shift);
+        }
+        rc = ensure_scratch(e, mx); if (rc) { cleanup(); return rc; }
     }
-    CU(cudaEventRecord(e->ev[3], s));
-    // ---- per chromosome: un-permute its position bins, reduce, and send rows home on the copy stream
-    uint32_t next_bin = 0;
-    for (uint32_t c = 0; c < n_chroms; c++) {
-        if (!nk[c]) continue;
-        if (pipelined && e->sc.out_list) {
-            const uint32_t b1 = (uint32_t)((off[c] + nk[c] - 1) >> pl.out_shift) + 1;
-            if (b1 > next_bin) {
-                pk_part_unpermute(next_bin, b1, N, e->g_rows, rb, 0, pl, e->sc, s);
+    bool first = true;
+    for (const Batch &bt : batches) {
+        const PkPartPlan &pl = bt.pl;
+        uint8_t *rows_b = e->g_rows + bt.base * rb;
+        if (pipelined) pk_part_begin(N, pl, e->sc, s);
+        // ---- pack (+ K1 of the partitioned probe) per chromosome as soon as its bytes are on the device
+        for (uint32_t c = bt.c0; c < bt.c1; c++) {
+            CU(cudaStreamWaitEvent(s, in_done[c], 0));
+            const uint64_t w0 = off[c] / 32, w1 = c + 1 < n_chroms ? off[c + 1] / 32 : nw;
+            pk_launch_pack(e->g_ascii + off[c], ltot + 64 - off[c], w1 - w0, e->g_words + w0, e->g_mask + w0, s);
+            e->stats.kernel_launches += 1;
+            if (pipelined && nk[c]) {
+                pk_part_append(e->g_words, e->g_mask, bt.base, off[c] - bt.base, nk[c], e->ks, N, rows_b, rb, 0, pl, e->sc, s);
                 e->stats.kernel_launches += 1;
-                next_bin = b1;
             }
         }
-        const uint8_t *rows_c = e->g_rows + off[c] * rb;
-        uint8_t *low_c = e->g_low + lowoff[c] * rb;
-        const bool want_low = (bitmap_low && bitmap_low[c]) || z;
-        if (nbins[c] || col_sums || want_low) {
-            pk_launch_reduce(rows_c, rb, N, 0, nk[c], nbins[c] ? binlen[c] : 0, nbins[c] ? e->d_hist + histoff[c] : nullptr,
-                             col_sums ? e->d_colsums : nullptr, want_low ? low_c : nullptr, step, s);
-            e->stats.kernel_launches += 1 + (want_low ? 1 : 0);
+        if (first) { CU(cudaEventRecord(e->ev[1], s)); CU(cudaEventRecord(e->ev[2], s)); }
+        if (pipelined) {
+            pk_part_probe(e->g_words, e->g_mask, bt.base, e->ks, e->h_tables.data(), N, rows_b, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
+            e->stats.kernel_launches += (pl.pb2 ? 1 : 0) + 2 * ((N + 31) / 32);
+            e->stats.probe_launches += 1;
+        } else {
+            rc = probe_any(e, e->g_words, e->g_mask, 0, npos, e->g_rows, rb, 0, s); if (rc) { cleanup(); return rc; }
         }
-        CU(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
-        CU(cudaEventRecord(done[c], s));
-        CU(cudaStreamWaitEvent(cs, done[c], 0));
-        if (bitmap1 && bitmap1[c]) CU(cudaMemcpyAsync(bitmap1[c], rows_c, nk[c] * rb, cudaMemcpyDeviceToHost, cs));
-        if (bitmap_low && bitmap_low[c]) CU(cudaMemcpyAsync(bitmap_low[c], low_c, ((nk[c] + step - 1) / step) * rb, cudaMemcpyDeviceToHost, cs));
+        if (first) CU(cudaEventRecord(e->ev[3], s));
+        first = false;
+        // ---- per chromosome: un-permute its position bins, reduce, and send rows home on the copy stream
+        uint32_t next_bin = 0;
+        for (uint32_t c = bt.c0; c < bt.c1; c++) {
+            if (!nk[c]) continue;
+            if (pipelined && e->sc.out_list) {
+                const uint32_t b1 = (uint32_t)((off[c] - bt.base + nk[c] - 1) >> pl.out_shift) + 1;
+                if (b1 > next_bin) {
+                    pk_part_unpermute(next_bin, b1, N, rows_b, rb, 0, pl, e->sc, s);
+                    e->stats.kernel_launches += 1;
+                    next_bin = b1;
+                }
+            }
+            const uint8_t *rows_c = e->g_rows + off[c] * rb;
+            uint8_t *low_c = e->g_low + lowoff[c] * rb;
+            const bool want_low = (bitmap_low && bitmap_low[c]) || z;
+            if (nbins[c] || col_sums || want_low) {
+                pk_launch_reduce(rows_c, rb, N, 0, nk[c], nbins[c] ? binlen[c] : 0, nbins[c] ? e->d_hist + histoff[c] : nullptr,
+                                 col_sums ? e->d_colsums : nullptr, want_low ? low_c : nullptr, step, s);
+                e->stats.kernel_launches += 1 + (want_low ? 1 : 0);
+            }
+            CU(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+            CU(cudaEventRecord(done[c], s));
+            CU(cudaStreamWaitEvent(cs, done[c], 0));
+            if (bitmap1 && bitmap1[c]) CU(cudaMemcpyAsync(bitmap1[c], rows_c, nk[c] * rb, cudaMemcpyDeviceToHost, cs));
+            if (bitmap_low && bitmap_low[c]) CU(cudaMemcpyAsync(bitmap_low[c], low_c, ((nk[c] + step - 1) / step) * rb, cudaMemcpyDeviceToHost, cs));
+        }
     }
     if (z) {
         // one stream per anchor, chromosomes back to back (cpp/anchor.cpp:167: bgzf_write appends chunk after chunk)
@@ -898,6 +935,8 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } g_tune_wstages = value; }
     else if (n == "k3_variant") { pk_part_set_variant(value); return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
+    else if (n == "e2e_batch_min") { e->e2e_batch_min = value < 0 ? 0 : (uint64_t)value; return PK_OK; }
+    else if (n == "e2e_batches") { if (value < 1 || value > 8) { pk_set_error("e2e_batches %d out of 1..8", value); return PK_EINVAL; } e->e2e_batches = value; return PK_OK; }
     else if (n == "unpermute") {
         if (e->unpermute != value) {       // the scratch layout depends on it: drop it, the next launch re-allocates
             int rc = set_device(e); if (rc) return rc;

@@ -394,6 +394,19 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
             for a, b in zip(got["chroms"], want["chroms"]):
                 assert (a["bitmap1"] == b["bitmap1"]).all(), knobs
                 assert (a["bin_hist"] == b["bin_hist"]).all(), knobs
+        # the same genome as 2 and 3 batches of whole chromosomes (copies of one batch under the kernels of the other)
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1, e2e_batch_min=0)
+        for nb in (2, 3, 8):
+            eng.tune(e2e_batches=nb)
+            got = eng.anchor_genome(seqs)
+            gz = eng.anchor_genome_bgzf(seqs)
+            assert (got["col_sums"] == want["col_sums"]).all() and (gz["col_sums"] == want["col_sums"]).all(), nb
+            for a, b, c in zip(got["chroms"], want["chroms"], gz["chroms"]):
+                assert (a["bitmap1"] == b["bitmap1"]).all() and (a["low"] == b["low"]).all(), nb
+                assert (a["bin_hist"] == b["bin_hist"]).all() and (c["bin_hist"] == b["bin_hist"]).all(), nb
+            import gzip
+            assert gzip.decompress(gz["gz"].tobytes()) == b"".join(c["bitmap1"].tobytes() for c in want["chroms"]), nb
+        eng.tune(e2e_batches=2, e2e_batch_min=32 << 20)
         # a short anchor against the same (large) tables: few partitions -> windows of > 16 KB -> L1/L2 kernel
         eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1)
         short = seqs[0][:30_000]
@@ -401,7 +414,7 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
         b = engd.anchor_chrom(short, hist=False)["bitmap1"]
         assert (a == b).all()
     finally:
-        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1)
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1, e2e_batches=2, e2e_batch_min=32 << 20)
     with pytest.raises(_lib.PkError):
         eng.tune(no_such_knob=1)
 
