@@ -144,6 +144,70 @@ def run_reference(args, wl, cores):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+# ------------------------------------------------------------------------ whole `panagram index` (time iii)
+INDEX_WORKLOADS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "configs0": dict(n=2, length=5_000_000, k=21, seed=20260000, anchors=None,
+                     name="configs[0]: 2 synthetic 5 Mbp genomes, k=21, both anchors"),
+    # the bounded sample the CPU arm uses for configs[1]
+    "configs1_sample": dict(n=8, length=6_000_000, k=21, seed=20260001, anchors=["g0"],
+                            name="configs[1] sample: 8 synthetic 6 Mbp genomes, k=21, 1 anchor"),
+    "configs1": dict(n=8, length=135_000_000, k=21, seed=20260001, anchors=["g0"],
+                     name="configs[1]: 8 synthetic 135 Mbp genomes, k=21, 1 anchor"),
+}
+
+
+def run_index_e2e(args, cores):
+    """FASTA files on disk -> finished anchor/<name>/ directories, ours (`python -m panagram_b200 index`: parse,
+    k-mer tables built on the GPU from the sequences, anchor, BGZF on the GPU, files written) and, as the
+    cpu_baseline leg, the reference's pipeline on the same files (cpp/Snakefile restated by oracle/refpipe.py over
+    the unmodified binaries: kmc + set_counts per genome, kmc_tools complex, run_anchor), outputs compared."""
+    from panagram_b200 import layout, synth
+    from panagram_b200.index import Index, IndexConfig
+    wl = INDEX_WORKLOADS[args.index_e2e]
+    tmp = Path(tempfile.mkdtemp(prefix="pk_idx_"))
+    unit = "anchored k-mers/s"
+    res = {"metric": "anchored k-mers/sec (positions x genomes), whole `panagram index` from FASTA files to anchor directories",
+           "unit": unit, "n_gpus": 1, "higher_is_better": True, "data": "synthetic", "dtype": "u64",
+           "config": {"workload": wl["name"], "k": wl["k"], "host_cores": cores}}
+    try:
+        samples = synth.make_pangenome(tmp / "fa", wl["n"], wl["length"], wl["seed"])
+        res["config"]["fasta_bytes"] = sum(os.path.getsize(p) for _, p in samples)
+        anchors = wl["anchors"] or [n for n, _ in samples]
+        tsv = tmp / "samples.tsv"
+        tsv.write_text("name\tfasta\n" + "".join(f"{n}\t{p}\n" for n, p in samples))
+        log = []
+        idx = Index(tsv, tmp / "ours", IndexConfig(k=wl["k"], cores=min(cores, 32), anchor_genomes=list(anchors)))
+        t0 = time.perf_counter()
+        out = idx.run(log=log.append)
+        ours_s = time.perf_counter() - t0
+        positions = sum(o["positions"] for o in out.values())
+        res.update(value=positions * wl["n"] / ours_s, total_s=round(ours_s, 3), positions=positions, log=log)
+        if not args.no_cpu_baseline:
+            from oracle import refpipe
+            if refpipe.have_ref():
+                t0 = time.perf_counter()
+                tm = refpipe.build_index(tmp / "ref", samples, wl["k"], anchors=list(anchors), threads=cores)
+                ref_s = time.perf_counter() - t0
+                res["cpu_baseline"] = {"value": positions * wl["n"] / ref_s, "unit": unit, "kind": "reference", "cores": cores,
+                                       "total_s": round(ref_s, 3), "stages_s": {k: round(v, 3) for k, v in tm.items()},
+                                       "sample": f"the whole workload; kmc/kmc_tools -t{cores}, run_anchor one thread per anchor "
+                                                 f"(cpp/anchor.cpp:217)"}
+                bad = []
+                for a in anchors:
+                    want = refpipe.read_anchor_dir(tmp / "ref" / "anchor" / a)
+                    d = tmp / "ours" / "anchor" / a
+                    got = {"chrs.tsv": (d / "chrs.tsv").read_text(), "bitsum.bins.tsv": (d / "bitsum.bins.tsv").read_text(),
+                           "bitmap.1": layout.read_bgzf(d / "bitmap.1.gz"), "bitmap.100": layout.read_bgzf(d / "bitmap.100.gz")}
+                    bad += [f"{a}/{key}" for key in got if got[key] != want[key]]
+                res["outputs_identical_to_reference"] = not bad
+                if bad:
+                    res["mismatch"] = bad
+        print(json.dumps(res))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -155,6 +219,8 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--probe-mode", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index-e2e", default="", choices=[""] + sorted(INDEX_WORKLOADS),
+                    help="instead of the anchoring step: time the whole `panagram index` run from FASTA files on disk")
     ap.add_argument("--e2e-batches", type=int, default=0, help="override the engine's batches per pk_anchor_genome call (0 = default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: assemble rows with the fused peer-memory gather+interleave kernel or NCCL all-gather + interleave")
@@ -167,6 +233,10 @@ def main():
     unit = "anchored k-mers/s"
     metric = "anchored k-mers/sec (positions x genomes) building pan-kmer bitmap"
 
+    if args.index_e2e:
+        if rank == 0:
+            run_index_e2e(args, cores)
+        return
     if args.impl == "reference":
         if rank != 0:
             return
@@ -332,6 +402,7 @@ def main():
         h[:] = c
         h_chroms.append(h)
     e2e_ms = None
+    e2e_ms_mean = None
     e2e_files = None
     e2e_timeline = None
     if world == 1:
@@ -344,7 +415,8 @@ def main():
             t1 = time.perf_counter()
             res = eng.anchor_genome(h_chroms, out=res)
             ts.append((time.perf_counter() - t1) * 1e3)
-        e2e_ms = sum(ts) / len(ts)
+        e2e_ms = statistics.median(ts)          # per-call wall times; the median keeps one host hiccup out of a 5-step mean
+        e2e_ms_mean = sum(ts) / len(ts)
         e2e_stats = eng.stats()
         # CUDA events of the last call on the engine's streams: H2D + pack + K1 (overlapped) | K2 + K3 | K4 + reduce per
         # chromosome | tail of the D2H copies
@@ -364,7 +436,7 @@ def main():
             ts.append((time.perf_counter() - t1) * 1e3)
         e2e_files = {"what": "pk_anchor_genome_bgzf: ASCII in (pinned host) -> bitmap.1.gz/.gzi + bitmap.100.gz/.gzi file "
                              "images (BGZF deflated on the GPU) + histograms + column sums out",
-                     "ms_per_step": sum(ts) / len(ts), "value": positions * n_total / (sum(ts) / len(ts) / 1e3), "unit": unit,
+                     "ms_per_step": statistics.median(ts), "value": positions * n_total / (statistics.median(ts) / 1e3), "unit": unit,
                      "h2d_bytes_per_step": int(h2d),
                      "d2h_bytes_per_step": int(rz["gz"].size + rz["gzi"].size + rz["gz_low"].size + rz["gzi_low"].size),
                      "raw_bitmap_bytes": int(positions * rb_local), "gz_bytes": int(rz["gz"].size)}
@@ -441,7 +513,7 @@ def main():
                            "setup_s": round(setup_s, 1)},
                 "e2e": {"value": positions * n_total / (e2e_ms / 1e3), "unit": unit, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "device_timeline_ms": e2e_timeline},
+                        "ms_per_step_mean": e2e_ms_mean, "device_timeline_ms": e2e_timeline},
                 "e2e_files": e2e_files, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "tables": {"keys": [t["n_keys"] for t in tstats], "overflow_frac": sum(t["n_overflow"] for t in tstats) /
                            max(1, sum(t["n_keys"] for t in tstats))}}

@@ -3,7 +3,7 @@
 Host-side mirror of ``KMCdb::anchor_fasta`` (``cpp/anchor.cpp:37-109``) and of
 ``Genome.run_anchor`` (``panagram/index.py:1012-1097``): parse the FASTA, run every
 chromosome through the engine (GPU), stream the rows into BGZF, and emit
-``chrs.tsv``, ``bitsum.bins.tsv`` and ``total_paircounts.csv``.
+``chrs.tsv``, ``bitsum.bins.tsv``, ``total_paircounts.csv`` and the two UMAP CSVs.
 """
 from __future__ import annotations
 
@@ -60,7 +60,7 @@ def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
 
 def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[str] | None = None,
                  bgzf_level: int = 6, threads: int | None = None, strip_cr: bool = False,
-                 bgzf: str = "gpu") -> dict:
+                 bgzf: str = "gpu", umap_bin_size: int = 100000) -> dict:
     """Anchor one genome and write its directory. Returns summary numbers.
 
     The engine must hold all N genomes (single-GPU layout). Chromosomes shorter
@@ -99,6 +99,29 @@ def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[st
         wl.close(outdir / f"bitmap.{step}.gzi")
     else:
         raise ValueError(f"bgzf={bgzf!r}: expected 'gpu' or 'zlib'")
+    # chrom_umaps.csv / genome_umap.csv (Genome.write_umaps, index.py:1107-1131) from the low-res rows
+    if bgzf == "gpu":
+        import gzip as _gzip
+        low_all = np.frombuffer(_gzip.decompress(res["gz_low"].tobytes()), dtype=np.uint8).reshape(-1, engine.row_bytes)
+    else:
+        low_all = np.concatenate([r["low"] for r in res["chroms"]]) if res["chroms"] else np.zeros((0, engine.row_bytes), np.uint8)
+    chrom_rows, genome_parts, lo = [], [], 0
+    for (cname, _), r in zip(recs, res["chroms"]):
+        n_low = (r["nkmers"] + step - 1) // step
+        starts, frac = layout.paircount_bins(low_all[lo:lo + n_low], engine.n_local, step, umap_bin_size)
+        lo += n_low
+        chrom_rows += layout.umap_rows(cname, starts, frac, umap_bin_size)
+        genome_parts.append((cname, starts, frac))
+    (outdir / "chrom_umaps.csv").write_text(layout.umaps_csv(chrom_rows))
+    if genome_parts:
+        g_starts = np.concatenate([p[1] for p in genome_parts])
+        g_frac = np.concatenate([p[2] for p in genome_parts])
+        g_names = np.concatenate([[p[0]] * len(p[1]) for p in genome_parts])
+        g_rows = layout.umap_rows("", g_starts, g_frac, umap_bin_size)
+        g_rows = [(str(n),) + r[1:] for n, r in zip(g_names, g_rows)]
+    else:
+        g_rows = []
+    (outdir / "genome_umap.csv").write_text(layout.umaps_csv(g_rows))
     col = res["col_sums"]
     for (cname, _), r in zip(recs, res["chroms"]):
         chroms.append((cname, r["nkmers"]))

@@ -14,24 +14,34 @@
 
 struct PkzMeta { uint32_t cdata, crc, isize, stored; };
 
-// one block (PKZ_LANES threads) per BGZF member; thread l deflates and CRCs piece l
+// one block (PKZ_LANES threads) per BGZF member; thread l deflates and CRCs piece l. The member's payload is
+// staged in shared memory first: every thread walks its own 510 bytes one at a time, and out of global memory
+// those byte loads missed L1 (16 resident blocks x 64 KB of payload per SM) and cost an L2 round trip each:
+// 1.07 ms for 135 MB, ~1100 cycles per byte per thread (profiles/r1h_launches.csv).
 __global__ void __launch_bounds__(PKZ_LANES) bgzf_encode_kernel(const uint8_t *__restrict__ in, uint64_t n, uint32_t dist,
                                                                 uint8_t *__restrict__ stage, uint16_t *__restrict__ piece_sizes,
                                                                 PkzMeta *__restrict__ meta, const uint32_t *__restrict__ g_tables) {
+    extern __shared__ __align__(16) uint8_t s_blk[];           // [PKZ_PAYLOAD]
     __shared__ uint32_t s_tab[256 + PKZ_CRC_MATS * 32];
     __shared__ uint32_t s_crc[PKZ_LANES / 32], s_size[PKZ_LANES / 32];
-    for (uint32_t i = threadIdx.x; i < 256 + PKZ_CRC_MATS * 32; i += blockDim.x) s_tab[i] = g_tables[i];
-    __syncthreads();
     const uint32_t l = threadIdx.x;
     const uint64_t b = blockIdx.x;
     const uint8_t *blk = in + b * PKZ_PAYLOAD;
     const uint32_t blen = (uint32_t)(n - b * PKZ_PAYLOAD < PKZ_PAYLOAD ? n - b * PKZ_PAYLOAD : PKZ_PAYLOAD);
+    for (uint32_t i = l; i < 256 + PKZ_CRC_MATS * 32; i += PKZ_LANES) s_tab[i] = g_tables[i];
+    if ((((uintptr_t)blk) & 15) == 0) {
+        for (uint32_t i = l * 16; i + 16 <= blen; i += PKZ_LANES * 16) *(uint4 *)(s_blk + i) = *(const uint4 *)(blk + i);
+        for (uint32_t i = (blen & ~15u) + l; i < blen; i += PKZ_LANES) s_blk[i] = blk[i];
+    } else {
+        for (uint32_t i = l; i < blen; i += PKZ_LANES) s_blk[i] = blk[i];
+    }
+    __syncthreads();
     const uint32_t s = l * PKZ_SUB < blen ? l * PKZ_SUB : blen;
     const uint32_t e = (l + 1) * PKZ_SUB < blen ? (l + 1) * PKZ_SUB : blen;
     uint32_t size = 0;
-    if (e > s) size = pkz_encode_piece(blk, s, e, dist, e == blen, stage + (b * PKZ_LANES + l) * PKZ_STAGE);
+    if (e > s) size = pkz_encode_piece(s_blk, s, e, dist, e == blen, stage + (b * PKZ_LANES + l) * PKZ_STAGE);
     piece_sizes[b * PKZ_LANES + l] = (uint16_t)size;
-    uint32_t crc = pkz_crc_update(s_tab, l == 0 ? 0xFFFFFFFFu : 0u, blk + s, e - s);
+    uint32_t crc = pkz_crc_update(s_tab, l == 0 ? 0xFFFFFFFFu : 0u, s_blk + s, e - s);
     crc = pkz_crc_shift(s_tab + 256, crc, blen - e);           // bytes that follow this piece
     crc = __reduce_xor_sync(0xffffffffu, crc);
     const uint32_t total = __reduce_add_sync(0xffffffffu, size);
@@ -163,7 +173,10 @@ void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_o
     uint16_t *piece_sizes = (uint16_t *)p;
     if (dist < 1) dist = 1;
     if (dist > 32768) dist = 32768;
-    if (nb) bgzf_encode_kernel<<<(unsigned)nb, PKZ_LANES, 0, s>>>(d_in, n, dist, stage, piece_sizes, meta, d_tables);
+    if (nb) {
+        cudaFuncSetAttribute(bgzf_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PKZ_PAYLOAD);
+        bgzf_encode_kernel<<<(unsigned)nb, PKZ_LANES, PKZ_PAYLOAD, s>>>(d_in, n, dist, stage, piece_sizes, meta, d_tables);
+    }
     bgzf_scan_kernel<<<1, 1024, 0, s>>>(meta, nb, coff, d_gzi, d_totals, d_out);
     if (nb) bgzf_assemble_kernel<<<(unsigned)nb, 256, 0, s>>>(d_in, n, stage, piece_sizes, meta, coff, d_out);
 }

@@ -152,3 +152,45 @@ def paircounts_csv(names: list[str], counts: np.ndarray, anchor: str) -> str:
             frac = "" if c == 0 else "inf"      # pandas: 0/0 -> NaN (empty field), c/0 -> inf
         lines.append(f"{n},{c},{frac}\n")
     return "".join(lines)
+
+
+# ---- UMAP inputs / files ----------------------------------------------------------
+def paircount_bins(rows_low: np.ndarray, n_genomes: int, step: int, bin_size: int) -> tuple[np.ndarray, np.ndarray]:
+    """Index.bitmap_to_paircount_bins (index.py:454-459) on the low-res rows of ONE chromosome
+    (row i = position i * step): per bin of `bin_size` positions the per-genome count of set bits, divided by
+    the bin's maximum over genomes (0/0 -> NaN, which the caller's .fillna(0) turns into 0).
+    Returns (bin starts [nbins], fractions [nbins, N])."""
+    rows_low = np.asarray(rows_low, dtype=np.uint8).reshape(len(rows_low), -1)
+    bits = np.unpackbits(rows_low, axis=1, bitorder="little")[:, :n_genomes]
+    pos = np.arange(bits.shape[0], dtype=np.int64) * step
+    bins = pos // bin_size
+    first = np.flatnonzero(np.r_[True, bins[1:] != bins[:-1]]) if bits.shape[0] else np.zeros(0, dtype=np.int64)
+    sums = np.add.reduceat(bits.astype(np.int64), first, axis=0) if bits.shape[0] else np.zeros((0, n_genomes), np.int64)
+    mx = sums.max(axis=1, keepdims=True) if sums.size else sums
+    with np.errstate(invalid="ignore", divide="ignore"):
+        frac = np.where(mx > 0, sums / np.maximum(mx, 1), 0.0)
+    return bins[first] * bin_size, frac
+
+
+def umap_rows(chrom: str, starts: np.ndarray, frac: np.ndarray, bin_size: int, neighbors: int = 4, dist: float = 0.0,
+              eps: float = 1.0, samples: int = 1) -> list[tuple]:
+    """Genome.run_umap (index.py:1133-1156): UMAP(n_neighbors, min_dist, n_components=2, random_state=42) +
+    DBSCAN(eps, min_samples) of the binned pair-counts -> (chrom, start, end, umap1, umap2, cluster) rows. When
+    umap-learn is not installed (or the fit fails) the reference's own fallback is written: zeros (index.py:1149-1152)."""
+    emb = None
+    try:
+        import umap  # type: ignore
+        from sklearn.cluster import DBSCAN
+        emb = umap.UMAP(n_neighbors=neighbors, min_dist=dist, n_components=2, random_state=42).fit_transform(frac)
+        clusters = DBSCAN(eps=eps, min_samples=samples).fit_predict(emb)
+    except Exception:
+        emb = None
+    if emb is None:
+        return [(chrom, int(s), int(s) + bin_size, 0, 0, 0) for s in starts]
+    return [(chrom, int(s), int(s) + bin_size, float(a), float(b), int(c)) for s, (a, b), c in zip(starts, emb, clusters)]
+
+
+def umaps_csv(rows: list[tuple]) -> str:
+    """chrom_umaps.csv (DataFrame.set_index("chrom").to_csv()) and genome_umap.csv (to_csv(index=False)) have the
+    same text: header chrom,start,end,umap1,umap2,cluster (index.py:1128-1131)."""
+    return "chrom,start,end,umap1,umap2,cluster\n" + "".join(",".join(map(str, r)) + "\n" for r in rows)
