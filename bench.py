@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--index-e2e", default="", choices=[""] + sorted(INDEX_WORKLOADS),
                     help="instead of the anchoring step: time the whole `panagram index` run from FASTA files on disk")
+    ap.add_argument("--group-tables", type=int, default=1, help="0: per-genome tables only (one probe per genome and position)")
     ap.add_argument("--e2e-batches", type=int, default=0, help="override the engine's batches per pk_anchor_genome call (0 = default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: assemble rows with the fused peer-memory gather+interleave kernel or NCCL all-gather + interleave")
@@ -286,6 +287,8 @@ def main():
     if anchor_chroms is None:
         anchor_chroms = make_genome(anc, 0, wl["seed"])
     del anc
+    if not args.group_tables:
+        eng.tune(group_tables=0)
     eng.finalize()
     if args.e2e_batches:
         eng.tune(e2e_batches=args.e2e_batches)
@@ -479,7 +482,8 @@ def main():
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
             traffic = None
-        roof = {"bound": "hbm", "kernel": ("probe_win_kernel" if ks.get("k_probe_window") else "probe_part_kernel") if ks["k_probe_ms"] > 0 else "probe_kernel",
+        roof = {"bound": "hbm", "kernel": ({2: "probe_win_kernel<group tables>", 1: "probe_win_kernel"}.get(int(ks.get("k_probe_window", 0)), "probe_part_kernel"))
+                if ks["k_probe_ms"] > 0 else "probe_kernel",
                 "achieved": alg_bytes / (k3_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (k3_ms / 1e3) / 1e9 / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k3_ms,
@@ -516,7 +520,8 @@ def main():
                         "ms_per_step_mean": e2e_ms_mean, "device_timeline_ms": e2e_timeline},
                 "e2e_files": e2e_files, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "tables": {"keys": [t["n_keys"] for t in tstats], "overflow_frac": sum(t["n_overflow"] for t in tstats) /
-                           max(1, sum(t["n_keys"] for t in tstats))}}
+                           max(1, sum(t["n_keys"] for t in tstats)),
+                           "group_tables": [eng.group_stats(u) for u in range((npg + 7) // 8)]}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -74,7 +74,11 @@ def main():
     for spec in args.settings or ["k3_window=1"]:
         knobs = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in spec.split(",") if kv}
         try:
+            refinalize = "group_tables" in knobs
             eng.tune(**knobs)
+            if refinalize:
+                eng.finalize()
+                print("   group tables:", eng.group_stats(0), flush=True)
             d_rows.zero_()
             for _ in range(2):
                 eng.probe_device(d_words.data_ptr(), d_mask.data_ptr(), 0, npos, d_rows.data_ptr(), rb, 0, st)

@@ -114,6 +114,12 @@ typedef struct pk_table_stats {
     uint64_t bytes;         /* device bytes */
 } pk_table_stats;
 int pk_engine_table_stats(const pk_engine *e, uint32_t genome, pk_table_stats *out);
+/* Group tables: pk_engine_finalize also merges the per-genome tables of every 8 consecutive local genomes into
+ * ONE table whose slots carry an 8-bit membership mask (the structure of the reference's merged "bitvec"
+ * database, workflow/Snakefile:54-69 / index.py:407-426, as a hash table), so that the partitioned probe
+ * answers 8 genomes with one bucket read. n_keys = distinct k-mers of the group; PK_ESTATE when group tables are
+ * switched off (pk_engine_tune "group_tables" 0) or could not be built. group = local genome index / 8. */
+int pk_engine_group_stats(const pk_engine *e, uint32_t group, pk_table_stats *out);
 
 /* ---- the hot path, host buffers ---------------------------------------------
  * pk_bin_len: the bin-length rule of KMCdb::write_bits (cpp/anchor.cpp:114-118) /
@@ -236,7 +242,8 @@ int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *se
  * them; tests run the parity suite under several settings. name = "k3_window" (1: probe out of table
  * windows staged in shared memory by TMA bulk copies when they fit, 0: always probe through L1/L2),
  * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_group" (0 = by window size, or 1, 2, 4 genomes per window group; two groups of windows are staged per block),
- * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "unpermute" (0/1: applies to
+ * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "group_tables" (0/1: per-engine;
+ * takes effect at the next pk_engine_finalize), "unpermute" (0/1: applies to
  * scratch allocated afterwards), "e2e_batches" (1..8: batches of whole chromosomes per pk_anchor_genome call;
  * copies of one batch overlap the kernels of the other), "e2e_batch_min" (positions from which a genome is
  * split into batches; default 32 Mi). Unknown names return PK_EINVAL. */
@@ -249,7 +256,7 @@ typedef struct pk_stats {
      * they ran on: K1 partition_seq, K2 partition_fine, K3 probe_part, K3 over the spill list,
      * K4 unpermute */
     float k_partition_ms, k_fine_ms, k_probe_ms, k_spill_ms, k_unpermute_ms;
-    float k_probe_window;    /* 1 when K3 ran as probe_win_kernel (windows staged by TMA), 0 for probe_part_kernel */
+    float k_probe_window;    /* K3 of the last launch: 2 probe_win_kernel on group tables, 1 on per-genome tables, 0 probe_part_kernel */
     uint64_t positions, probes, probe_launches, kernel_launches;
 } pk_stats;
 int pk_engine_stats(const pk_engine *e, pk_stats *out);

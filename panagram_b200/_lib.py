@@ -73,6 +73,7 @@ SIGNATURES = {
     "pk_engine_add_sequence_device": (C.c_int, [_vp, _u32, _vp, _u64]),
     "pk_engine_finalize": (C.c_int, [_vp]),
     "pk_engine_table_stats": (C.c_int, [_vp, _u32, C.POINTER(PkTableStats)]),
+    "pk_engine_group_stats": (C.c_int, [_vp, _u32, C.POINTER(PkTableStats)]),
     "pk_bin_len": (_u64, [C.POINTER(PkConfig), _u64]),
     "pk_anchor_genome": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pk_anchor_chrom": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _pu64]),

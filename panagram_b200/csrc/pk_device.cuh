@@ -51,13 +51,23 @@ __device__ __forceinline__ uint32_t pk_mix32(uint32_t x) {
 }
 
 // The 32-bit hash every table is indexed by (bucket = mulhi(hash, n_buckets)).
-//  S64: any good hash of the whole k-mer; the slot stores the whole k-mer.
 //  S32: the slot stores only the low 28 key bits (+ 4 displacement bits), so the remaining eb = 2k-28 high
 //       key bits must be recoverable from the home bucket: they are XOR-ed with a hash of the low bits
 //       (uniform, and a bijection for fixed low bits) and placed in the TOP eb bits of the hash; with
 //       n_buckets >= 2^eb two k-mers with equal low bits never share a home bucket.
+//  S64: the slot stores the whole k-mer, any good hash would do; the hash has the same structure with a 52-bit
+//       remainder (ebu = max(0, 2k-52) top bits carry the high key bits), because the GROUP tables (below) store
+//       52 key bits per slot and are indexed by the same hash as the per-genome tables.
+#define PK_U_REM_BITS 52
+#define PK_U_REM_MASK 0x000FFFFFFFFFFFFFull
 __device__ __forceinline__ uint32_t pk_key_hash(uint64_t canon, const PkKeySpec ks) {
-    if (ks.fmt == PK_FMT_S64) return pk_hash64(canon);
+    if (ks.fmt == PK_FMT_S64) {
+        const uint32_t m = pk_hash64(canon & PK_U_REM_MASK);
+        const uint32_t ebu = 2 * ks.k > PK_U_REM_BITS ? 2 * ks.k - PK_U_REM_BITS : 0;
+        if (ebu == 0) return m;
+        const uint32_t hi = (uint32_t)(canon >> PK_U_REM_BITS);
+        return ((hi ^ ((m * 0x9E3779B1u) >> (32 - ebu))) << (32 - ebu)) | (m >> ebu);
+    }
     const uint32_t lo = (uint32_t)canon & PK_S32_REM_MASK, m = pk_mix32(lo);
     if (ks.eb == 0) return m;
     const uint32_t hi = (uint32_t)(canon >> PK_S32_REM_BITS);
@@ -142,5 +152,66 @@ template <int FMT> __device__ __forceinline__ bool pk_lookup(const PkTable t, ui
         if (r == maxd) return FMT == PK_FMT_S32 ? pk_stash_contains(ks, g, canon) : false;
         b = b + 1 == t.n_buckets ? 0 : b + 1;
     }
+}
+// ------------------------------------------------------------------ group ("union") tables
+// One table per group of <= 8 genomes, derived from the per-genome tables at finalize: slot = 64 bits =
+// [membership mask 8][key remainder 52][displacement 4], 4 slots per 32 B bucket, EMPTY = ~0 (displacement 15
+// never occurs). ONE probe answers 8 genomes — the structure of the reference's own merged "bitvec" database
+// (counter = 32-genome bit vector, index.py:407-426), as a bucketed hash table. Indexed by the same hash as the
+// per-genome tables; for 2k <= 52 the remainder is the whole k-mer, above that the top 2k-52 key bits are implied
+// by the home bucket exactly as in the S32 format. Keys that find 15 full buckets in a row go to the engine-wide
+// stash under their genome, like S32 keys.
+#define PK_U_KEY_MASK 0x00FFFFFFFFFFFFFFull
+#define PK_U_MASK_SHIFT 56
+#define PK_U_GROUP 8u
+__device__ __forceinline__ uint64_t pk_u_key(uint64_t canon, uint32_t r) { return ((canon & PK_U_REM_MASK) << PK_S32_DISP_BITS) | r; }
+__device__ __forceinline__ uint32_t pk_u_max_disp(uint32_t n_buckets) { return n_buckets - 1 < PK_S32_MAX_DISP ? n_buckets - 1 : PK_S32_MAX_DISP; }
+// membership mask of `key56` in a bucket (0 when absent)
+__device__ __forceinline__ uint32_t pk_u_bucket_mask(const u64x4 &v, uint64_t key56) {
+    uint32_t m = 0;
+    if ((v.a & PK_U_KEY_MASK) == key56) m |= (uint32_t)(v.a >> PK_U_MASK_SHIFT);
+    if ((v.b & PK_U_KEY_MASK) == key56) m |= (uint32_t)(v.b >> PK_U_MASK_SHIFT);
+    if ((v.c & PK_U_KEY_MASK) == key56) m |= (uint32_t)(v.c >> PK_U_MASK_SHIFT);
+    if ((v.d & PK_U_KEY_MASK) == key56) m |= (uint32_t)(v.d >> PK_U_MASK_SHIFT);
+    return m;
+}
+// full lookup in a group table; g0 = local index of the group's first genome, ng = genomes in the group
+__device__ __forceinline__ uint32_t pk_u_lookup(const PkTable t, uint64_t canon, uint32_t h, uint32_t g0, uint32_t ng, const PkKeySpec ks) {
+    uint32_t b = __umulhi(h, t.n_buckets);
+    const uint32_t maxd = pk_u_max_disp(t.n_buckets);
+    for (uint32_t r = 0;; r++) {
+        const u64x4 v = pk_ld_bucket_ca((const char *)t.slots + 32ull * b);
+        const uint32_t m = pk_u_bucket_mask(v, pk_u_key(canon, r));
+        if (m) return m;
+        if (v.d == PK_EMPTY) return 0;
+        if (r == maxd) {
+            uint32_t sm = 0;
+            for (uint32_t g = 0; g < ng; g++) sm |= (uint32_t)pk_stash_contains(ks, g0 + g, canon) << g;
+            return sm;
+        }
+        b = b + 1 == t.n_buckets ? 0 : b + 1;
+    }
+}
+// set genome bit `bit` (0..7) of `canon` in group table t. 0 = bit was already set, 1 = set in an existing slot,
+// 2 = new slot in the home bucket, 3 = new slot in a later bucket, 4 = no room within 15 buckets (caller stashes)
+__device__ __forceinline__ int pk_u_insert(const PkTable t, uint64_t canon, uint32_t h, uint32_t bit) {
+    uint32_t b = __umulhi(h, t.n_buckets);
+    const uint32_t maxd = pk_u_max_disp(t.n_buckets);
+    const unsigned long long mbit = 1ull << (PK_U_MASK_SHIFT + bit);
+    for (uint32_t r = 0; r <= maxd; r++) {
+        const unsigned long long key56 = pk_u_key(canon, r);
+        unsigned long long *slot = t.slots + 4ull * b;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            unsigned long long cur = *(volatile unsigned long long *)(slot + i);
+            if (cur == PK_EMPTY) {
+                cur = atomicCAS(slot + i, PK_EMPTY, key56 | mbit);
+                if (cur == PK_EMPTY) return r == 0 ? 2 : 3;
+            }
+            if ((cur & PK_U_KEY_MASK) == key56) return (atomicOr(slot + i, mbit) & mbit) ? 0 : 1;
+        }
+        b = b + 1 == t.n_buckets ? 0 : b + 1;
+    }
+    return 4;
 }
 #endif

@@ -47,6 +47,12 @@ struct pk_engine {
     std::vector<HostTable> tabs;
     PkTable *d_tables = nullptr;
     std::vector<PkTable> h_tables;              // host copy of the descriptors (kernel-parameter path)
+    // group tables: one per PK_GROUP (8) local genomes, derived from the per-genome tables by finalize; the
+    // partitioned probe answers 8 genomes per probe out of them (pk_device.cuh)
+    std::vector<HostTable> utabs;
+    std::vector<PkTable> h_utables;             // empty when group tables are off or could not be built
+    int union_tables = 1;
+    unsigned long long *d_ucounters = nullptr;  // [4]
     unsigned long long *d_counters = nullptr;   // [3 * n_local]
     bool finalized = false;
     cudaStream_t stream = nullptr;              // build stream / default stream for device-level calls
@@ -147,6 +153,7 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (const char *tf = getenv("PK_TABLE_FMT")) { if (atoi(tf) == 64) e->ks.fmt = PK_FMT_S64; }
     if (const char *pf = getenv("PK_L2_PREFETCH")) e->l2_prefetch = atoi(pf);
     if (const char *up = getenv("PK_UNPERMUTE")) e->unpermute = atoi(up);
+    if (const char *ut = getenv("PK_GROUP_TABLES")) e->union_tables = atoi(ut) ? 1 : 0;
     if (const char *kv = getenv("PK_K3_VARIANT")) pk_part_set_variant(atoi(kv));
     {
         const char *we = getenv("PK_K3_WINDOW"), *wv = getenv("PK_K3W_VARIANT"), *ws = getenv("PK_K3W_GROUP");
@@ -179,6 +186,8 @@ extern "C" void pk_engine_destroy(pk_engine *e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (auto &t : e->tabs) cudaFree(t.dev.slots);
+    for (auto &t : e->utabs) cudaFree(t.dev.slots);
+    cudaFree(e->d_ucounters);
     cudaFree(e->sc.buf1); cudaFree(e->sc.buf2); cudaFree(e->sc.spill);
     cudaFree(e->sc.cursor1); cudaFree(e->sc.cursor2); cudaFree(e->sc.spill_cursor); cudaFree(e->sc.err);
     cudaFree(e->g_ascii); cudaFree(e->g_words); cudaFree(e->g_mask); cudaFree(e->g_rows); cudaFree(e->g_low); cudaFree(e->g_u32);
@@ -372,6 +381,84 @@ extern "C" int pk_engine_add_sequence_device(pk_engine *e, uint32_t genome, cons
     return add_sequence_device(e, genome, (const uint8_t *)d_ascii, len);
 }
 
+// Group tables (pk_device.cuh): merge the per-genome tables of every 8 local genomes into one table whose slots
+// carry an 8-bit membership mask. The number of distinct k-mers of a group is not known in advance (between the
+// largest genome's count and the sum): it is estimated by merging 1/64 of the hash range into a scratch table
+// first. A group that cannot be built (allocation failure, a neighbourhood of 15 full buckets with 64-bit keys)
+// switches group tables off for the engine: the per-genome tables answer every query on their own.
+#define PK_GROUP 8u
+static void drop_group_tables(pk_engine *e) {
+    for (auto &t : e->utabs) cudaFree(t.dev.slots);
+    e->utabs.clear();
+    e->h_utables.clear();
+}
+static int build_group_tables(pk_engine *e) {
+    drop_group_tables(e);
+    if (!e->union_tables) return PK_OK;
+    const uint32_t n_groups = (e->n_local + PK_GROUP - 1) / PK_GROUP;
+    if (!e->d_ucounters) CU(cudaMalloc(&e->d_ucounters, 4 * sizeof(unsigned long long)));
+    const double load = std::min(e->ks.fmt == PK_FMT_S32 ? 0.5 : 0.35, (double)e->cfg.load_factor);
+    const uint32_t ebu = 2 * e->cfg.k > 52 ? 2 * e->cfg.k - 52 : 0;
+    const int use_stash = e->ks.fmt == PK_FMT_S32;
+    e->utabs.resize(n_groups);
+    unsigned long long c[4] = {0, 0, 0, 0};
+    uint64_t sum = 0;
+    // not an error for the caller (the per-genome tables answer everything), but worth a line: it costs speed
+    auto fail = [&](const char *why) {
+        const cudaError_t ce = cudaGetLastError();
+        fprintf(stderr, "[pkanchor] group tables not built: %s (slots %llu, bits %llu, stashed %llu, failed %llu of %llu keys; cuda: %s)\n",
+                why, c[0], c[1], c[2], c[3], (unsigned long long)sum, cudaGetErrorString(ce));
+        drop_group_tables(e);
+        return PK_OK;
+    };
+    // the group tables are an acceleration structure: their fill is capped whatever the per-genome tables use. With 4
+    // slots per bucket, 2 of 315 M keys met 15 full buckets in a row at a fill of 0.49 (configs[1]); k <= 24 sends
+    // those to the stash, longer k-mers (no stash for > 48-bit keys) get a fill of 0.35 instead
+    for (uint32_t gi = 0; gi < n_groups; gi++) {
+        const uint32_t g0 = gi * PK_GROUP, ng = std::min(PK_GROUP, e->n_local - g0);
+        uint64_t mx = 0;
+        sum = 0;
+        for (uint32_t g = g0; g < g0 + ng; g++) { sum += e->tabs[g].n_keys; mx = std::max(mx, e->tabs[g].n_keys); }
+        uint64_t distinct = sum;
+        if (ng > 1 && sum >= (1ull << 22)) {
+            // estimate: merge the first 1/64 of every table's buckets (= of the hash range) into a scratch table
+            PkTable tmp{nullptr, 0, 0};
+            const uint64_t nbt = (uint64_t)((double)sum / 64 / (4.0 * 0.5)) + 4096;
+            if (cudaMalloc(&tmp.slots, nbt * 32) != cudaSuccess) return fail("scratch allocation");
+            tmp.n_buckets = (uint32_t)nbt;
+            pk_launch_fill_empty(tmp.slots, nbt * 4, e->stream);
+            cudaMemsetAsync(e->d_ucounters, 0, sizeof c, e->stream);
+            for (uint32_t g = g0; g < g0 + ng; g++)
+                pk_launch_union_merge(e->tabs[g].dev, e->tabs[g].dev.n_buckets / 64, 6, e->ks, tmp, g - g0, g, 0, e->d_ucounters, e->stream);
+            cudaMemcpyAsync(c, e->d_ucounters, sizeof c, cudaMemcpyDeviceToHost, e->stream);
+            const cudaError_t er = cudaStreamSynchronize(e->stream);
+            cudaFree(tmp.slots);
+            if (er != cudaSuccess) return fail("estimate");
+            distinct = std::min<uint64_t>(sum, std::max<uint64_t>(mx, (uint64_t)((double)(c[0] + c[3]) * 64 * 1.03) + 65536));
+        }
+        uint64_t nb = (uint64_t)((double)distinct / (4.0 * load)) + 2;
+        nb = std::max<uint64_t>(nb, std::max<uint64_t>(1ull << ebu, 16));
+        if (nb >= 0xFFFFFFFFull) return fail("too many buckets");
+        HostTable &u = e->utabs[gi];
+        if (cudaMalloc(&u.dev.slots, nb * 32) != cudaSuccess) { u.dev.slots = nullptr; return fail("allocation"); }
+        u.dev.n_buckets = (uint32_t)nb;
+        u.capacity = distinct; u.reserved = true;
+        pk_launch_fill_empty(u.dev.slots, nb * 4, e->stream);
+        cudaMemsetAsync(e->d_ucounters, 0, sizeof c, e->stream);
+        for (uint32_t g = g0; g < g0 + ng; g++)
+            pk_launch_union_merge(e->tabs[g].dev, e->tabs[g].dev.n_buckets, 0, e->ks, u.dev, g - g0, g, use_stash, e->d_ucounters, e->stream);
+        if (use_stash) pk_launch_union_merge_stash(e->ks, u.dev, g0, ng, e->d_ucounters, e->stream);
+        cudaMemcpyAsync(c, e->d_ucounters, sizeof c, cudaMemcpyDeviceToHost, e->stream);
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail("merge");
+        // every per-genome key must have arrived: bits set + stashed == sum of the genomes' key counts
+        if (c[3] || c[1] + c[2] != sum) return fail("merge incomplete");
+        u.n_keys = c[0];
+    }
+    e->h_utables.resize(n_groups);
+    for (uint32_t gi = 0; gi < n_groups; gi++) e->h_utables[gi] = e->utabs[gi].dev;
+    return PK_OK;
+}
+
 extern "C" int pk_engine_finalize(pk_engine *e) {
     if (!e) { pk_set_error("null engine"); return PK_EINVAL; }
     int rc = set_device(e); if (rc) return rc;
@@ -392,6 +479,7 @@ extern "C" int pk_engine_finalize(pk_engine *e) {
         }
     }
     rc = upload_tables(e); if (rc) return rc;
+    rc = build_group_tables(e); if (rc) return rc;
     e->finalized = true;
     return PK_OK;
 }
@@ -401,6 +489,15 @@ extern "C" int pk_engine_table_stats(const pk_engine *e, uint32_t genome, pk_tab
     if (!is_local(e, genome)) { pk_set_error("genome %u is not in this engine's shard", genome); return PK_EINVAL; }
     const HostTable &t = e->tabs[genome - e->cfg.genome_begin];
     out->n_keys = t.n_keys; out->n_buckets = t.dev.n_buckets; out->n_overflow = t.n_overflow;
+    out->bytes = (uint64_t)t.dev.n_buckets * 32;
+    return PK_OK;
+}
+
+extern "C" int pk_engine_group_stats(const pk_engine *e, uint32_t group, pk_table_stats *out) {
+    if (!e || !out) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (group >= e->utabs.size() || e->h_utables.empty()) { pk_set_error("no group table %u (group tables off, or not built)", group); return PK_ESTATE; }
+    const HostTable &t = e->utabs[group];
+    out->n_keys = t.n_keys; out->n_buckets = t.dev.n_buckets; out->n_overflow = 0;
     out->bytes = (uint64_t)t.dev.n_buckets * 32;
     return PK_OK;
 }
@@ -556,7 +653,8 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
             PkPartPlan pl;
             pk_part_plan(m, &pl);
             int rc = ensure_scratch(e, pl); if (rc) return rc;
-            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->h_tables.data(), e->n_local,
+            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->h_tables.data(),
+                                            e->h_utables.empty() ? nullptr : e->h_utables.data(), e->n_local,
                                             d_rows + o * row_stride, row_stride, col_offset, pl, e->sc, e->l2_prefetch, s, e->pev)) {
                 pk_set_error("partitioned probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return PK_ECUDA;
@@ -762,7 +860,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
         }
         if (first) { CU(cudaEventRecord(e->ev[1], s)); CU(cudaEventRecord(e->ev[2], s)); }
         if (pipelined) {
-            pk_part_probe(e->g_words, e->g_mask, bt.base, e->ks, e->h_tables.data(), N, rows_b, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
+            pk_part_probe(e->g_words, e->g_mask, bt.base, e->ks, e->h_tables.data(), e->h_utables.empty() ? nullptr : e->h_utables.data(), N, rows_b, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
             e->stats.kernel_launches += (pl.pb2 ? 1 : 0) + 2 * ((N + 31) / 32);
             e->stats.probe_launches += 1;
         } else {
@@ -935,6 +1033,11 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } g_tune_wstages = value; }
     else if (n == "k3_variant") { pk_part_set_variant(value); return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
+    else if (n == "group_tables") {        // 0: per-genome tables only; takes effect at the next pk_engine_finalize
+        e->union_tables = value ? 1 : 0;
+        if (!value) drop_group_tables(e);
+        return PK_OK;
+    }
     else if (n == "e2e_batch_min") { e->e2e_batch_min = value < 0 ? 0 : (uint64_t)value; return PK_OK; }
     else if (n == "e2e_batches") { if (value < 1 || value > 8) { pk_set_error("e2e_batches %d out of 1..8", value); return PK_EINVAL; } e->e2e_batches = value; return PK_OK; }
     else if (n == "unpermute") {

@@ -86,6 +86,10 @@ struct PkDecodeArgs {
     unsigned long long *d_counters;   // [3 * n_local]: inserted, overflow, fail per local genome
 };
 void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s);
+// merge a per-genome table into its group table (genome bit `bit`); see pk_kernels.cu
+void pk_launch_union_merge(PkTable src, uint32_t n_src_buckets, uint32_t hshift, PkKeySpec ks, PkTable dst, uint32_t bit, uint32_t g_local,
+                           int use_stash, unsigned long long *d_counters /*[4]*/, pk_stream_t s);
+void pk_launch_union_merge_stash(PkKeySpec ks, PkTable dst, uint32_t g0, uint32_t ng, unsigned long long *d_counters, pk_stream_t s);
 void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
                      const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                      uint32_t col_offset, pk_stream_t s);
@@ -135,12 +139,12 @@ void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0
                     uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
                     const PkPartScratch &sc, pk_stream_t s);
 void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, const PkTable *h_tables,
-                   uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                   const PkTable *h_utables /*group tables, one per 8 local genomes, or NULL*/, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
                    const PkPartScratch &sc, int prefetch, pk_stream_t s, struct CUevent_st **evs);
 void pk_part_unpermute(uint32_t bin0, uint32_t bin1, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                        uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
-                                const PkTable *d_tables, const PkTable *h_tables, uint32_t n_local, uint8_t *d_rows,
+                                const PkTable *d_tables, const PkTable *h_tables, const PkTable *h_utables, uint32_t n_local, uint8_t *d_rows,
                                 uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
                                 int prefetch, pk_stream_t s, struct CUevent_st **evs /*6 events or NULL*/);
 #endif

@@ -213,6 +213,88 @@ void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s) {
     decode_insert_kernel<<<grid_for(a.n), 256, 0, s>>>(a);
 }
 
+// ------------------------------------------------------------------ group tables (derived at finalize)
+// Merge one per-genome table into its group table: every stored k-mer is re-derived from its slot (S64: the slot
+// is the k-mer; S32: low 28 bits from the slot, the other bits from the HOME bucket = bucket - displacement, by
+// inverting pk_key_hash: the hash is (X << (32-eb)) | (mix32(lo) >> eb) for the one X that maps to the home bucket)
+// and its genome bit is set in the group table. n_src_buckets < src.n_buckets restricts the merge to a prefix of
+// the hash range (used to estimate the number of distinct k-mers of a group from 1/64 of it, with hshift = 6).
+// counters: [0] new slots created, [1] bits set, [2] keys sent to the stash, [3] failures (stash full)
+__global__ void __launch_bounds__(256) union_merge_kernel(PkTable src, uint32_t n_src_buckets, uint32_t hshift, PkKeySpec ks, PkTable dst,
+                                                          uint32_t bit, uint32_t g_local, int use_stash, unsigned long long *counters) {
+    const uint32_t spb = ks.fmt == PK_FMT_S32 ? 8 : 4;                 // slots per bucket
+    const uint64_t total = (uint64_t)n_src_buckets * spb;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t created = 0, set = 0, stashed = 0, failed = 0;
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < total; q += stride) {
+        const uint32_t b = (uint32_t)(q / spb), i = (uint32_t)(q % spb);
+        uint64_t canon;
+        uint32_t h;
+        if (ks.fmt == PK_FMT_S32) {
+            const uint32_t v = ((const uint32_t *)src.slots)[q];
+            if (v == PK_EMPTY32) continue;
+            const uint32_t lo = v >> PK_S32_DISP_BITS, disp = v & 15u;
+            const uint32_t home = b >= disp ? b - disp : b + src.n_buckets - disp;
+            const uint32_t m = pk_mix32(lo);
+            if (ks.eb == 0) {
+                h = m; canon = lo;
+            } else {
+                const uint32_t sh = 32 - ks.eb, low = m >> ks.eb;
+                // smallest hash of the home bucket: ceil(home * 2^32 / n_buckets)
+                const uint32_t hmin = (uint32_t)((((uint64_t)home << 32) + src.n_buckets - 1) / src.n_buckets);
+                uint32_t X = hmin >> sh;
+                h = (X << sh) | low;
+                if (__umulhi(h, src.n_buckets) != home) { X = (X + 1) & ((1u << ks.eb) - 1); h = (X << sh) | low; }
+                const uint32_t hi = X ^ ((m * 0x9E3779B1u) >> sh);
+                canon = ((uint64_t)hi << PK_S32_REM_BITS) | lo;
+            }
+        } else {
+            canon = src.slots[q];
+            if (canon == PK_EMPTY) continue;
+            h = pk_key_hash(canon, ks);
+        }
+        (void)i;
+        const int r = pk_u_insert(dst, canon, h << hshift, bit);      // hshift: a 2^-hshift prefix of the hash range fills all of dst
+        created += r >= 2 && r <= 3; set += r >= 1 && r <= 3;
+        if (r == 4) {
+            // counted by union_merge_stash_kernel, which runs after all table merges and sees every stash entry
+            if (use_stash) { const int sr = pk_stash_insert(ks, g_local, canon); failed += sr == 3; }
+            else failed++;
+        }
+    }
+    created = __reduce_add_sync(0xffffffffu, created); set = __reduce_add_sync(0xffffffffu, set);
+    stashed = __reduce_add_sync(0xffffffffu, stashed); failed = __reduce_add_sync(0xffffffffu, failed);
+    if ((threadIdx.x & 31) == 0) {
+        if (created) atomicAdd(counters, (unsigned long long)created);
+        if (set) atomicAdd(counters + 1, (unsigned long long)set);
+        if (stashed) atomicAdd(counters + 2, (unsigned long long)stashed);
+        if (failed) atomicAdd(counters + 3, (unsigned long long)failed);
+    }
+}
+// keys of the group's genomes that live in the engine-wide stash (S32 tables only): same merge
+__global__ void __launch_bounds__(256) union_merge_stash_kernel(PkKeySpec ks, PkTable dst, uint32_t g0, uint32_t ng, unsigned long long *counters) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= PK_STASH_SLOTS) return;
+    const unsigned long long e = ks.stash[i];
+    if (e == PK_EMPTY) return;
+    const uint32_t g = (uint32_t)(e >> 48);
+    if (g < g0 || g >= g0 + ng) return;
+    const uint64_t canon = e & 0x0000FFFFFFFFFFFFull;
+    const int r = pk_u_insert(dst, canon, pk_key_hash(canon, ks), g - g0);
+    if (r == 2 || r == 3) atomicAdd(counters, 1ull);
+    if (r >= 1 && r <= 3) atomicAdd(counters + 1, 1ull);
+    if (r == 4) atomicAdd(counters + 2, 1ull);                // stays in the stash, found there by pk_u_lookup
+}
+void pk_launch_union_merge_stash(PkKeySpec ks, PkTable dst, uint32_t g0, uint32_t ng, unsigned long long *d_counters, pk_stream_t s) {
+    union_merge_stash_kernel<<<PK_STASH_SLOTS / 256, 256, 0, s>>>(ks, dst, g0, ng, d_counters);
+}
+void pk_launch_union_merge(PkTable src, uint32_t n_src_buckets, uint32_t hshift, PkKeySpec ks, PkTable dst, uint32_t bit, uint32_t g_local,
+                           int use_stash, unsigned long long *d_counters, pk_stream_t s) {
+    if (!n_src_buckets) return;
+    const uint64_t total = (uint64_t)n_src_buckets * (ks.fmt == PK_FMT_S32 ? 8 : 4);
+    union_merge_kernel<<<grid_for(total), 256, 0, s>>>(src, n_src_buckets, hshift, ks, dst, bit, g_local, use_stash, d_counters);
+}
+
 // ------------------------------------------------------------------ probe (direct)
 // One thread per position; for each local genome one 32 B bucket load (LDG.256), U loads in
 // flight per thread. Row bits accumulate in a register and are stored once per 32 genomes.

@@ -18,6 +18,7 @@
 // repeats) go to a spill list that the same probe kernel drains with unconfined probes.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "pk_device.cuh"
@@ -198,7 +199,14 @@ struct ProbeArgs {
     const uint64_t *words;
     uint64_t p0;
     PkKeySpec ks;
-    uint32_t ng, grp;                 // genomes in this launch, column group (bytes 4*grp.. of a row)
+    uint32_t ng, grp;                 // tables in this launch, column group (bytes 4*grp.. of a row)
+    uint32_t tbits;                   // genomes per table: 1 (per-genome tables) or 8 (group tables: tabs[u] covers bits 8u..8u+7)
+    uint32_t g_first;                 // local index of the launch's first genome (stash keys)
+    uint32_t n_genomes;               // genomes covered by the launch (<= 32)
+    // window kernel: the loop runs over `ng` WINDOW PIECES; piece g is chunk c_of[g] (of chunk_buckets buckets; 0 = the
+    // whole window) of table tabs[t_of[g]]'s window — a window larger than a shared-memory stage is probed piece by piece
+    uint32_t chunk_buckets;
+    uint8_t t_of[32], c_of[32];
     uint8_t *rows;
     uint32_t row_stride, col_offset, nbl;
     int prefetch;
@@ -506,10 +514,22 @@ template <int FMT> __device__ __forceinline__ bool pw_full(const uint4 &last) {
 }
 template <int FMT> struct PwKey { typedef uint64_t type; };
 template <> struct PwKey<PK_FMT_S32> { typedef uint32_t type; };      // S32 compares 32-bit slots: keep 32 bits per item
+// group tables (pk_device.cuh): slot = [mask 8][key 56]; membership mask of key56 in a bucket read as two halves
+#define PK_FMT_GROUP 2
+template <> struct PwKey<PK_FMT_GROUP> { typedef uint64_t type; };
+__device__ __forceinline__ uint32_t pw_umask(const uint4 &A, const uint4 &B, uint64_t key56) {
+    const uint32_t lo = (uint32_t)key56, hi = (uint32_t)(key56 >> 32);
+    uint32_t m = 0;
+    if (A.x == lo && (A.y & 0x00FFFFFFu) == hi) m |= A.y >> 24;
+    if (A.z == lo && (A.w & 0x00FFFFFFu) == hi) m |= A.w >> 24;
+    if (B.x == lo && (B.y & 0x00FFFFFFu) == hi) m |= B.y >> 24;
+    if (B.z == lo && (B.w & 0x00FFFFFFu) == hi) m |= B.w >> 24;
+    return m;
+}
 
-template <int T, int IPT, int FMT, int MINB>
+template <int T, int IPT, int FMT, int MINB, int CHUNKED>
 __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constant__ ProbeArgs a, const uint32_t stage_bytes,
-                                                            const uint32_t gsz) {
+                                                            const uint32_t gsz, const uint32_t n_stages) {
     constexpr int CAP = T * IPT;
     typedef typename PwKey<FMT>::type key_t;
     extern __shared__ __align__(128) uint8_t s_win[];          // [2 * gsz][stage_bytes]
@@ -521,7 +541,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
     __shared__ uint16_t o_wc[T / 32][PP_OBINS];
     __shared__ uint32_t o_gb[PP_OBINS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t n_stages = 2 * gsz;
+    constexpr bool GRP = FMT == PK_FMT_GROUP;       // group tables: a probe returns an 8-bit membership mask
     const uint32_t win0 = pw_smem(s_win), bar0 = pw_smem(s_bar);
     const uint32_t xoff = (lane & 1) * 16;          // odd lanes read the bucket halves in the other order: spreads the banks
     // thread s initialises the mbarrier of stage s and issues the first copy into it straight away (other threads
@@ -538,14 +558,22 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
         const uint32_t h_lo = (uint32_t)(q << (32 - a.pb));
         const uint32_t h_hi = (uint32_t)(((q + 1) << (32 - a.pb)) - 1);
         // window of genome g = buckets [b0, b1] of its table; streamed into stage g % n_stages when it fits
-        auto issue = [&](uint32_t g) {
-            const PkTable t = a.tabs[g];
+        // piece g -> its table and its bucket range [cs, ce) inside this partition's window of that table
+        auto geom = [&](uint32_t g, uint32_t &cs, uint32_t &ce) -> PkTable {
+            const PkTable t = a.tabs[GRP ? a.t_of[g] : g];
             const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
-            const uint32_t bytes = (b1 - b0 + 1) * 32;
-            if (bytes <= stage_bytes) {
+            if constexpr (!CHUNKED) { cs = b0; ce = b1 + 1; }
+            else { cs = min(b0 + a.c_of[g] * a.chunk_buckets, b1 + 1); ce = min(cs + a.chunk_buckets, b1 + 1); }
+            return t;
+        };
+        auto issue = [&](uint32_t g) {
+            uint32_t cs, ce;
+            const PkTable t = geom(g, cs, ce);
+            const uint32_t bytes = (ce - cs) * 32;
+            if (bytes && bytes <= stage_bytes) {
                 const uint32_t s = g & (n_stages - 1);
                 pw_mbar_expect_tx(bar0 + 8 * s, bytes);
-                pw_bulk_g2s(win0 + s * stage_bytes, t.slots + 4ull * b0, bytes, bar0 + 8 * s);
+                pw_bulk_g2s(win0 + s * stage_bytes, t.slots + 4ull * cs, bytes, bar0 + 8 * s);
             }
         };
         if (tid < n_stages && tid < a.ng) issue(tid);
@@ -561,9 +589,22 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < IPT; j++) {
             key[j] = 0; h[j] = it[j].x; pos[j] = it[j].y; bits[j] = 0;
-            if (tid + j * T < cnt) key[j] = (key_t)pk_target<FMT>(pk_canon_at(a.words, a.p0 + it[j].y, a.ks.k), 0);
+            if (tid + j * T < cnt) {
+                const uint64_t canon = pk_canon_at(a.words, a.p0 + it[j].y, a.ks.k);
+                if constexpr (GRP) key[j] = pk_u_key(canon, 0);
+                else key[j] = (key_t)pk_target<GRP ? PK_FMT_S64 : FMT>(canon, 0);
+            }
         }
         __syncthreads();
+        // the whole answer of table g for one k-mer through global memory, as row bits of this launch
+        auto full_lookup = [&](const PkTable &t, uint64_t canon, uint32_t hh, uint32_t g) -> uint32_t {
+            if constexpr (GRP) {
+                const uint32_t ngg = min(PK_U_GROUP, a.n_genomes - PK_U_GROUP * g);
+                return pk_u_lookup(t, canon, hh, a.g_first + PK_U_GROUP * g, ngg, a.ks) << (PK_U_GROUP * g);
+            } else {
+                return (uint32_t)pk_lookup<GRP ? PK_FMT_S64 : FMT>(t, canon, hh, a.g_first + g, a.ks) << g;
+            }
+        };
         // ---- probe, group by group, out of the staged windows
         uint32_t grp_i = 0;
         for (uint32_t g0 = 0; g0 < a.ng; g0 += gsz, grp_i++) {
@@ -574,31 +615,40 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
                 const uint32_t slot = atomicAdd(qn, 1u);
                 if (slot < (uint32_t)PW_QCAP) {
                     q_key[slot] = key[j]; q_pos[slot] = pos[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
-                } else if (pk_lookup<FMT>(t, pk_canon_at(a.words, a.p0 + pos[j], a.ks.k), h[j], 32 * a.grp + g, a.ks)) {
-                    bits[j] |= 1u << g;     // queue full (pathological)
+                } else {                    // queue full (pathological)
+                    bits[j] |= full_lookup(t, pk_canon_at(a.words, a.p0 + pos[j], a.ks.k), h[j], GRP ? a.t_of[g] : g);
                 }
             };
             for (uint32_t g = g0; g < g1; g++) {
-                const PkTable t = a.tabs[g];
+                uint32_t cs, ce;
+                const PkTable t = geom(g, cs, ce);
                 const uint32_t s = g & (n_stages - 1);
-                const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
-                const uint32_t gbit = 1u << g;
-                if ((b1 - b0 + 1) * 32 <= stage_bytes) {
+                const uint32_t gbit = 1u << g, gsh = GRP ? PK_U_GROUP * a.t_of[g] : 0;
+                (void)gbit; (void)gsh;
+                if (CHUNKED && ce == cs) continue;                    // empty piece (short window): nothing was copied
+                if ((ce - cs) * 32 <= stage_bytes) {
                     pw_mbar_wait(bar0 + 8 * s, (par >> s) & 1);
                     par ^= 1u << s;
                     // + 32 * bucket = the bucket's first (even lanes) / second (odd lanes) half; kept opaque so that it
                     // stays in a register instead of being re-derived per item
-                    uint32_t wbase = win0 + s * stage_bytes - b0 * 32 + xoff, nb = t.n_buckets;
-                    asm volatile("" : "+r"(wbase), "+r"(nb));
+                    uint32_t wbase = win0 + s * stage_bytes - cs * 32 + xoff, nb = t.n_buckets, nbp = ce - cs;
+                    asm volatile("" : "+r"(wbase), "+r"(nb), "+r"(nbp));
 #pragma unroll
                     for (int j = 0; j < IPT; j++) {
                         const uint32_t i = tid + j * T;
-                        if (i < cnt) {
-                            const uint32_t wa = wbase + __umulhi(h[j], nb) * 32;
+                        const uint32_t b = __umulhi(h[j], nb);
+                        if (i < cnt && (!CHUNKED || b - cs < nbp)) {  // the item's home bucket lies in this piece
+                            const uint32_t wa = wbase + b * 32;
                             const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
-                            const bool hit = pw_hit<FMT>(A, B, key[j]);
-                            if (hit) bits[j] |= gbit;
-                            else if (pw_full<FMT>(xoff ? A : B)) defer(j, i, g, t);
+                            if constexpr (GRP) {
+                                const uint32_t m = pw_umask(A, B, key[j]);
+                                if (m) bits[j] |= m << gsh;
+                                else if (pw_full<PK_FMT_S64>(xoff ? A : B)) defer(j, i, g, t);
+                            } else {
+                                const bool hit = pw_hit<GRP ? PK_FMT_S64 : FMT>(A, B, key[j]);
+                                if (hit) bits[j] |= gbit;
+                                else if (pw_full<GRP ? PK_FMT_S64 : FMT>(xoff ? A : B)) defer(j, i, g, t);
+                            }
                         }
                     }
                 } else {
@@ -607,8 +657,14 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
                         const uint32_t i = tid + j * T;
                         if (i < cnt) {
                             const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
-                            if (pk_bucket_hit<FMT>(v, key[j])) bits[j] |= gbit;
-                            else if (pk_bucket_full<FMT>(v)) defer(j, i, g, t);
+                            if constexpr (GRP) {
+                                const uint32_t m = pk_u_bucket_mask(v, key[j]);
+                                if (m) bits[j] |= m << gsh;
+                                else if (v.d != PK_EMPTY) defer(j, i, g, t);
+                            } else {
+                                if (pk_bucket_hit<GRP ? PK_FMT_S64 : FMT>(v, key[j])) bits[j] |= gbit;
+                                else if (pk_bucket_full<GRP ? PK_FMT_S64 : FMT>(v)) defer(j, i, g, t);
+                            }
                         }
                     }
                 }
@@ -617,26 +673,33 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
             {   // drain the queue: walk on through the staged window, bucket by bucket
                 const uint32_t nq = min(*qn, (uint32_t)PW_QCAP);
                 for (uint32_t e = tid; e < nq; e += T) {
-                    const uint32_t meta = q_meta[e], g = meta & 31, hh = q_h[e];
+                    const uint32_t meta = q_meta[e], g = meta & 31, hh = q_h[e], u = GRP ? a.t_of[g] : g;
                     const key_t kk = q_key[e];
-                    const PkTable t = a.tabs[g];
-                    const uint32_t b0 = __umulhi(h_lo, t.n_buckets), b1 = __umulhi(h_hi, t.n_buckets);
-                    const uint32_t nbk = b1 - b0 + 1, off = __umulhi(hh, t.n_buckets) - b0;
-                    const uint32_t maxd = pk_max_disp<FMT>(t.n_buckets);
-                    int res = 2;            // 0 absent, 1 present, 2 undecided: leave the window -> global lookup
+                    uint32_t cs, ce;
+                    const PkTable t = geom(g, cs, ce);
+                    const uint32_t nbk = ce - cs, off = __umulhi(hh, t.n_buckets) - cs;
+                    const uint32_t maxd = GRP ? pk_u_max_disp(t.n_buckets) : pk_max_disp<GRP ? PK_FMT_S64 : FMT>(t.n_buckets);
+                    uint32_t found = 0;     // row bits of this launch the k-mer gets from table g
+                    bool decided = false;   // false: leave the window -> global lookup
                     if (nbk * 32 <= stage_bytes) {
                         const uint32_t wb = win0 + (g & (n_stages - 1)) * stage_bytes + xoff;
                         for (uint32_t r = 1; r <= maxd && off + r < nbk; r++) {
                             const uint32_t wa = wb + (off + r) * 32;
                             const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
-                            // S32: the slot value at displacement r is the home value + r; S64: the k-mer itself
-                            if (pw_hit<FMT>(A, B, FMT == PK_FMT_S32 ? (uint64_t)kk + r : (uint64_t)kk)) { res = 1; break; }
-                            if (!pw_full<FMT>(xoff ? A : B)) { res = 0; break; }
+                            // S32 / group: the slot value at displacement r is the home value + r; S64: the k-mer itself
+                            if constexpr (GRP) {
+                                const uint32_t m = pw_umask(A, B, (uint64_t)kk + r);
+                                if (m) { found = m << (PK_U_GROUP * u); decided = true; break; }
+                                if (!pw_full<PK_FMT_S64>(xoff ? A : B)) { decided = true; break; }
+                            } else {
+                                if (pw_hit<GRP ? PK_FMT_S64 : FMT>(A, B, FMT == PK_FMT_S32 ? (uint64_t)kk + r : (uint64_t)kk)) { found = 1u << u; decided = true; break; }
+                                if (!pw_full<GRP ? PK_FMT_S64 : FMT>(xoff ? A : B)) { decided = true; break; }
+                            }
                         }
                     }
-                    if (res == 2)       // rare: past the window's end, > 14 full buckets in a row (stash), or no window
-                        res = pk_lookup<FMT>(t, pk_canon_at(a.words, a.p0 + q_pos[e], a.ks.k), hh, 32 * a.grp + g, a.ks) ? 1 : 0;
-                    if (res) atomicOr(&s_bits[meta >> 5], 1u << g);
+                    if (!decided)       // rare: past the window's end, > 14 full buckets in a row (stash), or no window
+                        found = full_lookup(t, pk_canon_at(a.words, a.p0 + q_pos[e], a.ks.k), hh, u);
+                    if (found) atomicOr(&s_bits[meta >> 5], found);
                 }
             }
             __syncthreads();            // the group's windows and the queue are free again
@@ -724,15 +787,19 @@ static const K3Variant &k3_pick(uint32_t n_genomes_in_launch) {
     return k3_variants[n_genomes_in_launch >= 16 ? 1 : 0];
 }
 
-// window (TMA-staged) variants of K3; same block capacity as variants 0/1, so the partition plan is shared
-struct K3WinVariant { int threads, cap; void (*fn[2])(ProbeArgs, uint32_t, uint32_t); };
-#define K3W(T, IPT, MINB) {T, T * IPT, {probe_win_kernel<T, IPT, PK_FMT_S64, MINB>, probe_win_kernel<T, IPT, PK_FMT_S32, MINB>}}
+// window (TMA-staged) variants of K3; same block capacity as variants 0/1, so the partition plan is shared.
+// fn[0] / fn[1]: per-genome S64 / S32 tables, fn[2] / fn[3]: group tables, whole windows / windows in pieces
+struct K3WinVariant { int threads, cap; void (*fn[4])(ProbeArgs, uint32_t, uint32_t, uint32_t); };
+#define K3W(T, IPT, MINB) {T, T * IPT, {probe_win_kernel<T, IPT, PK_FMT_S64, MINB, 0>, probe_win_kernel<T, IPT, PK_FMT_S32, MINB, 0>, \
+                                        probe_win_kernel<T, IPT, PK_FMT_GROUP, MINB, 0>, probe_win_kernel<T, IPT, PK_FMT_GROUP, MINB, 1>}}
 static const K3WinVariant k3w_variants[] = {
     K3W(256, 3, 4),      // 0: <= 64 registers
     K3W(256, 3, 5),      // 1: <= 48 registers
     K3W(256, 3, 3),      // 2: <= 80 registers
     K3W(256, 3, 6),      // 3: <= 40 registers
 };
+#define PW_MAX_GROUP_STAGE_BYTES 32768u
+#define PW_GROUP_STAGE_TARGET 24576u          // pieces of a group-table window are at most this large
 static int g_k3_window = 1;          // 0: never use the window kernels
 static int g_k3_last_window = 0;     // did the last K3 launch use a window kernel?
 int pk_part_last_window(void) { return g_k3_last_window; }
@@ -743,19 +810,22 @@ void pk_part_set_window(int enable, int variant, int stages) {
     if (variant >= -1 && variant < (int)(sizeof k3w_variants / sizeof k3w_variants[0])) g_k3w_variant = variant;
     if (stages == 0 || stages == 1 || stages == 2 || stages == 4) g_k3w_group = stages;      // 2 * group stages: a power of two
 }
-static const K3WinVariant &k3w_pick(uint32_t n_genomes_in_launch) {
+// auto: per-genome tables 6 blocks/SM (profiles/r1e_sweep.json: 5.14 vs 5.32 ms), group tables 4 blocks/SM with up to
+// 64 registers (profiles/r1l_sweep.json: 2.29 vs 3.62 ms — one 20 KB window per block, the probe loop is short and
+// the item registers matter more than occupancy)
+static const K3WinVariant &k3w_pick(uint32_t n_genomes_in_launch, bool group_tables = false) {
     (void)n_genomes_in_launch;
-    return k3w_variants[g_k3w_variant >= 0 ? g_k3w_variant : 3];      // 6 blocks/SM: profiles/r1e_sweep.json
+    return k3w_variants[g_k3w_variant >= 0 ? g_k3w_variant : (group_tables ? 0 : 3)];
 }
 // bytes one stage must hold for every table of the launch, or 0 when some window does not fit a stage
-static uint32_t k3w_stage_bytes(const PkTable *tabs, uint32_t ng, uint32_t pb) {
+static uint32_t k3w_stage_bytes(const PkTable *tabs, uint32_t ng, uint32_t pb, uint32_t limit) {
     uint64_t mx = 0;
     for (uint32_t g = 0; g < ng; g++) {
         const uint64_t nbk = ((uint64_t)tabs[g].n_buckets >> pb) + 2;       // b1 - b0 + 1 <= ceil(nb / 2^pb) + 1
         mx = nbk > mx ? nbk : mx;
     }
     const uint64_t bytes = (mx * 32 + 127) & ~127ull;
-    return bytes <= PW_MAX_STAGE_BYTES ? (uint32_t)bytes : 0;
+    return bytes <= limit ? (uint32_t)bytes : 0;
 }
 
 // K4: scatter the (pos, bits) lists into rows. All blocks of one bin write inside a slice of
@@ -841,7 +911,7 @@ void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0
 
 // K2 + K3 (+ spill drain) over everything appended so far
 void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, const PkTable *h_tables,
-                   uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                   const PkTable *h_utables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
                    const PkPartScratch &sc, int prefetch, pk_stream_t s, cudaEvent_t *evs) {
     const int fi = ks.fmt == PK_FMT_S32 ? 1 : 0;
     const uint32_t n_groups = (n_local + 31) / 32;
@@ -864,10 +934,46 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     p.out_shift = pl.out_shift;
     if (evs) cudaEventRecord(evs[2], s);
     for (uint32_t grp = 0; grp < n_groups; grp++) {       // one launch per group of 32 genomes
-        p.grp = grp; p.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
+        const uint32_t ngen = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
+        p.grp = grp; p.g_first = 32 * grp; p.n_genomes = ngen;
+        g_k3_last_window = 0;
+        if (g_k3_window && h_utables && k3_pick(ngen).cap == k3w_pick(ngen).cap) {
+            // group tables: one probe per 8 genomes; the launch walks the (<= 4) group tables of its 32 genomes. A
+            // window larger than PW_GROUP_STAGE_TARGET is cut into equal pieces that pass through the stages one
+            // after the other (every item probes the piece its home bucket lies in).
+            const uint32_t nt = (ngen + PK_U_GROUP - 1) / PK_U_GROUP;
+            uint64_t maxw = 0, win[4];
+            for (uint32_t u = 0; u < nt; u++) {
+                p.tabs[u] = h_utables[4 * grp + u];
+                win[u] = ((uint64_t)p.tabs[u].n_buckets >> p.pb) + 2;          // buckets, upper bound
+                maxw = std::max(maxw, win[u]);
+            }
+            const uint64_t target = PW_GROUP_STAGE_TARGET / 32;
+            const uint64_t nch = (maxw + target - 1) / target;
+            const uint64_t cb = ((maxw + nch - 1) / nch + 3) & ~3ull;          // buckets per piece, a multiple of 128 bytes
+            uint32_t np = 0;
+            bool ok = cb * 32 <= PW_MAX_GROUP_STAGE_BYTES;
+            for (uint32_t u = 0; u < nt && ok; u++)
+                for (uint64_t c = 0; c * cb < win[u]; c++) {
+                    if (np == 32) { ok = false; break; }
+                    p.t_of[np] = (uint8_t)u; p.c_of[np] = (uint8_t)c; np++;
+                }
+            if (ok && np) {
+                const K3WinVariant &wv = k3w_pick(ngen, true);
+                const uint32_t stage_bytes = (uint32_t)cb * 32, n_stages = np == 1 ? 1 : 2;
+                p.ng = np; p.tbits = PK_U_GROUP; p.chunk_buckets = nch > 1 ? (uint32_t)cb : 0;
+                const int fk = nch > 1 ? 3 : 2;
+                cudaFuncSetAttribute(wv.fn[fk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
+                wv.fn[fk]<<<p.n_regions, wv.threads, (size_t)n_stages * stage_bytes, s>>>(p, stage_bytes, 1, n_stages);
+                g_k3_last_window = 2;
+                continue;
+            }
+        }
+        p.chunk_buckets = 0;
+        for (uint32_t g = 0; g < 32; g++) { p.t_of[g] = (uint8_t)g; p.c_of[g] = 0; }
+        p.ng = ngen; p.tbits = 1;
         for (uint32_t g = 0; g < p.ng; g++) p.tabs[g] = h_tables[32 * grp + g];
-        const uint32_t stage_bytes = g_k3_window && k3_pick(p.ng).cap == k3w_pick(p.ng).cap ? k3w_stage_bytes(p.tabs, p.ng, p.pb) : 0;
-        g_k3_last_window = stage_bytes != 0;
+        const uint32_t stage_bytes = g_k3_window && k3_pick(p.ng).cap == k3w_pick(p.ng).cap ? k3w_stage_bytes(p.tabs, p.ng, p.pb, PW_MAX_STAGE_BYTES) : 0;
         if (stage_bytes) {
             const K3WinVariant &wv = k3w_pick(p.ng);
             // two genomes per group while four windows stay under ~24 KB (6 blocks/SM), else one: measured on
@@ -875,7 +981,8 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
             const uint32_t gsz = g_k3w_group ? g_k3w_group : (4 * stage_bytes <= 24576 ? 2 : 1);
             const size_t dyn = (size_t)2 * gsz * stage_bytes;
             cudaFuncSetAttribute(wv.fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
-            wv.fn[fi]<<<p.n_regions, wv.threads, dyn, s>>>(p, stage_bytes, gsz);
+            wv.fn[fi]<<<p.n_regions, wv.threads, dyn, s>>>(p, stage_bytes, gsz, 2 * gsz);
+            g_k3_last_window = 1;
         } else {
             const K3Variant &kv = k3_pick(p.ng);
             kv.fn[fi]<<<p.n_regions, kv.threads, 0, s>>>(p);
@@ -886,6 +993,7 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = k3_pick(1).cap; sp.pb = 0;
     for (uint32_t grp = 0; grp < n_groups; grp++) {
         sp.grp = grp; sp.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
+        sp.tbits = 1; sp.g_first = 32 * grp; sp.n_genomes = sp.ng;
         for (uint32_t g = 0; g < sp.ng; g++) sp.tabs[g] = h_tables[32 * grp + g];
         const K3Variant &kv = k3_pick(sp.ng);
         kv.fn[fi]<<<148 * 2, kv.threads, 0, s>>>(sp);
@@ -903,7 +1011,7 @@ void pk_part_unpermute(uint32_t bin0, uint32_t bin1, uint32_t n_local, uint8_t *
 }
 
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
-                                const PkTable *d_tables, const PkTable *h_tables, uint32_t n_local, uint8_t *d_rows,
+                                const PkTable *d_tables, const PkTable *h_tables, const PkTable *h_utables, uint32_t n_local, uint8_t *d_rows,
                                 uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
                                 int prefetch, pk_stream_t s, cudaEvent_t *evs) {
     if (!n) return 0;
@@ -912,7 +1020,7 @@ int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask,
     if (evs) cudaEventRecord(evs[0], s);
     pk_part_append(d_words, d_mask, p0, 0, n, ks, n_local, d_rows, row_stride, col_offset, pl, sc, s);
     if (evs) cudaEventRecord(evs[1], s);
-    pk_part_probe(d_words, d_mask, p0, ks, h_tables, n_local, d_rows, row_stride, col_offset, pl, sc, prefetch, s, evs);
+    pk_part_probe(d_words, d_mask, p0, ks, h_tables, h_utables, n_local, d_rows, row_stride, col_offset, pl, sc, prefetch, s, evs);
     pk_part_unpermute(0, pl.out_bins, n_local, d_rows, row_stride, col_offset, pl, sc, s);
     if (evs) cudaEventRecord(evs[5], s);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -96,6 +96,14 @@ class Engine:
         check(self._L.pk_engine_table_stats(self._h, genome, C.byref(s)))
         return {f: getattr(s, f) for f, _ in s._fields_}
 
+    def group_stats(self, group: int) -> dict | None:
+        """The group table of local genomes [8*group, 8*group+8) (pk_engine_group_stats); None when group tables
+        are off or were not built."""
+        s = PkTableStats()
+        if self._L.pk_engine_group_stats(self._h, group, C.byref(s)) != 0:
+            return None
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
     # ---- hot path, host buffers --------------------------------------------
     def bin_len(self, nkmers: int) -> int:
         return int(self._L.pk_bin_len(C.byref(self.cfg), nkmers))

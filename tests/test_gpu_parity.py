@@ -364,6 +364,10 @@ def test_partitioned_path_large_vs_oracle_and_direct(n_genomes, k, repeats, load
         dbs.append(oracle.OracleDB.from_kmers(k, allk[keep], cnt[keep]))
     for g in range(n_genomes):
         assert engs["partitioned"].table_stats(g)["n_keys"] == kk[g].size
+    # group tables (8 genomes per table, built at finalize): exactly the distinct k-mers of each group
+    for u in range((n_genomes + 7) // 8):
+        gs = engs["partitioned"].group_stats(u)
+        assert gs is not None and gs["n_keys"] == np.unique(np.concatenate([kk[g] for g in range(8 * u, min(8 * u + 8, n_genomes))])).size
     want = oracle.anchor_chrom(dbs, n_genomes, anchor_seqs[0].tobytes())
     assert (rp["chroms"][0]["bitmap1"] == want["bitmap1"]).all()
     assert (rp["chroms"][0]["bin_hist"] == want["bin_hist"]).all()
@@ -394,6 +398,19 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
             for a, b in zip(got["chroms"], want["chroms"]):
                 assert (a["bitmap1"] == b["bitmap1"]).all(), knobs
                 assert (a["bin_hist"] == b["bin_hist"]).all(), knobs
+        # per-genome tables only (one probe per genome) vs group tables (one probe per 8 genomes)
+        eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1, group_tables=0)
+        eng.finalize()
+        assert eng.group_stats(0) is None
+        for knobs in (dict(k3_window=1), dict(k3_window=0)):
+            eng.tune(**knobs)
+            got = eng.anchor_genome(seqs)
+            assert (got["col_sums"] == want["col_sums"]).all(), knobs
+            for a, b in zip(got["chroms"], want["chroms"]):
+                assert (a["bitmap1"] == b["bitmap1"]).all() and (a["bin_hist"] == b["bin_hist"]).all(), knobs
+        eng.tune(k3_window=1, group_tables=1)
+        eng.finalize()
+        assert eng.group_stats(0)["n_keys"] >= max(eng.table_stats(g)["n_keys"] for g in range(min(8, n_genomes)))
         # the same genome as 2 and 3 batches of whole chromosomes (copies of one batch under the kernels of the other)
         eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1, e2e_batch_min=0)
         for nb in (2, 3, 8):
