@@ -477,7 +477,8 @@ def main():
         stage_ms = statistics.median(step_ms)
         traffic = None
         try:
-            tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(args.workload)
+            key = args.workload if int(ks.get("k_probe_window", 0)) == 2 else args.workload + "_per_genome_tables"
+            tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(key)
             if tj and world == 1 and ks["k_probe_ms"] > 0:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
@@ -487,6 +488,11 @@ def main():
                 "achieved": alg_bytes / (k3_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (k3_ms / 1e3) / 1e9 / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k3_ms,
+                # the same kernel against the bytes it really moves (ncu dram__bytes of one launch / its live duration):
+                # `frac` above charges 32 B per (position, genome) as SURVEY §8d defines; a group table answers 8
+                # genomes per sector, so that figure exceeds 1 while this one says how close the kernel is to the pins
+                "physical": ({"dram_bytes_per_launch": traffic, "achieved": traffic / (k3_ms / 1e3) / 1e9, "unit": "GB/s",
+                              "frac": traffic / (k3_ms / 1e3) / 1e9 / hbm_peak} if traffic else None),
                 "stage": {"what": "all kernels of the probe stage (partition_seq + partition_fine + probe_part + spill + unpermute)",
                           "ms": stage_ms, "achieved": alg_bytes / (stage_ms / 1e3) / 1e9,
                           "frac": alg_bytes / (stage_ms / 1e3) / 1e9 / hbm_peak,

@@ -61,6 +61,20 @@ int pk_kmcdb_open(const char *prefix, pk_kmcdb **out);
 int pk_kmcdb_info_get(const pk_kmcdb *db, pk_kmcdb_info *info);
 void pk_kmcdb_close(pk_kmcdb *db);
 
+/* ---- FASTA reader ---------------------------------------------------------
+ * Replaces the getline loop of KMCdb::anchor_fasta (cpp/anchor.cpp:74-100) / Genome.iter_fasta
+ * (panagram/index.py:922-930) in front of the engine. Host only. Record name = header up to the first ' '
+ * (cpp/anchor.cpp:84,97); sequence = the lines concatenated verbatim ('\r' stays, as with getline). strip_cr != 0
+ * applies what `kmc -fm` / Biopython see instead: a trailing '\r' is cut from every line, bytes < 32 are dropped
+ * from the sequence, the name is the header's first whitespace-separated token. Sequences live in page-locked
+ * memory (plain memory when no CUDA driver is present) owned by the handle; pointers stay valid until
+ * pk_fasta_close. Plain-text files only (gzip: PK_EUNSUPPORTED). */
+typedef struct pk_fasta pk_fasta;
+int pk_fasta_open(const char *path, int strip_cr, pk_fasta **out);
+uint32_t pk_fasta_n_records(const pk_fasta *fa);
+int pk_fasta_record(const pk_fasta *fa, uint32_t i, const char **name, const uint8_t **seq, uint64_t *len);
+void pk_fasta_close(pk_fasta *fa);
+
 /* ---- engine ---------------------------------------------------------------
  * Replaces KMCdb::KMCdb (cpp/anchor.cpp:21-35) / Genome._load_kmc
  * (panagram/index.py:847-863): instead of ceil(N/32) merged "bitvec" databases

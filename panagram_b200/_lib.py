@@ -63,6 +63,10 @@ SIGNATURES = {
     "pk_kmcdb_open": (C.c_int, [_cp, _pp]),
     "pk_kmcdb_info_get": (C.c_int, [_vp, C.POINTER(PkKmcdbInfo)]),
     "pk_kmcdb_close": (None, [_vp]),
+    "pk_fasta_open": (C.c_int, [_cp, C.c_int, _pp]),
+    "pk_fasta_n_records": (_u32, [_vp]),
+    "pk_fasta_record": (C.c_int, [_vp, _u32, C.POINTER(_cp), _pp, _pu64]),
+    "pk_fasta_close": (None, [_vp]),
     "pk_engine_create": (C.c_int, [C.POINTER(PkConfig), _pp]),
     "pk_engine_destroy": (None, [_vp]),
     "pk_engine_reserve": (C.c_int, [_vp, _u32, _u64]),

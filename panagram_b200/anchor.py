@@ -18,6 +18,39 @@ from .engine import Engine
 
 
 def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
+    """[(name, uint8 sequence)]: the native reader (pk_fasta_open: one memchr pass into page-locked memory) for
+    plain files, `parse_fasta_numpy` for gzip input. Same rules, same result (tests/test_host.py)."""
+    import ctypes as C
+    import weakref
+    from . import _lib
+    path = str(path)
+    if path.endswith(".gz") or path.endswith(".bgz"):
+        return parse_fasta_numpy(path, strip_cr)
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.pk_fasta_open(path.encode(), int(bool(strip_cr)), C.byref(h))
+    if rc == -5:                                    # PK_EUNSUPPORTED: gzip magic without a .gz suffix
+        return parse_fasta_numpy(path, strip_cr)
+    _lib.check(rc)
+    n = L.pk_fasta_n_records(h)
+    recs, base, total = [], None, 0
+    for i in range(n):
+        name, seq, ln = C.c_char_p(), C.c_void_p(), C.c_uint64()
+        _lib.check(L.pk_fasta_record(h, i, C.byref(name), C.byref(seq), C.byref(ln)))
+        if base is None:
+            base = seq.value or 0
+        recs.append((name.value.decode(errors="replace"), (seq.value or 0) - base, ln.value))
+        total = max(total, (seq.value or 0) - base + ln.value)
+    if not recs or not base:
+        L.pk_fasta_close(h)
+        return [(nm, np.zeros(0, dtype=np.uint8)) for nm, _, _ in recs]
+    buf = (C.c_uint8 * max(total, 1)).from_address(base)
+    weakref.finalize(buf, L.pk_fasta_close, h)      # the arrays below keep `buf` (hence the handle) alive
+    whole = np.frombuffer(buf, dtype=np.uint8)
+    return [(nm, whole[o:o + ln]) for nm, o, ln in recs]
+
+
+def parse_fasta_numpy(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
     """[(name, uint8 sequence)] with the C++ reference's rules (cpp/anchor.cpp:74-100):
     the record name is the header up to the first space, sequence lines are
     concatenated verbatim (a trailing \\r stays in the sequence unless strip_cr,
@@ -25,11 +58,9 @@ def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
     (kmc_core/splitter.cpp: "c < 32 // newliners") and Biopython strips line ends,
     index.py:922-930). gzip-aware like Genome.iter_fasta."""
     path = str(path)
-    if path.endswith(".gz") or path.endswith(".bgz"):
-        with gzip.open(path, "rb") as fh:
-            raw = fh.read()
-    else:
-        raw = Path(path).read_bytes()
+    raw = Path(path).read_bytes()
+    if path.endswith(".gz") or path.endswith(".bgz") or raw[:2] == b"\x1f\x8b":
+        raw = gzip.decompress(raw)
     buf = np.frombuffer(raw, dtype=np.uint8)
     nl = np.flatnonzero(buf == 10)
     starts = np.concatenate(([0], nl + 1))

@@ -107,3 +107,39 @@ def test_index_prepare_writes_reference_config_files(pan3, tmp_path):
     bad.write_text("name\tfasta\nbad name!\tx.fa\n")
     with pytest.raises(ValueError):
         main(["index", str(bad), "--prepare"])
+
+
+def test_native_fasta_reader_equals_the_numpy_parser(tmp_path, pan3):
+    """pk_fasta_open (csrc/pk_fasta.cpp) follows the same rules as anchor.parse_fasta_numpy — the C++ reference's
+    (cpp/anchor.cpp:74-100: name to the first space, lines verbatim) and, with strip_cr, kmc's/Biopython's."""
+    from panagram_b200 import anchor
+    cases = {
+        "plain": b">chr1 desc here\nACGT\nNNAC\n>chr2\nacgtn\n",
+        "crlf": b">chr1 x\r\nACGT\r\nAC\rGT\r\n>c2\r\nTT\r\n",
+        "no_trailing_newline": b">a\nACGT\n>b\nGG",
+        "leading_garbage_and_blank_lines": b"junk\n\n>a\n\nAC\n\nGT\n>b\n",
+        "header_only_and_empty_name": b">\nACGT\n> spaced\nTT\n>\tTabbed name\nGG\n",
+        "control_bytes": b">a\nAC\x01GT\x0bTT\n>b\tx y\nA\tC\n",
+        "empty": b"",
+        "no_records": b"ACGT\nACGT\n",
+        "gt_inside_line": b">a\nAC>GT\n>b\nTT\n",
+    }
+    for label, data in cases.items():
+        p = tmp_path / f"{label}.fa"
+        p.write_bytes(data)
+        for strip in (False, True):
+            got = anchor.parse_fasta(p, strip_cr=strip)
+            want = anchor.parse_fasta_numpy(p, strip_cr=strip)
+            assert [n for n, _ in got] == [n for n, _ in want], (label, strip)
+            assert [s.tobytes() for _, s in got] == [s.tobytes() for _, s in want], (label, strip)
+    for name, path in pan3["fasta"].items():          # the golden fixtures (CRLF, IUPAC, lowercase, N runs)
+        for strip in (False, True):
+            got, want = anchor.parse_fasta(path, strip_cr=strip), anchor.parse_fasta_numpy(path, strip_cr=strip)
+            assert [(n, s.tobytes()) for n, s in got] == [(n, s.tobytes()) for n, s in want]
+    import gzip
+    gz = tmp_path / "x.fa.gz"
+    gz.write_bytes(gzip.compress(cases["plain"]))
+    assert [(n, s.tobytes()) for n, s in anchor.parse_fasta(gz)] == [("chr1", b"ACGTNNAC"), ("chr2", b"acgtn")]
+    disguised = tmp_path / "y.fa"                      # gzip magic without the suffix: handed to the numpy path
+    disguised.write_bytes(gzip.compress(cases["plain"]))
+    assert [(n, s.tobytes()) for n, s in anchor.parse_fasta(disguised)] == [("chr1", b"ACGTNNAC"), ("chr2", b"acgtn")]
