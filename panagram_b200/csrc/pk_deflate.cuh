@@ -113,33 +113,8 @@ PKZ_FN PkzDist pkz_dist(uint32_t d) {
     return r;
 }
 
-// bit j of the result = (blk[base + j] == blk[base + j - dist]) for j < n (n <= 32), 0 where base + j < dist
-PKZ_FN uint32_t pkz_eqmask(const uint8_t *blk, uint32_t base, uint32_t n, uint32_t dist) {
-    uint32_t m = 0;
-#ifdef __CUDACC__
-#pragma unroll 8
-#endif
-    for (uint32_t j = 0; j < n; j++) {
-        const uint32_t i = base + j;
-        m |= (uint32_t)(i >= dist && blk[i] == blk[i - dist]) << j;
-    }
-    return m;
-}
-PKZ_FN uint32_t pkz_ctz(uint32_t v) {          // trailing zero bits, v != 0
-#ifdef __CUDA_ARCH__
-    return __ffs((int)v) - 1;
-#else
-    uint32_t r = 0;
-    while (!(v & 1)) { v >>= 1; r++; }
-    return r;
-#endif
-}
-
 // Deflate bytes [s, e) of the member payload `blk` (history = blk[0, s)) into `out` as one byte-aligned
-// piece. Returns the piece length (<= PKZ_STAGE - 4 for e - s <= PKZ_SUB). Greedy: at every position the run of
-// bytes equal to the byte `dist` before them; >= 3 -> one match (<= 258), else a literal. The "equal to the byte
-// dist before" bits are computed once per position, 32 at a time, and runs are measured on the bit masks (the first
-// version compared byte by byte from every position: 119 thread-instructions per input byte on the GPU).
+// piece. Returns the piece length (<= PKZ_STAGE for e - s <= PKZ_SUB).
 PKZ_FN uint32_t pkz_encode_piece(const uint8_t *blk, uint32_t s, uint32_t e, uint32_t dist, bool final, uint8_t *out) {
     PkzBits w;
     w.acc = 0; w.nbits = 0; w.pos = 0; w.out = out;
@@ -148,24 +123,11 @@ PKZ_FN uint32_t pkz_encode_piece(const uint8_t *blk, uint32_t s, uint32_t e, uin
     pkz_put(w, final ? 1u : 0u, 1);
     pkz_put(w, 1, 2);                                        // BTYPE = 01: fixed Huffman
     uint32_t i = s;
-    uint32_t wb = s, wn = e - s < 32 ? e - s : 32;           // cached window of equality bits: positions [wb, wb + wn)
-    uint32_t wm = pkz_eqmask(blk, wb, wn, dist);
     while (i < e) {
-        const uint32_t maxl = e - i < PKZ_MAX_MATCH ? e - i : PKZ_MAX_MATCH;
         uint32_t len = 0;
-        for (;;) {
-            uint32_t off = i + len - wb;
-            if (off >= wn) {                                 // move the window to the position under test
-                wb = i + len; wn = e - wb < 32 ? e - wb : 32;
-                wm = pkz_eqmask(blk, wb, wn, dist);
-                off = 0;
-            }
-            const uint32_t avail = wn - off < maxl - len ? wn - off : maxl - len;
-            const uint32_t zeros = ~(wm >> off);             // the first 0 bit ends the run
-            uint32_t ones = zeros ? pkz_ctz(zeros) : 32;
-            if (ones > avail) ones = avail;
-            len += ones;
-            if (ones < avail || len == maxl) break;
+        if (i >= dist) {
+            const uint32_t maxl = e - i < PKZ_MAX_MATCH ? e - i : PKZ_MAX_MATCH;
+            while (len < maxl && blk[i + len] == blk[i + len - dist]) len++;
         }
         if (len >= PKZ_MIN_MATCH) {
             pkz_put_length(w, len);

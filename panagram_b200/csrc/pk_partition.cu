@@ -842,23 +842,11 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const uint2 *__restrict_
     const uint32_t nb = min(4u, nbl - 4 * grp);
     const bool al4 = nb == 4 && ((row_stride | col_offset) & 3) == 0;
     const uint32_t t1 = min(cnt, t0 + UP_TILE);
-    // all of a thread's list entries are loaded before the first scattered store: the kernel sat on one dependent
-    // load -> store per iteration (84 stall cycles per issue on long_scoreboard, profiles/r1h_ncu_unpermute.txt)
-    constexpr int UPT = UP_TILE / 256;
-    uint2 e[UPT];
-#pragma unroll
-    for (int j = 0; j < UPT; j++) {
-        const uint32_t i = t0 + threadIdx.x + j * 256;
-        e[j] = i < t1 ? src[i] : make_uint2(0xffffffffu, 0);
-    }
-#pragma unroll
-    for (int j = 0; j < UPT; j++) {
-        if (t0 + threadIdx.x + j * 256 < t1) {
-            uint8_t *dst = rows + (uint64_t)e[j].x * row_stride + col_offset + 4 * grp;
-            if (al4) *(uint32_t *)dst = e[j].y;
-            else if (nb == 1) dst[0] = (uint8_t)e[j].y;
-            else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(e[j].y >> (8 * qb));
-        }
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += 256) {
+        const uint2 e = src[i];
+        uint8_t *dst = rows + (uint64_t)e.x * row_stride + col_offset + 4 * grp;
+        if (al4) *(uint32_t *)dst = e.y;
+        else for (uint32_t qb = 0; qb < nb; qb++) dst[qb] = (uint8_t)(e.y >> (8 * qb));
     }
 }
 
