@@ -622,6 +622,21 @@ __global__ void __launch_bounds__(256) gather_interleave_kernel(const __grid_con
                     }
                 }
             }
+        } else if (a.w == 1 && a.n_ranks == 2 && a.row_stride == 2 && (((uintptr_t)out) & 15) == 0) {
+            // two ranks of 8 genomes: 4 rows per thread, byte-interleaved in registers, one 8-byte store
+            for (uint32_t r4 = threadIdx.x * 4; r4 < nrows; r4 += 256 * 4) {
+                const uint32_t x0 = *(const uint32_t *)(g_tile + r4), x1 = *(const uint32_t *)(g_tile + plane_bytes + r4);
+                const uint32_t lo = __byte_perm(x0, x1, 0x5140), hi = __byte_perm(x0, x1, 0x7362);
+                if (r4 + 4 <= nrows) {
+                    *(uint2 *)(out + (uint64_t)r4 * 2) = make_uint2(lo, hi);
+                } else {
+                    const uint32_t v[2] = {lo, hi};
+                    for (uint32_t j = 0; r4 + j < nrows; j++) {
+                        out[(uint64_t)(r4 + j) * 2] = (uint8_t)(v[j >> 1] >> (16 * (j & 1)));
+                        out[(uint64_t)(r4 + j) * 2 + 1] = (uint8_t)(v[j >> 1] >> (16 * (j & 1) + 8));
+                    }
+                }
+            }
         } else if (a.row_stride == rw && (((uintptr_t)out) & 15) == 0) {
             const uint32_t total = nrows * rw;
             for (uint32_t o = threadIdx.x * 16; o < total; o += 256 * 16) {

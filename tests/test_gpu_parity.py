@@ -297,6 +297,27 @@ def test_device_level_sharded_gather_equals_single_engine():
     assert torch.equal(rows, rows2)
 
 
+@pytest.mark.parametrize("n_ranks,w", [(2, 1), (4, 1), (8, 1), (16, 1), (3, 1), (2, 2), (8, 2), (5, 3), (2, 4)])
+def test_fused_gather_interleave_kernel(n_ranks, w):
+    """pk_gather_interleave_device (the peer-memory exchange of the genome-sharded path): rows[i][r*w:(r+1)*w] =
+    planes[r][i]. The planes are ordinary device buffers here — the kernel does not care whether a pointer is
+    peer-mapped — so every layout branch (1 byte x 2 / 4k ranks, general) runs on one GPU, ragged sizes included."""
+    import torch
+    eng = Engine(21, 1)
+    eng.add_keys(0, np.array([1], dtype=np.uint64))
+    eng.finalize()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(n_ranks * 10 + w)
+    for n in (1, 5, 4096, 100_003, 1_000_000):
+        planes = [torch.from_numpy(rng.integers(0, 256, size=(n, w), dtype=np.uint8)).to(dev) for _ in range(n_ranks)]
+        rows = torch.zeros((n, n_ranks * w), dtype=torch.uint8, device=dev)
+        eng.gather_interleave_device([p.data_ptr() for p in planes], n, w, rows.data_ptr(), n_ranks * w, st)
+        torch.cuda.synchronize()
+        want = np.concatenate([p.cpu().numpy() for p in planes], axis=1)
+        assert (rows.cpu().numpy() == want).all(), (n_ranks, w, n)
+
+
 def big_case(n_genomes, k, length, seed, repeats=False):
     """A seeded pan-genome too large for the Python oracle loops but fine for the C oracle."""
     from panagram_b200 import synth
