@@ -223,8 +223,9 @@ def main():
                     help="instead of the anchoring step: time the whole `panagram index` run from FASTA files on disk")
     ap.add_argument("--group-tables", type=int, default=1, help="0: per-genome tables only (one probe per genome and position)")
     ap.add_argument("--e2e-batches", type=int, default=0, help="override the engine's batches per pk_anchor_genome call (0 = default)")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: assemble rows with the fused peer-memory gather+interleave kernel or NCCL all-gather + interleave")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-serial", "nccl"],
+                    help="N>1: assemble rows with the fused peer-memory gather+interleave kernel (on a side stream under the "
+                         "next probe, or serially on the probe's stream) or NCCL all-gather + interleave")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -325,7 +326,7 @@ def main():
     torch.cuda.synchronize()
 
     p2p = None
-    if world > 1 and args.exchange == "p2p":
+    if world > 1 and args.exchange in ("p2p", "p2p-serial"):
         # fused exchange over peer memory: each rank's planes (two, ping-pong) are IPC-mapped into every peer;
         # stream-ordered barriers (1-element NCCL all-reduce) order the ranks, the data itself never goes
         # through NCCL. The gather+interleave of step i runs on a side stream under the probe of step i+1
@@ -350,10 +351,14 @@ def main():
             dist.all_reduce(flag)                            # ... on every rank: plane b may be overwritten
             eng.probe_device(d_words.data_ptr(), d_mask.data_ptr(), 0, npos, planes[b], rb_local, 0, st)
             dist.all_reduce(flag)                            # every rank's plane b is complete
-            p2p["probed"][b].record(tstream)
-            side.wait_event(p2p["probed"][b])
-            eng.gather_interleave_device(peers[b], npos, rb_local, d_rows2[b].data_ptr(), rb_full, side.cuda_stream)
-            p2p["gathered"][b].record(side)
+            if args.exchange == "p2p-serial":
+                eng.gather_interleave_device(peers[b], npos, rb_local, d_rows2[b].data_ptr(), rb_full, st)
+                p2p["gathered"][b].record(tstream)
+            else:
+                p2p["probed"][b].record(tstream)
+                side.wait_event(p2p["probed"][b])
+                eng.gather_interleave_device(peers[b], npos, rb_local, d_rows2[b].data_ptr(), rb_full, side.cuda_stream)
+                p2p["gathered"][b].record(side)
             p2p["i"] = i + 1
             return
         eng.probe_device(d_words.data_ptr(), d_mask.data_ptr(), 0, npos, d_local.data_ptr(), rb_local, 0, st)
@@ -518,7 +523,7 @@ def main():
                            "l2": "inputs (per-genome tables, %.1f GB/GPU) are far larger than L2; no flush needed"
                                  % (sum(t["bytes"] for t in tstats) / 1e9),
                            "parallelism": (f"genome-sharded x{world}, exchange=" +
-                                           ("fused peer-memory gather+interleave kernel" if p2p else "NCCL all-gather + interleave"))
+                                           (("fused peer-memory gather+interleave kernel" + (" (serial)" if args.exchange == "p2p-serial" else " (under the next probe)")) if p2p else "NCCL all-gather + interleave"))
                            if world > 1 else "1 GPU",
                            "setup_s": round(setup_s, 1)},
                 "e2e": {"value": positions * n_total / (e2e_ms / 1e3), "unit": unit, "ms_per_step": e2e_ms,

@@ -143,3 +143,34 @@ def test_native_fasta_reader_equals_the_numpy_parser(tmp_path, pan3):
     disguised = tmp_path / "y.fa"                      # gzip magic without the suffix: handed to the numpy path
     disguised.write_bytes(gzip.compress(cases["plain"]))
     assert [(n, s.tobytes()) for n, s in anchor.parse_fasta(disguised)] == [("chr1", b"ACGTNNAC"), ("chr2", b"acgtn")]
+
+
+def test_umap_inputs_and_csv_match_the_reference_restated_in_pandas():
+    """layout.paircount_bins == Index.bitmap_to_paircount_bins (index.py:454-459) restated with the reference's own
+    pandas calls; umap CSV text = DataFrame(...).to_csv() of Genome.run_umap's zero-fill fallback (index.py:1149-1156)."""
+    import pandas as pd
+    from panagram_b200 import layout
+    rng = np.random.default_rng(11)
+    for n_genomes, nrows, step, bin_size in ((8, 5000, 100, 100000), (3, 777, 100, 100000), (35, 2500, 100, 50000), (9, 1, 100, 100000)):
+        nb = (n_genomes + 7) // 8
+        rows = rng.integers(0, 256, size=(nrows, nb), dtype=np.uint8)
+        rows[rng.random(nrows) < 0.1] = 0
+        starts, frac = layout.paircount_bins(rows, n_genomes, step, bin_size)
+        bits = np.unpackbits(rows, axis=1, bitorder="little")[:, :n_genomes]
+        bitmap = pd.DataFrame(bits, index=np.arange(0, nrows * step, step))
+        df = bitmap.set_index(bitmap.index // bin_size)
+        pc = df.groupby(level=0).sum()
+        pc = pc.set_index(pc.index * bin_size).T
+        pc = pc.div(pc.max(axis=0), axis=1).T.fillna(0)
+        assert list(pc.index) == list(starts)
+        assert np.allclose(pc.to_numpy(dtype=float), frac)
+        # the fallback rows and their CSV text
+        urows = layout.umap_rows("chrA", starts, frac, bin_size)
+        want = pd.DataFrame({"umap1": 0, "umap2": 0, "cluster": 0}, index=pd.MultiIndex.from_product([["chrA"], starts], names=["chrom", "start"])).reset_index()
+        want["end"] = want["start"] + bin_size
+        want = want[["chrom", "start", "end", "umap1", "umap2", "cluster"]]
+        try:
+            import umap  # noqa: F401
+        except ImportError:
+            assert layout.umaps_csv(urows) == want.to_csv(index=False)
+            assert layout.umaps_csv(urows) == want.set_index("chrom").to_csv()
