@@ -111,7 +111,7 @@ def run_reference(args, wl, cores):
     (untimed, like our table build); each step times `run_anchor N . g0 g0.fa` (cpp/Snakefile:55)."""
     from oracle import refpipe
     from panagram_b200 import synth
-    n = wl["n_per_gpu"] * 1          # the CPU arm always runs the 1-GPU genome count
+    n = wl["n_per_gpu"] * max(1, getattr(args, "gpus", 1))     # the same genome count as our arm at this N (weak scaling)
     if not refpipe.have_ref():
         return {"impl": "reference", "unavailable": "oracle/_ref binaries missing (build with make -C oracle ref)"}
     length = min(wl["length"], CPU_SAMPLE_LEN)
@@ -248,7 +248,9 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-                "data": "synthetic", "config": {"workload": wl["name"], "k": wl["k"], "sample": r["sample"]},
+                "data": "synthetic",
+                "config": {"workload": wl["name"] + (f" x{args.gpus} genome shards ({wl['n_per_gpu'] * args.gpus} genomes)" if args.gpus > 1 else ""),
+                           "k": wl["k"], "n_genomes": wl["n_per_gpu"] * max(1, args.gpus), "sample": r["sample"]},
                 "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference",
                                  "sample": r["sample"],
                                  "note": f"run_anchor parallelises over anchors only (cpp/anchor.cpp:217): 1 anchor "
@@ -506,7 +508,7 @@ def main():
                                          "unpermute": ks["k_unpermute_ms"]}}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            a2 = argparse.Namespace(steps=1, warmup=0)
+            a2 = argparse.Namespace(steps=1, warmup=0, gpus=1)
             r = run_reference(a2, wl, cores)
             if "unavailable" not in r:
                 cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"],
