@@ -2,24 +2,31 @@
 """bench.py — anchored k-mers/sec (positions x genomes) building the pan-kmer bitmap.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+                  [--group-tables 0|1] [--e2e-batches B] [--exchange p2p|p2p-serial|nccl] [--index-e2e W]
 
 One "step" = one pass of the hot path over one anchor genome: every k-mer position of the
 anchor probed against every genome's k-mer set and the N-bit rows written.
 
 Workloads (BASELINE.json `configs`; synthetic genomes per SURVEY.md §8d, panagram_b200/synth.py):
-  configs1  8 x 135 Mbp, k=21, 1 anchor — the configuration the metric is quoted on (default)
-  configs2  32 x 150 Mbp, k=21, 1 anchor
-  small     8 x 8 Mbp, k=21 (plumbing check)
+  configs1   8 x 135 Mbp, k=21, 1 anchor — the configuration the metric is quoted on (default)
+  configs2   32 x 150 Mbp, k=21, 1 anchor
+  configs3s  one GPU's shard of configs[3]: 8 x 150 Mbp, k=31
+  small      8 x 8 Mbp, k=21 (plumbing check)
 At N GPUs the genomes are sharded by genome (weak scaling: 8 genomes' tables per GPU, 8N
-genomes in total, every rank probes all anchor positions against its shard, one NCCL
-all-gather of the per-rank column bytes + an interleave kernel assemble the N-bit rows).
+genomes in total, every rank probes all anchor positions against its shard, one fused peer-memory
+gather+interleave kernel — or an NCCL all-gather + interleave kernel — assembles the N-bit rows).
 
-`value`   device-resident: packed anchor already in HBM, CUDA events around the probe stage
-          (partition + probe kernels [+ all-gather + interleave at N>1]).
-`e2e`     the public call a user makes (Engine.anchor_genome -> pk_anchor_genome) with pinned
-          HOST buffers: ASCII in, bitmap rows / low-res rows / histograms / column sums out.
+`value`     device-resident: packed anchor already in HBM, CUDA events around the probe stage
+            (partition + probe kernels [+ exchange at N>1]).
+`e2e`       the public call a user makes (Engine.anchor_genome -> pk_anchor_genome) with pinned
+            HOST buffers: ASCII in, bitmap rows / low-res rows / histograms / column sums out.
+`e2e_files` the same with the two bitmaps delivered as BGZF file images deflated on the GPU.
+`roofline`  the probe kernel: SURVEY §8d's algorithmic bytes / its CUDA-event duration (`frac`), and the DRAM
+            bytes ncu counted for the same launch / that duration (`physical`).
 `--impl reference`  the reference's own CPU implementation (oracle/_ref/run_anchor, built from
-          the unmodified cpp/anchor.cpp + KMC API) on a bounded sample of the same workload.
+            the unmodified cpp/anchor.cpp + KMC API) on a bounded sample of the same workload.
+`--index-e2e W`     instead: the whole `panagram index` run, FASTA files on disk -> anchor directories,
+            next to the reference's pipeline on the same files, outputs compared.
 """
 from __future__ import annotations
 
