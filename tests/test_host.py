@@ -174,3 +174,36 @@ def test_umap_inputs_and_csv_match_the_reference_restated_in_pandas():
         except ImportError:
             assert layout.umaps_csv(urows) == want.to_csv(index=False)
             assert layout.umaps_csv(urows) == want.set_index("chrom").to_csv()
+
+
+def test_s32_hash_is_invertible_from_slot_and_home_bucket():
+    """The group-table merge (csrc/pk_kernels.cu::union_merge_kernel) re-derives a k-mer from an S32 slot: low 28 bits
+    from the slot, the other 2k-28 bits from the slot's HOME bucket by inverting pk_key_hash — the hash is
+    (X << (32-eb)) | (mix32(lo) >> eb) for the one X whose hash maps to that bucket. Restated in numpy and checked for
+    the table sizes the engine produces (>= 2^eb buckets)."""
+    rng = np.random.default_rng(1)
+
+    def mix32(x):
+        x = x.astype(np.uint32).copy()
+        x ^= x >> np.uint32(16); x *= np.uint32(0x7FEB352D); x ^= x >> np.uint32(15); x *= np.uint32(0x846CA68B); x ^= x >> np.uint32(16)
+        return x
+
+    for k, nb in [(21, 33748694), (21, 1 << 14), (21, 16385), (24, 1 << 20), (24, 40000000), (16, 1000), (15, 77)]:
+        eb = max(0, 2 * k - 28)
+        canon = rng.integers(0, 1 << (2 * k), size=100000, dtype=np.uint64)
+        lo = (canon & np.uint64(0x0FFFFFFF)).astype(np.uint32)
+        m = mix32(lo)
+        hi = (canon >> np.uint64(28)).astype(np.uint32)
+        f = (m * np.uint32(0x9E3779B1)) >> np.uint32(32 - eb)
+        h = ((hi ^ f) << np.uint32(32 - eb)) | (m >> np.uint32(eb))                      # pk_key_hash, S32, eb > 0
+        home = (h.astype(np.uint64) * np.uint64(nb)) >> np.uint64(32)
+        sh, low = 32 - eb, m >> np.uint32(eb)
+        hmin = ((home << np.uint64(32)) + np.uint64(nb - 1)) // np.uint64(nb)            # smallest hash of the home bucket
+        X = (hmin >> np.uint64(sh)).astype(np.uint32)
+        h2 = (X << np.uint32(sh)) | low
+        miss = ((h2.astype(np.uint64) * np.uint64(nb)) >> np.uint64(32)) != home
+        X = np.where(miss, (X + np.uint32(1)) & np.uint32((1 << eb) - 1), X)
+        h3 = (X << np.uint32(sh)) | low
+        assert (((h3.astype(np.uint64) * np.uint64(nb)) >> np.uint64(32)) == home).all()
+        back = ((X ^ f).astype(np.uint64) << np.uint64(28)) | lo.astype(np.uint64)
+        assert (back == canon).all() and (h3 == h).all(), (k, nb)
