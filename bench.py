@@ -529,8 +529,10 @@ def main():
                 "config": {"workload": wl["name"] + (f" x{world} genome shards ({n_total} genomes)" if world > 1 else ""),
                            "k": k, "n_genomes": n_total, "genomes_per_gpu": npg, "positions": positions,
                            "load_factor": args.load_factor, "probe_mode": args.probe_mode,
-                           "l2": "inputs (per-genome tables, %.1f GB/GPU) are far larger than L2; no flush needed"
-                                 % (sum(t["bytes"] for t in tstats) / 1e9),
+                           "l2": "no flush needed: every step streams its tables (group tables %.1f GB/GPU, derived from %.1f GB of "
+                                 "per-genome tables) and 3.3 GB of partition scratch, far more than the 126 MB L2"
+                                 % (sum((eng.group_stats(u) or {"bytes": 0})["bytes"] for u in range((npg + 7) // 8)) / 1e9,
+                                    sum(t["bytes"] for t in tstats) / 1e9),
                            "parallelism": (f"genome-sharded x{world}, exchange=" +
                                            (("fused peer-memory gather+interleave kernel" + (" (serial)" if args.exchange == "p2p-serial" else " (under the next probe)")) if p2p else "NCCL all-gather + interleave"))
                            if world > 1 else "1 GPU",
