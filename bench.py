@@ -530,9 +530,9 @@ def main():
                            "k": k, "n_genomes": n_total, "genomes_per_gpu": npg, "positions": positions,
                            "load_factor": args.load_factor, "probe_mode": args.probe_mode,
                            "l2": "no flush needed: every step streams its tables (group tables %.1f GB/GPU, derived from %.1f GB of "
-                                 "per-genome tables) and 3.3 GB of partition scratch, far more than the 126 MB L2"
+                                 "per-genome tables) and %.1f GB of partition scratch, far more than the 126 MB L2"
                                  % (sum((eng.group_stats(u) or {"bytes": 0})["bytes"] for u in range((npg + 7) // 8)) / 1e9,
-                                    sum(t["bytes"] for t in tstats) / 1e9),
+                                    sum(t["bytes"] for t in tstats) / 1e9, positions * 24 / 1e9),
                            "parallelism": (f"genome-sharded x{world}, exchange=" +
                                            (("fused peer-memory gather+interleave kernel" + (" (serial)" if args.exchange == "p2p-serial" else " (under the next probe)")) if p2p else "NCCL all-gather + interleave"))
                            if world > 1 else "1 GPU",
