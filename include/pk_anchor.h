@@ -120,6 +120,13 @@ int pk_engine_add_sequence(pk_engine *e, uint32_t genome, const char *ascii, uin
 /* as pk_engine_add_sequence, from ASCII already resident in device memory */
 int pk_engine_add_sequence_device(pk_engine *e, uint32_t genome, const void *d_ascii, uint64_t len);
 int pk_engine_finalize(pk_engine *e);
+/* pk_engine_seal_group: build the group table (below) of local genomes [8*group, 8*group+8) NOW, from their
+ * per-genome tables as they stand. With the "group_only" knob set (pk_engine_tune) those per-genome tables are
+ * freed at once — they are build intermediates then, and every lookup is answered from the group tables — so
+ * a host that adds genomes group by group never holds more than one group's per-genome tables (64 genomes of
+ * 150 Mbp at k=31: ~110 GB of group tables instead of 154 GB + 110 GB). pk_engine_finalize seals what is left.
+ * Adding k-mers to a sealed genome is PK_ESTATE. */
+int pk_engine_seal_group(pk_engine *e, uint32_t group);
 
 typedef struct pk_table_stats {
     uint64_t n_keys;        /* distinct k-mers stored */
@@ -168,6 +175,16 @@ int pk_anchor_genome(pk_engine *e, uint32_t n_chroms, const char *const *seqs, c
 int pk_anchor_chrom(pk_engine *e, const char *ascii, uint64_t len,
                     uint8_t *bitmap1, uint8_t *bitmap_low,
                     uint64_t *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out);
+
+/* The rank-local half of the genome-sharded path (cpp/anchor.cpp has no counterpart: it holds every
+ * genome in one process). pk_anchor_layout: the concatenated ("cat") row numbering one call uses — chromosome c's
+ * k-mer p is row cat_off[c] + p; returns the number of rows a plane must hold. pk_anchor_genome_plane: H2D + pack +
+ * probe of all chromosomes, pipelined exactly as pk_anchor_genome, with the shard's row bytes written to the
+ * caller-owned DEVICE plane [plane_rows][ceil(N_local/8)] (e.g. from pk_device_alloc, IPC-exported to the peers);
+ * rows between chromosomes are zero or unwritten. Complete when the call returns. */
+uint64_t pk_anchor_layout(uint32_t n_chroms, const uint64_t *lens, uint64_t *cat_off);
+int pk_anchor_genome_plane(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                           void *d_plane, uint64_t plane_rows, uint64_t *nkmers_out);
 
 /* Replaces CKMCFile::GetCountersForRead as the anchoring path calls it on
  * bitvec database `dbi` (cpp/anchor.cpp:148; index.py:932-938):
@@ -228,6 +245,20 @@ int pk_ipc_close(pk_engine *e, void *d_ptr);
 int pk_gather_interleave_device(pk_engine *e, const void *const *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w,
                                 void *d_rows, uint32_t row_stride, void *stream);
 
+/* Position-split exchange: instead of every rank assembling every row (an all-gather: R times the NVLink and
+ * HBM-write volume anyone needs), rank r assembles only ITS slice of the output rows — the slice it then reduces,
+ * compresses and stores — reading that slice of all R planes in place over NVLink:
+ *   rows[seg.dst_row + i][q*w .. q*w+w) = planes[q][seg.src_row + i][0..w)     0 <= i < seg.n_rows, for every segment
+ * A slice is a list of segments because the planes are numbered like the concatenated anchor (chromosomes
+ * separated by gap rows) while the output is the bitmap stream (chromosomes back to back, cpp/anchor.cpp:167).
+ * plane_rows = rows allocated in every plane; row_bytes = bytes of a full row (ceil(N/8): a narrow last shard is
+ * clipped). One kernel, no shared memory, every byte crosses NVLink once. Segment lists are cached by content:
+ * repeating the previous call's list costs no upload. */
+typedef struct pk_segment { uint64_t src_row, n_rows, dst_row; } pk_segment;
+int pk_gather_slice_device(pk_engine *e, const void *const *d_planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w,
+                           const pk_segment *segs, uint32_t n_segs, void *d_rows, uint32_t row_stride, uint32_t row_bytes,
+                           void *stream);
+
 /* ---- BGZF output on the GPU ------------------------------------------------------
  * Replaces bgzf_open/bgzf_index_build_init/bgzf_write/bgzf_index_dump/bgzf_close as KMCdb::anchor_fasta and
  * write_bits use them (cpp/anchor.cpp:46-54,102-106,167,177; Python path: bgzip.BGZipWriter + `bgzip -rI`,
@@ -252,12 +283,13 @@ int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *se
                           uint8_t *const *gz, const uint64_t *gz_cap, uint8_t *const *gzi, const uint64_t *gzi_cap,
                           uint64_t *sizes, uint64_t *const *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out);
 
-/* Tuning knobs of the partitioned probe (process-wide; no reference counterpart). Results never depend on
+/* Tuning knobs of the partitioned probe (per engine; no reference counterpart). Results never depend on
  * them; tests run the parity suite under several settings. name = "k3_window" (1: probe out of table
  * windows staged in shared memory by TMA bulk copies when they fit, 0: always probe through L1/L2),
  * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_group" (0 = by window size, or 1, 2, 4 genomes per window group; two groups of windows are staged per block),
- * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "group_tables" (0/1: per-engine;
- * takes effect at the next pk_engine_finalize), "unpermute" (0/1: applies to
+ * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "group_tables" (0/1;
+ * takes effect at the next pk_engine_finalize), "group_only" (0/1: free a group's per-genome tables once its
+ * group table is built; see pk_engine_seal_group), "unpermute" (0/1: applies to
  * scratch allocated afterwards), "e2e_batches" (1..8: batches of whole chromosomes per pk_anchor_genome call;
  * copies of one batch overlap the kernels of the other), "e2e_batch_min" (positions from which a genome is
  * split into batches; default 32 Mi). Unknown names return PK_EINVAL. */

@@ -52,6 +52,10 @@ class PkStats(C.Structure):
                 ("kernel_launches", C.c_uint64)]
 
 
+class PkSegment(C.Structure):
+    _fields_ = [("src_row", C.c_uint64), ("n_rows", C.c_uint64), ("dst_row", C.c_uint64)]
+
+
 # every symbol include/pk_anchor.h declares: name -> (restype, argtypes)
 _vp, _cp, _u32, _u64, _sz = C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_size_t
 _pp = C.POINTER(C.c_void_p)
@@ -76,11 +80,14 @@ SIGNATURES = {
     "pk_engine_add_sequence": (C.c_int, [_vp, _u32, _vp, _u64]),
     "pk_engine_add_sequence_device": (C.c_int, [_vp, _u32, _vp, _u64]),
     "pk_engine_finalize": (C.c_int, [_vp]),
+    "pk_engine_seal_group": (C.c_int, [_vp, _u32]),
     "pk_engine_table_stats": (C.c_int, [_vp, _u32, C.POINTER(PkTableStats)]),
     "pk_engine_group_stats": (C.c_int, [_vp, _u32, C.POINTER(PkTableStats)]),
     "pk_bin_len": (_u64, [C.POINTER(PkConfig), _u64]),
     "pk_anchor_genome": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pk_anchor_chrom": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _pu64]),
+    "pk_anchor_layout": (_u64, [_u32, _vp, _vp]),
+    "pk_anchor_genome_plane": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _u64, _vp]),
     "pk_get_counters_for_read": (C.c_int, [_vp, _u32, _vp, _u64, _vp, _pu64]),
     "pk_host_alloc": (C.c_int, [_pp, _sz]),
     "pk_host_free": (C.c_int, [_vp]),
@@ -101,6 +108,7 @@ SIGNATURES = {
     "pk_ipc_open": (C.c_int, [_vp, _vp, _pp]),
     "pk_ipc_close": (C.c_int, [_vp, _vp]),
     "pk_gather_interleave_device": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _vp, _u32, _vp]),
+    "pk_gather_slice_device": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _vp, _u32, _vp, _u32, _u32, _vp]),
 }
 
 _LIB = None

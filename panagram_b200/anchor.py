@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import gzip
 import os
+import shutil
 from pathlib import Path
 
 import numpy as np
@@ -89,57 +90,17 @@ def parse_fasta_numpy(path, strip_cr: bool = False) -> list[tuple[str, np.ndarra
     return recs
 
 
-def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[str] | None = None,
-                 bgzf_level: int = 6, threads: int | None = None, strip_cr: bool = False,
-                 bgzf: str = "gpu", umap_bin_size: int = 100000) -> dict:
-    """Anchor one genome and write its directory. Returns summary numbers.
-
-    The engine must hold all N genomes (single-GPU layout). Chromosomes shorter
-    than k + min_bin_count - 1 have no defined bins in the reference
-    (cpp/anchor.cpp:116-120 divides by zero): they raise ValueError here.
-    bgzf="gpu": the .gz/.gzi files are compressed on the GPU (pk_anchor_genome_bgzf) and arrive as file
-    images; bgzf="zlib": raw rows come back and are deflated by zlib on a host thread pool
-    (`bgzf_level`, `threads`). Both decompress to the same bytes.
-    """
+def write_text_files(outdir, name: str, chrom_names: list[str], nks: list[int], binlens: list[int], hists: list,
+                     col_sums, low_all: np.ndarray, n_genomes: int, step: int, genome_names: list[str] | None,
+                     umap_bin_size: int = 100000) -> None:
+    """Everything of an anchor directory but the bitmaps: chrs.tsv, bitsum.bins.tsv (cpp/anchor.cpp:57-69,84-85,
+    184-189), total_paircounts.csv (index.py:1068-1074) and chrom_umaps.csv / genome_umap.csv (Genome.write_umaps,
+    index.py:1107-1131) from the low-res rows `low_all` [sum(ceil(nk/step)), row_bytes] of all chromosomes."""
     outdir = Path(outdir)
-    outdir.mkdir(parents=True, exist_ok=True)
-    threads = threads or min(32, os.cpu_count() or 1)
-    step = engine.lowres_step
-    recs = parse_fasta(fasta, strip_cr=strip_cr)
-    for cname, seq in recs:
-        nk = seq.size - engine.k + 1
-        if nk < 1 or engine.bin_len(nk) == 0:
-            raise ValueError(f"{fasta}: chromosome {cname!r} has {max(nk, 0)} k-mers; the reference "
-                             "needs at least min_bin_count (cpp/anchor.cpp:116-120)")
-    chroms, bins = [], []
-    positions = 0
-    if bgzf == "gpu":
-        res = engine.anchor_genome_bgzf([s for _, s in recs])             # the whole genome in one batch
-        for key, fn in (("gz", "bitmap.1.gz"), ("gzi", "bitmap.1.gzi"), ("gz_low", f"bitmap.{step}.gz"),
-                        ("gzi_low", f"bitmap.{step}.gzi")):
-            with open(outdir / fn, "wb") as fh:
-                fh.write(res[key].data)
-    elif bgzf == "zlib":
-        w1 = layout.BgzfWriter(outdir / "bitmap.1.gz", bgzf_level, threads)
-        wl = layout.BgzfWriter(outdir / f"bitmap.{step}.gz", bgzf_level, threads)
-        res = engine.anchor_genome([s for _, s in recs], pinned=True)
-        for r in res["chroms"]:
-            w1.write(r["bitmap1"])
-            wl.write(r["low"])
-        w1.close(outdir / "bitmap.1.gzi")
-        wl.close(outdir / f"bitmap.{step}.gzi")
-    else:
-        raise ValueError(f"bgzf={bgzf!r}: expected 'gpu' or 'zlib'")
-    # chrom_umaps.csv / genome_umap.csv (Genome.write_umaps, index.py:1107-1131) from the low-res rows
-    if bgzf == "gpu":
-        import gzip as _gzip
-        low_all = np.frombuffer(_gzip.decompress(res["gz_low"].tobytes()), dtype=np.uint8).reshape(-1, engine.row_bytes)
-    else:
-        low_all = np.concatenate([r["low"] for r in res["chroms"]]) if res["chroms"] else np.zeros((0, engine.row_bytes), np.uint8)
     chrom_rows, genome_parts, lo = [], [], 0
-    for (cname, _), r in zip(recs, res["chroms"]):
-        n_low = (r["nkmers"] + step - 1) // step
-        starts, frac = layout.paircount_bins(low_all[lo:lo + n_low], engine.n_local, step, umap_bin_size)
+    for cname, nk in zip(chrom_names, nks):
+        n_low = (nk + step - 1) // step
+        starts, frac = layout.paircount_bins(low_all[lo:lo + n_low], n_genomes, step, umap_bin_size)
         lo += n_low
         chrom_rows += layout.umap_rows(cname, starts, frac, umap_bin_size)
         genome_parts.append((cname, starts, frac))
@@ -153,13 +114,65 @@ def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[st
     else:
         g_rows = []
     (outdir / "genome_umap.csv").write_text(layout.umaps_csv(g_rows))
-    col = res["col_sums"]
-    for (cname, _), r in zip(recs, res["chroms"]):
-        chroms.append((cname, r["nkmers"]))
-        bins.append((r["binlen"], r["bin_hist"]))
-        positions += r["nkmers"]
-    (outdir / "chrs.tsv").write_text(layout.chrs_tsv(chroms))
-    (outdir / "bitsum.bins.tsv").write_text(layout.bins_tsv(engine.n_local, bins))
+    (outdir / "chrs.tsv").write_text(layout.chrs_tsv(list(zip(chrom_names, nks))))
+    (outdir / "bitsum.bins.tsv").write_text(layout.bins_tsv(n_genomes, list(zip(binlens, hists))))
     if genome_names is not None and name in genome_names:
-        (outdir / "total_paircounts.csv").write_text(layout.paircounts_csv(genome_names, col, name))
-    return {"positions": positions, "chroms": len(chroms), "col_sums": col}
+        (outdir / "total_paircounts.csv").write_text(layout.paircounts_csv(genome_names, col_sums, name))
+
+
+def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[str] | None = None,
+                 bgzf_level: int = 6, threads: int | None = None, strip_cr: bool = False,
+                 bgzf: str = "gpu", umap_bin_size: int = 100000) -> dict:
+    """Anchor one genome and write its directory. Returns summary numbers.
+
+    The engine must hold all N genomes (single-GPU layout; sharded.anchor_fasta_sharded is the multi-GPU
+    form). Chromosomes shorter than k + min_bin_count - 1 have no defined bins in the reference
+    (cpp/anchor.cpp:116-120 divides by zero): they raise ValueError here.
+    bgzf="gpu": the .gz/.gzi files are compressed on the GPU (pk_anchor_genome_bgzf) and arrive as file
+    images; bgzf="zlib": raw rows come back and are deflated by zlib on a host thread pool
+    (`bgzf_level`, `threads`). Both decompress to the same bytes.
+    The directory is built as `<outdir>.tmp` and renamed when complete (a killed run leaves no
+    half-written anchor directory behind).
+    """
+    final = Path(outdir)
+    outdir = final.with_name(final.name + ".tmp")
+    if outdir.exists():
+        shutil.rmtree(outdir)
+    outdir.mkdir(parents=True)
+    threads = threads or min(32, os.cpu_count() or 1)
+    step = engine.lowres_step
+    recs = parse_fasta(fasta, strip_cr=strip_cr)
+    for cname, seq in recs:
+        nk = seq.size - engine.k + 1
+        if nk < 1 or engine.bin_len(nk) == 0:
+            shutil.rmtree(outdir)
+            raise ValueError(f"{fasta}: chromosome {cname!r} has {max(nk, 0)} k-mers; the reference "
+                             "needs at least min_bin_count (cpp/anchor.cpp:116-120)")
+    if bgzf == "gpu":
+        res = engine.anchor_genome_bgzf([s for _, s in recs])             # the whole genome in one batch
+        for key, fn in (("gz", "bitmap.1.gz"), ("gzi", "bitmap.1.gzi"), ("gz_low", f"bitmap.{step}.gz"),
+                        ("gzi_low", f"bitmap.{step}.gzi")):
+            with open(outdir / fn, "wb") as fh:
+                fh.write(res[key].data)
+        low_all = np.frombuffer(gzip.decompress(res["gz_low"].tobytes()), dtype=np.uint8).reshape(-1, engine.row_bytes)
+    elif bgzf == "zlib":
+        w1 = layout.BgzfWriter(outdir / "bitmap.1.gz", bgzf_level, threads)
+        wl = layout.BgzfWriter(outdir / f"bitmap.{step}.gz", bgzf_level, threads)
+        res = engine.anchor_genome([s for _, s in recs], pinned=True)
+        for r in res["chroms"]:
+            w1.write(r["bitmap1"])
+            wl.write(r["low"])
+        w1.close(outdir / "bitmap.1.gzi")
+        wl.close(outdir / f"bitmap.{step}.gzi")
+        low_all = np.concatenate([r["low"] for r in res["chroms"]]) if res["chroms"] else np.zeros((0, engine.row_bytes), np.uint8)
+    else:
+        shutil.rmtree(outdir)
+        raise ValueError(f"bgzf={bgzf!r}: expected 'gpu' or 'zlib'")
+    col = res["col_sums"]
+    nks = [r["nkmers"] for r in res["chroms"]]
+    write_text_files(outdir, name, [c for c, _ in recs], nks, [r["binlen"] for r in res["chroms"]],
+                     [r["bin_hist"] for r in res["chroms"]], col, low_all, engine.n_local, step, genome_names, umap_bin_size)
+    if final.exists():
+        shutil.rmtree(final)
+    os.replace(outdir, final)
+    return {"positions": sum(nks), "chroms": len(nks), "col_sums": col}

@@ -14,12 +14,28 @@ import numpy as np
 
 
 def _index(args) -> int:
+    import os
     from .index import Index, IndexConfig
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # one process per GPU: re-launch this very command under torchrun (127.0.0.1 rendezvous)
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "-m", "panagram_b200"] + list(args.argv)
+        return subprocess.call(cmd)
+    if args.gpus > 1:
+        import torch
+        import torch.distributed as dist
+        args.device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(args.device)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{args.device}"))
     cfg = IndexConfig(k=args.k, cores=args.cores, lowres_step=args.lowres_step, max_bin_kbp=args.max_bin_kbp,
                       min_bin_count=args.min_bin_count, anchor_genomes=args.anchor_genomes, prepare=args.prepare,
                       kmc={"memory": args.kmc_memory, "threads": args.kmc_threads, "use_existing": args.kmc_use_existing})
     idx = Index(args.input, args.prefix, cfg, device=args.device, load_factor=args.load_factor)
-    idx.run(log=lambda m: print(m, file=sys.stderr))
+    idx.run(log=lambda m: print(m, file=sys.stderr), genome_ranks=args.genome_ranks or None)
+    if args.gpus > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     return 0
 
 
@@ -70,6 +86,10 @@ def main(argv=None) -> int:
     p.add_argument("--kmc.use_existing", dest="kmc_use_existing", action="store_true")
     p.add_argument("--device", type=int, default=0, help="CUDA ordinal")
     p.add_argument("--load_factor", type=float, default=0.5, help="k-mer table fill target")
+    p.add_argument("--gpus", type=int, default=1, help="GPUs of this node: one process per GPU, k-mer tables sharded by genome")
+    p.add_argument("--genome_ranks", type=int, default=0,
+                   help="ranks per genome group (default: all GPUs form one group); gpus / genome_ranks groups hold "
+                        "replicas of the tables and take the anchors round-robin")
     p.set_defaults(fn=_index)
     b = sub.add_parser("bitdump", help="Query pan-kmer bitmap for debugging")
     b.add_argument("index_dir")
@@ -78,6 +98,7 @@ def main(argv=None) -> int:
     b.add_argument("step", type=int, nargs="?", default=1)
     b.set_defaults(fn=_bitdump)
     args = ap.parse_args(argv)
+    args.argv = list(sys.argv[1:] if argv is None else argv)
     return args.fn(args)
 
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "pk_internal.h"
+#include "pk_gather.cuh"
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -29,8 +30,6 @@ void pk_set_error(const char *fmt, ...) {
         }                                                                                          \
     } while (0)
 
-// process-wide tuning state of the partitioned probe (pk_engine_tune / PK_K3* environment variables)
-static int g_tune_window = 1, g_tune_wvariant = -1, g_tune_wstages = 0;
 
 // ------------------------------------------------------------------ engine
 struct HostTable {
@@ -38,6 +37,7 @@ struct HostTable {
     uint64_t capacity = 0;      // keys reserved for
     uint64_t n_keys = 0, n_overflow = 0;
     bool reserved = false;
+    bool sealed = false;        // its keys live in the group table only (group_only): no inserts, no per-genome lookups
 };
 
 struct pk_engine {
@@ -51,7 +51,9 @@ struct pk_engine {
     // partitioned probe answers 8 genomes per probe out of them (pk_device.cuh)
     std::vector<HostTable> utabs;
     std::vector<PkTable> h_utables;             // empty when group tables are off or could not be built
+    PkTable *d_utables = nullptr;               // the same descriptors on the device (direct probe, spill)
     int union_tables = 1;
+    int group_only = 0;                         // free the per-genome tables once their group table is built
     unsigned long long *d_ucounters = nullptr;  // [4]
     unsigned long long *d_counters = nullptr;   // [3 * n_local]
     bool finalized = false;
@@ -73,6 +75,7 @@ struct pk_engine {
     int e2e_batches = 2;                        // batches of whole chromosomes per pk_anchor_genome call (copy/compute overlap)
     uint64_t e2e_batch_min = 32ull << 20;       // ... for genomes of at least this many positions
     bool pev_valid = false;
+    PkPartTune tune{};                          // tuning state of the partitioned probe (pk_engine_tune / PK_K3* environment)
     PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
     PkPartPlan sc_plan{};
     int l2_prefetch = 1;
@@ -87,6 +90,11 @@ struct pk_engine {
     uint8_t *z_gz[2] = {nullptr, nullptr}; uint64_t z_gz_cap[2] = {0, 0};
     unsigned long long *z_gzi[2] = {nullptr, nullptr}; uint64_t z_gzi_cap[2] = {0, 0};
     unsigned long long *z_totals = nullptr;     // [4]
+    // position-split exchange: the last segment list, on the device (pk_gather_slice_device)
+    std::vector<PkgSeg> seg_host;
+    PkgSeg *d_segs = nullptr; uint64_t d_segs_cap = 0;
+    uint32_t seg_w = 0;
+    uint64_t seg_chunks = 0;
     pk_stats stats{};
 };
 
@@ -154,14 +162,14 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (const char *pf = getenv("PK_L2_PREFETCH")) e->l2_prefetch = atoi(pf);
     if (const char *up = getenv("PK_UNPERMUTE")) e->unpermute = atoi(up);
     if (const char *ut = getenv("PK_GROUP_TABLES")) e->union_tables = atoi(ut) ? 1 : 0;
-    if (const char *kv = getenv("PK_K3_VARIANT")) pk_part_set_variant(atoi(kv));
+    if (const char *kv = getenv("PK_K3_VARIANT")) { const int v = atoi(kv); if (v >= -1 && v < pk_part_n_variants()) e->tune.variant = v; }
     {
         const char *we = getenv("PK_K3_WINDOW"), *wv = getenv("PK_K3W_VARIANT"), *ws = getenv("PK_K3W_GROUP");
-        if (we) g_tune_window = atoi(we);
-        if (wv) g_tune_wvariant = atoi(wv);
-        if (ws && (atoi(ws) == 0 || atoi(ws) == 1 || atoi(ws) == 2 || atoi(ws) == 4)) g_tune_wstages = atoi(ws);
-        pk_part_set_window(g_tune_window, g_tune_wvariant, g_tune_wstages);
+        if (we) e->tune.window = atoi(we);
+        if (wv && atoi(wv) >= -1 && atoi(wv) < pk_part_n_wvariants()) e->tune.wvariant = atoi(wv);
+        if (ws && (atoi(ws) == 0 || atoi(ws) == 1 || atoi(ws) == 2 || atoi(ws) == 4)) e->tune.wgroup = atoi(ws);
     }
+    e->sc.tune = &e->tune; e->sc.last_window = &e->tune.last_window;
     e->n_local = cfg->genome_end - cfg->genome_begin;
     e->row_bytes = (e->n_local + 7) / 8;
     e->tabs.resize(e->n_local);
@@ -187,7 +195,7 @@ extern "C" void pk_engine_destroy(pk_engine *e) {
     cudaDeviceSynchronize();
     for (auto &t : e->tabs) cudaFree(t.dev.slots);
     for (auto &t : e->utabs) cudaFree(t.dev.slots);
-    cudaFree(e->d_ucounters);
+    cudaFree(e->d_ucounters); cudaFree(e->d_utables);
     cudaFree(e->sc.buf1); cudaFree(e->sc.buf2); cudaFree(e->sc.spill);
     cudaFree(e->sc.cursor1); cudaFree(e->sc.cursor2); cudaFree(e->sc.spill_cursor); cudaFree(e->sc.err);
     cudaFree(e->g_ascii); cudaFree(e->g_words); cudaFree(e->g_mask); cudaFree(e->g_rows); cudaFree(e->g_low); cudaFree(e->g_u32);
@@ -201,6 +209,7 @@ extern "C" void pk_engine_destroy(pk_engine *e) {
     cudaFree(e->z_tables); cudaFree(e->z_scratch); cudaFree(e->z_cat); cudaFree(e->z_totals);
     for (int i = 0; i < 2; i++) { cudaFree(e->z_gz[i]); cudaFree(e->z_gzi[i]); }
     cudaFree(e->sc.out_list); cudaFree(e->sc.out_cursor);
+    cudaFree(e->d_segs);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -222,6 +231,7 @@ extern "C" int pk_engine_reserve(pk_engine *e, uint32_t genome, uint64_t max_key
     int rc = set_device(e); if (rc) return rc;
     HostTable &t = e->tabs[genome - e->cfg.genome_begin];
     if (t.reserved) { pk_set_error("genome %u already reserved", genome); return PK_ESTATE; }
+    if (t.sealed) { pk_set_error("genome %u is sealed in its group table", genome); return PK_ESTATE; }
     // 32-byte buckets of 4 (S64) or 8 (S32) slots; S32 needs n_buckets >= 2^eb so that k-mers with equal
     // low bits never share a home bucket (pk_key_hash), and always a free slot somewhere for walk-ons to stop
     const double slots_per_bucket = e->ks.fmt == PK_FMT_S32 ? 8.0 : 4.0;
@@ -236,6 +246,20 @@ extern "C" int pk_engine_reserve(pk_engine *e, uint32_t genome, uint64_t max_key
     CU(cudaGetLastError());
     e->finalized = false;
     return upload_tables(e);
+}
+
+// a genome's table is about to change: not allowed once sealed; a group table already built from it is dropped
+// (rebuilt by the next finalize)
+static int touch_genome(pk_engine *e, uint32_t g_local) {
+    if (e->tabs[g_local].sealed) { pk_set_error("genome %u is sealed in its group table (group_only): no more k-mers can be added", e->cfg.genome_begin + g_local); return PK_ESTATE; }
+    const uint32_t gi = g_local / 8;
+    if (gi < e->utabs.size() && e->utabs[gi].reserved) {
+        cudaFree(e->utabs[gi].dev.slots);
+        e->utabs[gi] = HostTable{};
+        e->h_utables.clear();
+    }
+    e->finalized = false;
+    return PK_OK;
 }
 
 static int ensure_stage(pk_engine *e, size_t bytes) {
@@ -260,15 +284,37 @@ static int ingest_kmc(pk_engine *e, const char *prefix, bool bitvec, uint32_t ge
     rc = set_device(e); if (rc) return rc;
     if (!bitvec) {
         if (!is_local(e, genome_or_first)) return PK_OK;
+        rc = touch_genome(e, genome_or_first - e->cfg.genome_begin); if (rc) return rc;
         if (!e->tabs[genome_or_first - e->cfg.genome_begin].reserved) {
             rc = pk_engine_reserve(e, genome_or_first, I.total_kmers); if (rc) return rc;
         }
-    } else {
+    }
+    const uint64_t recs_per_chunk = std::max<uint64_t>(1, (32ull << 20) / std::max<uint32_t>(1, db->rec_size));
+    rc = ensure_stage(e, recs_per_chunk * std::max<uint32_t>(1, db->rec_size)); if (rc) return rc;
+    if (bitvec) {
+        // size every genome's table from ITS k-mer count, not from the union's (up to 32x too much): one pass over
+        // the counters, popcount per bit
+        unsigned long long *d_bits = nullptr;
+        CU(cudaMalloc(&d_bits, 32 * sizeof(unsigned long long)));
+        struct Freer { void *p; ~Freer() { cudaFree(p); } } fb{d_bits};
+        CU(cudaMemsetAsync(d_bits, 0, 32 * sizeof(unsigned long long), e->stream));
+        for (uint64_t r0 = 0; r0 < I.total_kmers && db->rec_size; r0 += recs_per_chunk) {
+            const uint64_t n = std::min(recs_per_chunk, I.total_kmers - r0);
+            CU(cudaStreamSynchronize(e->stream));   // staging buffer reuse
+            if (!pk_kmcdb_read_records(db, r0, n, e->h_stage)) { pk_set_error("%s.kmc_suf: read error", prefix); return PK_EIO; }
+            CU(cudaMemcpyAsync(e->d_stage, e->h_stage, n * db->rec_size, cudaMemcpyHostToDevice, e->stream));
+            pk_launch_count_bits(e->d_stage, n, db->rec_size, db->suf_size, I.counter_size, I.min_count, I.max_count, d_bits, e->stream);
+            CU(cudaGetLastError());
+        }
+        unsigned long long bits[32];
+        CU(cudaMemcpyAsync(bits, d_bits, sizeof bits, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
         for (uint32_t j = 0; j < 32 && genome_or_first + j < e->cfg.n_genomes; j++) {
             const uint32_t g = genome_or_first + j;
-            if (is_local(e, g) && !e->tabs[g - e->cfg.genome_begin].reserved) {
-                // upper bound: every k-mer of the union could belong to this genome
-                rc = pk_engine_reserve(e, g, I.total_kmers); if (rc) return rc;
+            if (!is_local(e, g)) continue;
+            rc = touch_genome(e, g - e->cfg.genome_begin); if (rc) return rc;
+            if (!e->tabs[g - e->cfg.genome_begin].reserved) {
+                rc = pk_engine_reserve(e, g, I.counter_size ? bits[j] : I.total_kmers); if (rc) return rc;
             }
         }
     }
@@ -276,8 +322,6 @@ static int ingest_kmc(pk_engine *e, const char *prefix, bool bitvec, uint32_t ge
     CU(cudaMalloc(&d_lut, db->lut.size() * 8));
     struct Freer { void *p; ~Freer() { cudaFree(p); } } freer{d_lut};
     CU(cudaMemcpyAsync(d_lut, db->lut.data(), db->lut.size() * 8, cudaMemcpyHostToDevice, e->stream));
-    const uint64_t recs_per_chunk = std::max<uint64_t>(1, (32ull << 20) / std::max<uint32_t>(1, db->rec_size));
-    rc = ensure_stage(e, recs_per_chunk * std::max<uint32_t>(1, db->rec_size)); if (rc) return rc;
     PkDecodeArgs a{};
     a.d_lut = d_lut; a.n_lut_slots = db->lut.size() - 1; a.single_lut = db->single_lut;
     a.suf_size = db->suf_size; a.counter_size = I.counter_size; a.rec_size = db->rec_size;
@@ -318,11 +362,20 @@ extern "C" int pk_engine_add_keys(pk_engine *e, uint32_t genome, const uint64_t 
     if (genome >= e->cfg.n_genomes) { pk_set_error("genome %u out of range", genome); return PK_EINVAL; }
     if (!is_local(e, genome)) return PK_OK;
     int rc = set_device(e); if (rc) return rc;
+    rc = touch_genome(e, genome - e->cfg.genome_begin); if (rc) return rc;
     HostTable &t = e->tabs[genome - e->cfg.genome_begin];
     if (!t.reserved) { rc = pk_engine_reserve(e, genome, n); if (rc) return rc; }
-    const uint64_t kmask = e->cfg.k == 32 ? ~0ull : ((1ull << (2 * e->cfg.k)) - 1);
-    for (uint64_t i = 0; i < n; i++)
-        if (keys[i] & ~kmask) { pk_set_error("key %llu has bits above 2k", (unsigned long long)i); return PK_EINVAL; }
+    const uint32_t k = e->cfg.k;
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t x = keys[i];
+        if (x & ~kmask) { pk_set_error("key %llu has bits above 2k", (unsigned long long)i); return PK_EINVAL; }
+        // canonical = min(x, revcomp(x)) (kmer_api.h:373-386); a non-canonical key could never be found by a probe,
+        // and ~0 (T^32, whose canonical form is A^32 = 0) is the EMPTY slot
+        uint64_t r = ~x, rc = 0;
+        for (uint32_t b = 0; b < k; b++) { rc = (rc << 2) | (r & 3); r >>= 2; }
+        if (rc < x) { pk_set_error("key %llu is not canonical (its reverse complement is smaller)", (unsigned long long)i); return PK_EINVAL; }
+    }
     uint64_t *d_keys = nullptr;
     if (n) {
         CU(cudaMalloc(&d_keys, n * 8));
@@ -338,6 +391,7 @@ extern "C" int pk_engine_add_keys(pk_engine *e, uint32_t genome, const uint64_t 
 }
 
 static int add_sequence_device(pk_engine *e, uint32_t genome, const uint8_t *d_ascii, uint64_t len) {
+    int trc = touch_genome(e, genome - e->cfg.genome_begin); if (trc) return trc;
     HostTable &t = e->tabs[genome - e->cfg.genome_begin];
     if (!t.reserved) { pk_set_error("genome %u: pk_engine_reserve must precede add_sequence", genome); return PK_ESTATE; }
     if (len < e->cfg.k) return PK_OK;
@@ -386,76 +440,135 @@ extern "C" int pk_engine_add_sequence_device(pk_engine *e, uint32_t genome, cons
 // largest genome's count and the sum): it is estimated by merging 1/64 of the hash range into a scratch table
 // first. A group that cannot be built (allocation failure, a neighbourhood of 15 full buckets with 64-bit keys)
 // switches group tables off for the engine: the per-genome tables answer every query on their own.
+//
+// group_only (pk_engine_tune "group_only" 1): the per-genome tables of a group are FREED once its group table
+// holds their keys — they are build intermediates then, and every lookup (partitioned probe, direct probe, spill,
+// pk_get_counters_for_read) is answered from the group tables. 64 genomes of configs[3] (k = 31) need 154 GB as
+// per-genome tables + ~110 GB as group tables; sealed group by group (pk_engine_seal_group) the peak is the
+// group tables + ONE group's per-genome tables.
 #define PK_GROUP 8u
 static void drop_group_tables(pk_engine *e) {
     for (auto &t : e->utabs) cudaFree(t.dev.slots);
     e->utabs.clear();
     e->h_utables.clear();
 }
-static int build_group_tables(pk_engine *e) {
-    drop_group_tables(e);
-    if (!e->union_tables) return PK_OK;
+static int refresh_counts(pk_engine *e) {
+    std::vector<unsigned long long> c(3 * e->n_local);
+    CU(cudaMemcpyAsync(c.data(), e->d_counters, c.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (uint32_t i = 0; i < e->n_local; i++) {
+        if (e->tabs[i].sealed) continue;
+        e->tabs[i].n_keys = c[3 * i]; e->tabs[i].n_overflow = c[3 * i + 1];
+        if (c[3 * i + 2]) {
+            pk_set_error("genome %u: table too small (%llu keys did not fit a table reserved for %llu)",
+                         e->cfg.genome_begin + i, c[3 * i + 2], (unsigned long long)e->tabs[i].capacity);
+            return PK_ENOMEM;
+        }
+    }
+    return PK_OK;
+}
+// 1 = built, 0 = could not be built (a note went to stderr; the caller decides), < 0 = error
+static int build_group(pk_engine *e, uint32_t gi) {
     const uint32_t n_groups = (e->n_local + PK_GROUP - 1) / PK_GROUP;
+    if (e->utabs.size() != n_groups) e->utabs.assign(n_groups, HostTable{});
+    HostTable &u = e->utabs[gi];
+    if (u.reserved) return 1;
     if (!e->d_ucounters) CU(cudaMalloc(&e->d_ucounters, 4 * sizeof(unsigned long long)));
     const double load = std::min(e->ks.fmt == PK_FMT_S32 ? 0.5 : 0.35, (double)e->cfg.load_factor);
     const uint32_t ebu = 2 * e->cfg.k > 52 ? 2 * e->cfg.k - 52 : 0;
     const int use_stash = e->ks.fmt == PK_FMT_S32;
-    e->utabs.resize(n_groups);
     unsigned long long c[4] = {0, 0, 0, 0};
-    uint64_t sum = 0;
-    // not an error for the caller (the per-genome tables answer everything), but worth a line: it costs speed
+    uint64_t sum = 0, mx = 0;
     auto fail = [&](const char *why) {
         const cudaError_t ce = cudaGetLastError();
-        fprintf(stderr, "[pkanchor] group tables not built: %s (slots %llu, bits %llu, stashed %llu, failed %llu of %llu keys; cuda: %s)\n",
-                why, c[0], c[1], c[2], c[3], (unsigned long long)sum, cudaGetErrorString(ce));
-        drop_group_tables(e);
-        return PK_OK;
+        fprintf(stderr, "[pkanchor] group table %u not built: %s (slots %llu, bits %llu, stashed %llu, failed %llu of %llu keys; cuda: %s)\n",
+                gi, why, c[0], c[1], c[2], c[3], (unsigned long long)sum, cudaGetErrorString(ce));
+        if (u.dev.slots) { cudaFree(u.dev.slots); u = HostTable{}; }
+        return 0;
     };
     // the group tables are an acceleration structure: their fill is capped whatever the per-genome tables use. With 4
     // slots per bucket, 2 of 315 M keys met 15 full buckets in a row at a fill of 0.49 (configs[1]); k <= 24 sends
     // those to the stash, longer k-mers (no stash for > 48-bit keys) get a fill of 0.35 instead
-    for (uint32_t gi = 0; gi < n_groups; gi++) {
-        const uint32_t g0 = gi * PK_GROUP, ng = std::min(PK_GROUP, e->n_local - g0);
-        uint64_t mx = 0;
-        sum = 0;
-        for (uint32_t g = g0; g < g0 + ng; g++) { sum += e->tabs[g].n_keys; mx = std::max(mx, e->tabs[g].n_keys); }
-        uint64_t distinct = sum;
-        if (ng > 1 && sum >= (1ull << 22)) {
-            // estimate: merge the first 1/64 of every table's buckets (= of the hash range) into a scratch table
-            PkTable tmp{nullptr, 0, 0};
-            const uint64_t nbt = (uint64_t)((double)sum / 64 / (4.0 * 0.5)) + 4096;
-            if (cudaMalloc(&tmp.slots, nbt * 32) != cudaSuccess) return fail("scratch allocation");
-            tmp.n_buckets = (uint32_t)nbt;
-            pk_launch_fill_empty(tmp.slots, nbt * 4, e->stream);
-            cudaMemsetAsync(e->d_ucounters, 0, sizeof c, e->stream);
-            for (uint32_t g = g0; g < g0 + ng; g++)
-                pk_launch_union_merge(e->tabs[g].dev, e->tabs[g].dev.n_buckets / 64, 6, e->ks, tmp, g - g0, g, 0, e->d_ucounters, e->stream);
-            cudaMemcpyAsync(c, e->d_ucounters, sizeof c, cudaMemcpyDeviceToHost, e->stream);
-            const cudaError_t er = cudaStreamSynchronize(e->stream);
-            cudaFree(tmp.slots);
-            if (er != cudaSuccess) return fail("estimate");
-            distinct = std::min<uint64_t>(sum, std::max<uint64_t>(mx, (uint64_t)((double)(c[0] + c[3]) * 64 * 1.03) + 65536));
-        }
-        uint64_t nb = (uint64_t)((double)distinct / (4.0 * load)) + 2;
-        nb = std::max<uint64_t>(nb, std::max<uint64_t>(1ull << ebu, 16));
-        if (nb >= 0xFFFFFFFFull) return fail("too many buckets");
-        HostTable &u = e->utabs[gi];
-        if (cudaMalloc(&u.dev.slots, nb * 32) != cudaSuccess) { u.dev.slots = nullptr; return fail("allocation"); }
-        u.dev.n_buckets = (uint32_t)nb;
-        u.capacity = distinct; u.reserved = true;
-        pk_launch_fill_empty(u.dev.slots, nb * 4, e->stream);
+    const uint32_t g0 = gi * PK_GROUP, ng = std::min(PK_GROUP, e->n_local - g0);
+    for (uint32_t g = g0; g < g0 + ng; g++) { sum += e->tabs[g].n_keys; mx = std::max(mx, e->tabs[g].n_keys); }
+    uint64_t distinct = sum;
+    if (ng > 1 && sum >= (1ull << 22)) {
+        // estimate: merge the first 1/64 of every table's buckets (= of the hash range) into a scratch table
+        PkTable tmp{nullptr, 0, 0};
+        const uint64_t nbt = (uint64_t)((double)sum / 64 / (4.0 * 0.5)) + 4096;
+        if (cudaMalloc(&tmp.slots, nbt * 32) != cudaSuccess) return fail("scratch allocation");
+        tmp.n_buckets = (uint32_t)nbt;
+        pk_launch_fill_empty(tmp.slots, nbt * 4, e->stream);
         cudaMemsetAsync(e->d_ucounters, 0, sizeof c, e->stream);
         for (uint32_t g = g0; g < g0 + ng; g++)
-            pk_launch_union_merge(e->tabs[g].dev, e->tabs[g].dev.n_buckets, 0, e->ks, u.dev, g - g0, g, use_stash, e->d_ucounters, e->stream);
-        if (use_stash) pk_launch_union_merge_stash(e->ks, u.dev, g0, ng, e->d_ucounters, e->stream);
+            pk_launch_union_merge(e->tabs[g].dev, e->tabs[g].dev.n_buckets / 64, 6, e->ks, tmp, g - g0, g, 0, e->d_ucounters, e->stream);
         cudaMemcpyAsync(c, e->d_ucounters, sizeof c, cudaMemcpyDeviceToHost, e->stream);
-        if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail("merge");
-        // every per-genome key must have arrived: bits set + stashed == sum of the genomes' key counts
-        if (c[3] || c[1] + c[2] != sum) return fail("merge incomplete");
-        u.n_keys = c[0];
+        const cudaError_t er = cudaStreamSynchronize(e->stream);
+        cudaFree(tmp.slots);
+        if (er != cudaSuccess) return fail("estimate");
+        distinct = std::min<uint64_t>(sum, std::max<uint64_t>(mx, (uint64_t)((double)(c[0] + c[3]) * 64 * 1.03) + 65536));
+    }
+    uint64_t nb = (uint64_t)((double)distinct / (4.0 * load)) + 2;
+    nb = std::max<uint64_t>(nb, std::max<uint64_t>(1ull << ebu, 16));
+    if (nb >= 0xFFFFFFFFull) return fail("too many buckets");
+    if (cudaMalloc(&u.dev.slots, nb * 32) != cudaSuccess) { u.dev.slots = nullptr; return fail("allocation"); }
+    u.dev.n_buckets = (uint32_t)nb;
+    u.capacity = distinct;
+    pk_launch_fill_empty(u.dev.slots, nb * 4, e->stream);
+    cudaMemsetAsync(e->d_ucounters, 0, sizeof c, e->stream);
+    for (uint32_t g = g0; g < g0 + ng; g++)
+        pk_launch_union_merge(e->tabs[g].dev, e->tabs[g].dev.n_buckets, 0, e->ks, u.dev, g - g0, g, use_stash, e->d_ucounters, e->stream);
+    if (use_stash) pk_launch_union_merge_stash(e->ks, u.dev, g0, ng, e->d_ucounters, e->stream);
+    cudaMemcpyAsync(c, e->d_ucounters, sizeof c, cudaMemcpyDeviceToHost, e->stream);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail("merge");
+    // every per-genome key must have arrived: bits set + stashed == sum of the genomes' key counts
+    if (c[3] || c[1] + c[2] != sum) return fail("merge incomplete");
+    u.n_keys = c[0];
+    u.reserved = true;
+    if (e->group_only) {
+        for (uint32_t g = g0; g < g0 + ng; g++) {
+            cudaFree(e->tabs[g].dev.slots);
+            e->tabs[g].dev = PkTable{nullptr, 0, 0};
+            e->tabs[g].sealed = true;
+        }
+    }
+    return 1;
+}
+
+extern "C" int pk_engine_seal_group(pk_engine *e, uint32_t group) {
+    if (!e) { pk_set_error("null engine"); return PK_EINVAL; }
+    const uint32_t n_groups = (e->n_local + PK_GROUP - 1) / PK_GROUP;
+    if (group >= n_groups) { pk_set_error("group %u out of range (%u groups of 8 local genomes)", group, n_groups); return PK_EINVAL; }
+    if (!e->union_tables) { pk_set_error("group tables are switched off"); return PK_ESTATE; }
+    int rc = set_device(e); if (rc) return rc;
+    const uint32_t g0 = group * PK_GROUP, ng = std::min(PK_GROUP, e->n_local - g0);
+    for (uint32_t g = g0; g < g0 + ng; g++)
+        if (!e->tabs[g].reserved) { rc = pk_engine_reserve(e, e->cfg.genome_begin + g, 0); if (rc) return rc; }
+    rc = refresh_counts(e); if (rc) return rc;
+    rc = build_group(e, group);
+    if (rc < 0) return rc;
+    if (rc == 0) { pk_set_error("group table %u could not be built (see stderr)", group); return PK_ENOMEM; }
+    e->finalized = false;
+    return PK_OK;
+}
+
+static int build_group_tables(pk_engine *e) {
+    const uint32_t n_groups = (e->n_local + PK_GROUP - 1) / PK_GROUP;
+    e->h_utables.clear();
+    if (!e->union_tables) { drop_group_tables(e); return PK_OK; }
+    for (uint32_t gi = 0; gi < n_groups; gi++) {
+        const int rc = build_group(e, gi);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            if (e->group_only) { pk_set_error("group table %u could not be built and group_only is set (see stderr)", gi); return PK_ENOMEM; }
+            drop_group_tables(e);          // not an error for the caller: the per-genome tables answer everything
+            return PK_OK;
+        }
     }
     e->h_utables.resize(n_groups);
     for (uint32_t gi = 0; gi < n_groups; gi++) e->h_utables[gi] = e->utabs[gi].dev;
+    if (!e->d_utables) CU(cudaMalloc(&e->d_utables, sizeof(PkTable) * n_groups));
+    CU(cudaMemcpy(e->d_utables, e->h_utables.data(), sizeof(PkTable) * n_groups, cudaMemcpyHostToDevice));
     return PK_OK;
 }
 
@@ -467,19 +580,10 @@ extern "C" int pk_engine_finalize(pk_engine *e) {
             rc = pk_engine_reserve(e, e->cfg.genome_begin + i, 0); if (rc) return rc;
         }
     }
-    std::vector<unsigned long long> c(3 * e->n_local);
-    CU(cudaMemcpyAsync(c.data(), e->d_counters, c.size() * 8, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    for (uint32_t i = 0; i < e->n_local; i++) {
-        e->tabs[i].n_keys = c[3 * i]; e->tabs[i].n_overflow = c[3 * i + 1];
-        if (c[3 * i + 2]) {
-            pk_set_error("genome %u: table too small (%llu keys did not fit a table reserved for %llu)",
-                         e->cfg.genome_begin + i, c[3 * i + 2], (unsigned long long)e->tabs[i].capacity);
-            return PK_ENOMEM;
-        }
-    }
+    rc = refresh_counts(e); if (rc) return rc;
     rc = upload_tables(e); if (rc) return rc;
     rc = build_group_tables(e); if (rc) return rc;
+    rc = upload_tables(e); if (rc) return rc;          // sealed genomes: null descriptors
     e->finalized = true;
     return PK_OK;
 }
@@ -605,12 +709,53 @@ extern "C" int pk_gather_interleave_device(pk_engine *e, const void *const *d_pl
     return PK_OK;
 }
 
+extern "C" int pk_gather_slice_device(pk_engine *e, const void *const *d_planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w,
+                                      const pk_segment *segs, uint32_t n_segs, void *d_rows, uint32_t row_stride, uint32_t row_bytes,
+                                      void *stream) {
+    if (!e || !d_planes || !d_rows || (!segs && n_segs)) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (n_ranks == 0 || n_ranks > PKG_MAX_RANKS || w == 0) { pk_set_error("n_ranks %u / w %u out of range (<= %d ranks)", n_ranks, w, PKG_MAX_RANKS); return PK_EINVAL; }
+    if (row_bytes == 0 || row_bytes > row_stride || (uint64_t)(n_ranks - 1) * w >= row_bytes) {
+        pk_set_error("row_bytes %u does not fit %u ranks of %u bytes in a stride of %u", row_bytes, n_ranks, w, row_stride);
+        return PK_EINVAL;
+    }
+    for (uint32_t i = 0; i < n_segs; i++)
+        if (segs[i].src_row + segs[i].n_rows > plane_rows) { pk_set_error("segment %u leaves the planes (%llu rows)", i, (unsigned long long)plane_rows); return PK_EINVAL; }
+    if (!n_segs) return PK_OK;
+    int rc = set_device(e); if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    bool same = e->d_segs && e->seg_w == w && e->seg_host.size() == n_segs;
+    for (uint32_t i = 0; same && i < n_segs; i++)
+        same = e->seg_host[i].src_row == segs[i].src_row && e->seg_host[i].n_rows == segs[i].n_rows && e->seg_host[i].dst_row == segs[i].dst_row;
+    if (!same) {
+        // a new list: rare (once per anchor and slice); the upload is synchronous so that seg_host may be rewritten
+        e->seg_host.resize(n_segs);
+        for (uint32_t i = 0; i < n_segs; i++) e->seg_host[i] = PkgSeg{segs[i].src_row, segs[i].n_rows, segs[i].dst_row, 0};
+        e->seg_chunks = pkg_plan_segments(e->seg_host.data(), n_segs, w);
+        e->seg_w = w;
+        if (e->d_segs_cap < n_segs) {
+            CU(cudaDeviceSynchronize());
+            cudaFree(e->d_segs); e->d_segs = nullptr; e->d_segs_cap = 0;
+            CU(cudaMalloc(&e->d_segs, sizeof(PkgSeg) * n_segs));
+            e->d_segs_cap = n_segs;
+        } else {
+            CU(cudaDeviceSynchronize());        // an earlier launch may still read the old list
+        }
+        CU(cudaMemcpy(e->d_segs, e->seg_host.data(), sizeof(PkgSeg) * n_segs, cudaMemcpyHostToDevice));
+    }
+    if (pk_launch_gather_slice(d_planes, n_ranks, plane_rows, w, e->d_segs, n_segs, e->seg_chunks, (uint8_t *)d_rows, row_stride, row_bytes, s)) {
+        pk_set_error("gather_slice launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return PK_ECUDA;
+    }
+    return PK_OK;
+}
+
 // ------------------------------------------------------------------ probe dispatch
 static void free_scratch(pk_engine *e) {
     cudaFree(e->sc.buf1); cudaFree(e->sc.buf2); cudaFree(e->sc.spill);
     cudaFree(e->sc.cursor1); cudaFree(e->sc.cursor2); cudaFree(e->sc.spill_cursor); cudaFree(e->sc.err);
     cudaFree(e->sc.out_list); cudaFree(e->sc.out_cursor);
     e->sc = PkPartScratch{};
+    e->sc.tune = &e->tune; e->sc.last_window = &e->tune.last_window;
     e->sc_plan = PkPartPlan{};
 }
 
@@ -651,10 +796,10 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
         const bool part = mode == 2 || (mode == 0 && m >= (1ull << 20));
         if (part) {
             PkPartPlan pl;
-            pk_part_plan(m, &pl);
+            pk_part_plan(m, e->tune, &pl);
             int rc = ensure_scratch(e, pl); if (rc) return rc;
             if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->h_tables.data(),
-                                            e->h_utables.empty() ? nullptr : e->h_utables.data(), e->n_local,
+                                            e->h_utables.empty() ? nullptr : e->h_utables.data(), e->h_utables.empty() ? nullptr : e->d_utables, e->n_local,
                                             d_rows + o * row_stride, row_stride, col_offset, pl, e->sc, e->l2_prefetch, s, e->pev)) {
                 pk_set_error("partitioned probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return PK_ECUDA;
@@ -663,8 +808,11 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
             e->stats.probe_launches += 1;
             e->pev_valid = true;
         } else {
-            pk_launch_probe(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->n_local, d_rows + o * row_stride,
-                            row_stride, col_offset, s);
+            if (!e->h_utables.empty())
+                pk_launch_probe_group(d_words, d_mask, p0 + o, m, e->ks, e->d_utables, e->n_local, d_rows + o * row_stride, row_stride, col_offset, s);
+            else
+                pk_launch_probe(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->n_local, d_rows + o * row_stride,
+                                row_stride, col_offset, s);
             e->stats.kernel_launches += 1;
             e->stats.probe_launches += 1;
         }
@@ -715,9 +863,35 @@ static int ensure_bgzf_tables(pk_engine *e) {
     return PK_OK;
 }
 
+// rank-local half of the genome-sharded path (pk_anchor_genome_plane): rows go to a caller-owned device plane in
+// the concatenated numbering, nothing is reduced or copied back
+struct PlaneOut { uint8_t *d_plane; uint64_t plane_rows; };
+
+// destroys the per-chromosome events of one anchor_genome_impl call on every way out
+struct EventBag {
+    std::vector<cudaEvent_t> ev;
+    ~EventBag() { for (auto x : ev) if (x) cudaEventDestroy(x); }
+};
+
+// Layout of an anchor in the concatenated ("cat") numbering all device buffers of one call use: chromosome c
+// starts at cat_off[c], a multiple of 32 bases (it owns whole packed words), with at least one 'N' before it,
+// so no window spans two chromosomes. Returns the total length (= rows a plane needs).
+static uint64_t anchor_layout(uint32_t n_chroms, const uint64_t *lens, uint64_t *cat_off) {
+    uint64_t ltot = 0;
+    for (uint32_t c = 0; c < n_chroms; c++) {
+        if (cat_off) cat_off[c] = ltot;
+        ltot = (ltot + lens[c] + 1 + 31) & ~31ull;
+    }
+    return ltot;
+}
+extern "C" uint64_t pk_anchor_layout(uint32_t n_chroms, const uint64_t *lens, uint64_t *cat_off) {
+    if (n_chroms && !lens) return 0;
+    return anchor_layout(n_chroms, lens, cat_off);
+}
+
 static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
                               uint8_t *const *bitmap1, uint8_t *const *bitmap_low, uint64_t *const *bin_hist,
-                              uint64_t *col_sums, uint64_t *nkmers_out, const BgzfOut *z) {
+                              uint64_t *col_sums, uint64_t *nkmers_out, const BgzfOut *z, const PlaneOut *plane = nullptr) {
     NEED_FINAL(e);
     if (n_chroms && (!seqs || !lens)) { pk_set_error("null argument"); return PK_EINVAL; }
     const uint32_t k = e->cfg.k, step = e->cfg.lowres_step, rb = e->row_bytes, N = e->n_local;
@@ -729,7 +903,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     for (uint32_t c = 0; c < n_chroms; c++) {
         if (!seqs[c] && lens[c]) { pk_set_error("null sequence %u", c); return PK_EINVAL; }
         off[c] = ltot;
-        ltot = (ltot + lens[c] + 1 + 31) & ~31ull;
+        ltot = (ltot + lens[c] + 1 + 31) & ~31ull;      // == anchor_layout()
         nk[c] = lens[c] >= k ? lens[c] - k + 1 : 0;        // len < k: nothing (kmc_file.cpp:878-882)
         binlen[c] = nk[c] ? pk_bin_len(&e->cfg, nk[c]) : 0;
         const bool want_hist = bin_hist && bin_hist[c] && nk[c];
@@ -784,7 +958,12 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     rc = grow(e->g_ascii, e->g_ascii_cap, ltot + 64); if (rc) return rc;
     rc = grow(e->g_words, e->g_words_cap, nw); if (rc) return rc;
     rc = grow(e->g_mask, e->g_mask_cap, nw); if (rc) return rc;
-    rc = grow(e->g_rows, e->g_rows_cap, ltot * rb); if (rc) return rc;
+    if (plane) {
+        if (!plane->d_plane || plane->plane_rows < ltot) { pk_set_error("plane of %llu rows is too small for %llu", (unsigned long long)plane->plane_rows, (unsigned long long)ltot); return PK_EINVAL; }
+    } else {
+        rc = grow(e->g_rows, e->g_rows_cap, ltot * rb); if (rc) return rc;
+    }
+    uint8_t *const rows_all = plane ? plane->d_plane : e->g_rows;
     rc = grow(e->g_low, e->g_low_cap, (lowtot + 1) * rb); if (rc) return rc;
     rc = grow(e->d_hist, e->hist_cap, histtot + 1); if (rc) return rc;
     if (!e->ev[0]) for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
@@ -793,9 +972,10 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     cudaStream_t s = e->stream, cs = e->copy_stream, hs = e->in_stream;
     const uint32_t mode = e->cfg.probe_mode;
     const uint64_t sub = e->cfg.chunk_positions ? e->cfg.chunk_positions : PK_PART_MAX_N;
-    const bool pipelined = (mode == 2 || (mode == 0 && npos >= (1ull << 20))) && npos <= sub;
-    std::vector<cudaEvent_t> in_done(n_chroms, nullptr), done(n_chroms, nullptr);
-    auto cleanup = [&]() { for (auto ev : in_done) if (ev) cudaEventDestroy(ev); for (auto ev : done) if (ev) cudaEventDestroy(ev); };
+    bool pipelined = mode == 2 || (mode == 0 && npos >= (1ull << 20));
+    EventBag bag_in, bag_done;
+    bag_in.ev.assign(n_chroms, nullptr); bag_done.ev.assign(n_chroms, nullptr);
+    std::vector<cudaEvent_t> &in_done = bag_in.ev, &done = bag_done.ev;
     CU(cudaEventRecord(e->ev[0], s));
     CU(cudaStreamWaitEvent(hs, e->ev[0], 0));
     // ---- H2D on the input stream, chromosome by chromosome
@@ -811,11 +991,15 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     // best for the kernels; but with ONE batch nothing overlaps the first H2D and the last D2H (2.7 + 1.3 ms of
     // an 11.1 ms call on configs[1], profiles/r1f_bench.json). Two batches of whole chromosomes let the copy
     // engines run under the other batch's kernels while the tables are still read only twice.
+    // A batch is one partitioned launch: at most `sub` positions (PK_PART_MAX_N, or the chunk_positions knob). A
+    // genome beyond that gets more batches; a single chromosome beyond it takes the sub-launch loop of probe_any.
     struct Batch { uint32_t c0, c1; uint64_t base, npos; PkPartPlan pl; };
     std::vector<Batch> batches;
-    {
-        uint32_t nb = 1;
-        if (pipelined && e->e2e_batches > 1 && npos >= e->e2e_batch_min) nb = (uint32_t)e->e2e_batches;
+    uint32_t nb = 1;
+    if (pipelined && e->e2e_batches > 1 && npos >= e->e2e_batch_min) nb = (uint32_t)e->e2e_batches;
+    if (pipelined && npos > sub) nb = std::max<uint32_t>(nb, (uint32_t)((npos + sub - 1) / sub));
+    for (int attempt = 0; attempt < 4; attempt++) {
+        batches.clear();
         uint32_t c = 0;
         for (uint32_t b = 0; b < nb && c < n_chroms; b++) {
             // cut after the chromosome at which the running length first reaches (b+1)/nb of the total
@@ -830,22 +1014,27 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
             batches.push_back(bt);
         }
         if (!batches.empty()) batches.back().c1 = n_chroms;
+        uint64_t mxb = 0;
+        for (const Batch &bt : batches) mxb = std::max(mxb, bt.npos);
+        if (!pipelined || mxb <= sub) break;
+        if (attempt == 3 || nb >= n_chroms) { pipelined = false; nb = 1; attempt = 2; continue; }   // one last pass lays out the single batch
+        nb = std::min<uint32_t>(n_chroms, nb * 2);
     }
     if (pipelined) {
         PkPartPlan mx{};
         for (auto &bt : batches) {
-            pk_part_plan(bt.npos ? bt.npos : 1, &bt.pl);
+            pk_part_plan(bt.npos ? bt.npos : 1, e->tune, &bt.pl);
             mx.buf1_items = std::max(mx.buf1_items, bt.pl.buf1_items); mx.buf2_items = std::max(mx.buf2_items, bt.pl.buf2_items);
             mx.spill_items = std::max(mx.spill_items, bt.pl.spill_items);
             mx.n_regions1 = std::max(mx.n_regions1, bt.pl.n_regions1); mx.n_regions2 = std::max(mx.n_regions2, bt.pl.n_regions2);
             mx.out_shift = std::max(mx.out_shift, bt.pl.out_shift);
         }
-        rc = ensure_scratch(e, mx); if (rc) { cleanup(); return rc; }
+        rc = ensure_scratch(e, mx); if (rc) return rc;
     }
     bool first = true;
     for (const Batch &bt : batches) {
         const PkPartPlan &pl = bt.pl;
-        uint8_t *rows_b = e->g_rows + bt.base * rb;
+        uint8_t *rows_b = rows_all + bt.base * rb;
         if (pipelined) pk_part_begin(N, pl, e->sc, s);
         // ---- pack (+ K1 of the partitioned probe) per chromosome as soon as its bytes are on the device
         for (uint32_t c = bt.c0; c < bt.c1; c++) {
@@ -860,11 +1049,12 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
         }
         if (first) { CU(cudaEventRecord(e->ev[1], s)); CU(cudaEventRecord(e->ev[2], s)); }
         if (pipelined) {
-            pk_part_probe(e->g_words, e->g_mask, bt.base, e->ks, e->h_tables.data(), e->h_utables.empty() ? nullptr : e->h_utables.data(), N, rows_b, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
+            pk_part_probe(e->g_words, e->g_mask, bt.base, e->ks, e->h_tables.data(), e->h_utables.empty() ? nullptr : e->h_utables.data(),
+                          e->h_utables.empty() ? nullptr : e->d_utables, N, rows_b, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
             e->stats.kernel_launches += (pl.pb2 ? 1 : 0) + 2 * ((N + 31) / 32);
             e->stats.probe_launches += 1;
         } else {
-            rc = probe_any(e, e->g_words, e->g_mask, 0, npos, e->g_rows, rb, 0, s); if (rc) { cleanup(); return rc; }
+            rc = probe_any(e, e->g_words, e->g_mask, 0, npos, rows_all, rb, 0, s); if (rc) return rc;
         }
         if (first) CU(cudaEventRecord(e->ev[3], s));
         first = false;
@@ -880,7 +1070,8 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
                     next_bin = b1;
                 }
             }
-            const uint8_t *rows_c = e->g_rows + off[c] * rb;
+            if (plane) continue;                    // the caller exchanges, reduces and stores (genome-sharded path)
+            const uint8_t *rows_c = rows_all + off[c] * rb;
             uint8_t *low_c = e->g_low + lowoff[c] * rb;
             const bool want_low = (bitmap_low && bitmap_low[c]) || z;
             if (nbins[c] || col_sums || want_low) {
@@ -911,7 +1102,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
         CU(cudaMemcpyAsync(tot, e->z_totals, sizeof tot, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         for (int i = 0; i < 2; i++) {
-            if (tot[2 * i] > z->gz_cap[i] || tot[2 * i + 1] > z->gzi_cap[i]) { cleanup(); pk_set_error("BGZF image larger than its bound (internal error)"); return PK_ECUDA; }
+            if (tot[2 * i] > z->gz_cap[i] || tot[2 * i + 1] > z->gzi_cap[i]) { pk_set_error("BGZF image larger than its bound (internal error)"); return PK_ECUDA; }
             CU(cudaMemcpyAsync(z->gz[i], e->z_gz[i], tot[2 * i], cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(z->gzi[i], e->z_gzi[i], tot[2 * i + 1], cudaMemcpyDeviceToHost, s));
             z->sizes[2 * i] = tot[2 * i]; z->sizes[2 * i + 1] = tot[2 * i + 1];
@@ -931,7 +1122,6 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     CU(cudaStreamSynchronize(cs));
     CU(cudaEventRecord(e->ev[5], s));
     CU(cudaEventSynchronize(e->ev[5]));
-    cleanup();
     rc = check_part_error(e); if (rc) return rc;
     for (uint32_t c = 0; c < n_chroms; c++)
         if (nbins[c]) memcpy(bin_hist[c], hist_h.data() + histoff[c], nbins[c] * (N + 1) * 8);
@@ -958,6 +1148,13 @@ extern "C" int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char
                                      uint64_t *sizes, uint64_t *const *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out) {
     const BgzfOut z{gz, gz_cap, gzi, gzi_cap, sizes};
     return anchor_genome_impl(e, n_chroms, seqs, lens, nullptr, nullptr, bin_hist, col_sums, nkmers_out, &z);
+}
+
+extern "C" int pk_anchor_genome_plane(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
+                                      void *d_plane, uint64_t plane_rows, uint64_t *nkmers_out) {
+    if (!d_plane) { pk_set_error("null argument"); return PK_EINVAL; }
+    const PlaneOut p{(uint8_t *)d_plane, plane_rows};
+    return anchor_genome_impl(e, n_chroms, seqs, lens, nullptr, nullptr, nullptr, nullptr, nkmers_out, nullptr, &p);
 }
 
 extern "C" uint64_t pk_bgzf_bound(uint64_t n_bytes) { return pk_bgzf_bound_impl(n_bytes); }
@@ -1028,14 +1225,18 @@ extern "C" int pk_get_counters_for_read(pk_engine *e, uint32_t dbi, const char *
 extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     if (!e || !name) { pk_set_error("null argument"); return PK_EINVAL; }
     const std::string n(name);
-    if (n == "k3_window") g_tune_window = value;
-    else if (n == "k3w_variant") g_tune_wvariant = value;
-    else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } g_tune_wstages = value; }
-    else if (n == "k3_variant") { pk_part_set_variant(value); return PK_OK; }
+    if (n == "k3_window") { e->tune.window = value; return PK_OK; }
+    else if (n == "k3w_variant") { if (value >= -1 && value < pk_part_n_wvariants()) e->tune.wvariant = value; return PK_OK; }
+    else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } e->tune.wgroup = value; return PK_OK; }
+    else if (n == "k3_variant") { if (value >= -1 && value < pk_part_n_variants()) e->tune.variant = value; return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
     else if (n == "group_tables") {        // 0: per-genome tables only; takes effect at the next pk_engine_finalize
         e->union_tables = value ? 1 : 0;
         if (!value) drop_group_tables(e);
+        return PK_OK;
+    }
+    else if (n == "group_only") {          // free per-genome tables once their group table is built (finalize / seal_group)
+        e->group_only = value ? 1 : 0;
         return PK_OK;
     }
     else if (n == "e2e_batch_min") { e->e2e_batch_min = value < 0 ? 0 : (uint64_t)value; return PK_OK; }
@@ -1050,7 +1251,6 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
         return PK_OK;
     }
     else { pk_set_error("unknown tuning knob '%s'", name); return PK_EINVAL; }
-    pk_part_set_window(g_tune_window, g_tune_wvariant, g_tune_wstages);
     return PK_OK;
 }
 
@@ -1058,7 +1258,7 @@ extern "C" int pk_engine_stats(const pk_engine *e, pk_stats *out) {
     if (!e || !out) { pk_set_error("null argument"); return PK_EINVAL; }
     *out = e->stats;
     out->k_partition_ms = out->k_fine_ms = out->k_probe_ms = out->k_spill_ms = out->k_unpermute_ms = 0.f;
-    out->k_probe_window = (float)pk_part_last_window();
+    out->k_probe_window = (float)e->tune.last_window;
     if (e->pev_valid) {      // kernels of the last partitioned launch, timed on their own stream
         CU(cudaEventSynchronize(e->pev[5]));
         CU(cudaEventElapsedTime(&out->k_unpermute_ms, e->pev[4], e->pev[5]));

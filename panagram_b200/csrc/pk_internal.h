@@ -86,6 +86,8 @@ struct PkDecodeArgs {
     unsigned long long *d_counters;   // [3 * n_local]: inserted, overflow, fail per local genome
 };
 void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s);
+void pk_launch_count_bits(const uint8_t *d_recs, uint64_t n, uint32_t rec_size, uint32_t suf_size, uint32_t counter_size, uint64_t min_count,
+                          uint64_t max_count, unsigned long long *d_bits, pk_stream_t s);
 // merge a per-genome table into its group table (genome bit `bit`); see pk_kernels.cu
 void pk_launch_union_merge(PkTable src, uint32_t n_src_buckets, uint32_t hshift, PkKeySpec ks, PkTable dst, uint32_t bit, uint32_t g_local,
                            int use_stash, unsigned long long *d_counters /*[4]*/, pk_stream_t s);
@@ -93,6 +95,11 @@ void pk_launch_union_merge_stash(PkKeySpec ks, PkTable dst, uint32_t g0, uint32_
 void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
                      const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                      uint32_t col_offset, pk_stream_t s);
+void pk_launch_probe_group(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
+                           const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, pk_stream_t s);
+void pk_launch_items_group(const void *d_buf, const uint32_t *d_counts, const unsigned long long *d_flat_total, uint32_t n_regions, uint64_t cap,
+                           const uint64_t *d_words, uint64_t p0, PkKeySpec ks, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
+                           uint32_t row_stride, uint32_t col_offset, pk_stream_t s);
 void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
                       uint64_t binlen, unsigned long long *d_bin_hist, unsigned long long *d_col_sums,
                       uint8_t *d_rows_low, uint32_t step, pk_stream_t s);
@@ -100,6 +107,8 @@ void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n,
                           uint32_t row_stride, pk_stream_t s);
 int pk_launch_gather_interleave(const void *const *planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,
                                 uint32_t row_stride, pk_stream_t s);
+int pk_launch_gather_slice(const void *const *planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w, const void *d_segs,
+                           uint32_t n_segs, uint64_t n_chunks, uint8_t *d_rows, uint32_t row_stride, uint32_t row_bytes, pk_stream_t s);
 void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
                            uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
 
@@ -114,13 +123,26 @@ void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_o
                     unsigned long long *d_totals, uint8_t *d_scratch, const uint32_t *d_tables, pk_stream_t s);
 
 // ---- partitioned probe (pk_partition.cu) ----
-#define PK_PART_MAX_N (512ull << 20)   // positions per partitioned launch (2^18 partitions of <= 2560 mean fill)
+// positions per partitioned launch: 2^18 fine partitions (9 + 9 radix bits, PT_MAXB = 512 digits per pass) of a
+// mean fill of 640 = 5/6 of the K3 block capacity of 768. A longer launch would overflow the fixed-capacity
+// regions en masse into the spill list, so longer batches are cut into sub-launches.
+#define PK_PART_MAX_N (640ull << 18)
 struct PkPartPlan {
     uint32_t pb1, pb2, cap1, cap2, n_regions1, n_regions2;
     uint64_t buf1_items, buf2_items, spill_items;   // 8-byte (hash, pos) items
     uint32_t out_shift, out_bins;                   // un-permute lists: out_bins bins of 2^out_shift positions
 };
+// tuning state of the partitioned probe: per engine (two engines of one process — thread per GPU — do not share it)
+struct PkPartTune {
+    int variant = -1;       // L1/L2 kernel variant, -1 auto
+    int window = 1;         // 0: never use the window kernels
+    int wvariant = -1;      // window kernel variant, -1 auto
+    int wgroup = 0;         // genomes per window group (2 * group stage buffers); 0 = by window size
+    int last_window = 0;    // K3 of the last launch: 2 window kernel on group tables, 1 on per-genome tables, 3 L1/L2 on group tables, 0 L1/L2 kernel
+};
 struct PkPartScratch {
+    const PkPartTune *tune;                         // never NULL on the engine's paths
+    int *last_window;
     void *buf1, *buf2, *spill;
     uint32_t *cursor1, *cursor2;
     unsigned long long *spill_cursor;
@@ -130,21 +152,20 @@ struct PkPartScratch {
     uint64_t out_items;
 };
 uint32_t pk_part_obins(void);
-void pk_part_set_variant(int v);
-int pk_part_last_window(void);
-void pk_part_set_window(int enable, int variant, int stages);   // TMA-staged K3 (PK_K3_WINDOW / PK_K3W_VARIANT / PK_K3W_STAGES)
-void pk_part_plan(uint64_t n, PkPartPlan *pl);
+int pk_part_n_variants(void);
+int pk_part_n_wvariants(void);
+void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl);
 void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
 void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t off, uint64_t n, PkKeySpec ks,
                     uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
                     const PkPartScratch &sc, pk_stream_t s);
 void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, const PkTable *h_tables,
-                   const PkTable *h_utables /*group tables, one per 8 local genomes, or NULL*/, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                   const PkTable *h_utables /*group tables, one per 8 local genomes, or NULL*/, const PkTable *d_utables /*the same on the device*/, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
                    const PkPartScratch &sc, int prefetch, pk_stream_t s, struct CUevent_st **evs);
 void pk_part_unpermute(uint32_t bin0, uint32_t bin1, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                        uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
-                                const PkTable *d_tables, const PkTable *h_tables, const PkTable *h_utables, uint32_t n_local, uint8_t *d_rows,
+                                const PkTable *d_tables, const PkTable *h_tables, const PkTable *h_utables, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
                                 uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
                                 int prefetch, pk_stream_t s, struct CUevent_st **evs /*6 events or NULL*/);
 #endif

@@ -11,6 +11,7 @@
 
 #include "pk_internal.h"
 #include "pk_device.cuh"
+#include "pk_gather.cuh"
 
 // ------------------------------------------------------------------ fill / pack
 __global__ void __launch_bounds__(256) fill_empty_kernel(ulonglong2 *slots2, uint64_t n2) {
@@ -213,6 +214,41 @@ void pk_launch_decode_insert(const PkDecodeArgs &a, pk_stream_t s) {
     decode_insert_kernel<<<grid_for(a.n), 256, 0, s>>>(a);
 }
 
+// per-bit popcount of the counters of a bitvec database (counter bit j = genome first + j): how many k-mers each of
+// its <= 32 genomes has, so that every table is sized for its own genome
+__global__ void __launch_bounds__(256) count_bits_kernel(const uint8_t *__restrict__ recs, uint64_t n, uint32_t rec_size, uint32_t suf_size,
+                                                         uint32_t counter_size, uint64_t min_count, uint64_t max_count,
+                                                         unsigned long long *__restrict__ bits) {
+    __shared__ unsigned int sh[32];
+    if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x; i0 < n; i0 += stride) {
+        const uint64_t i = i0 + threadIdx.x;
+        uint64_t cnt = 0;
+        if (i < n) {
+            const uint8_t *rec = recs + i * rec_size + suf_size;
+            for (uint32_t b = 0; b < counter_size; b++) cnt |= (uint64_t)rec[b] << (8 * b);
+            if (cnt < min_count || cnt > max_count) cnt = 0;
+        }
+        const uint32_t c32 = (uint32_t)cnt;
+        uint32_t mine = 0;
+        for (uint32_t j = 0; j < 32; j++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (c32 >> j) & 1);
+            if (lane == j) mine = __popc(m);
+        }
+        if (mine) atomicAdd(&sh[lane], mine);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&bits[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+void pk_launch_count_bits(const uint8_t *d_recs, uint64_t n, uint32_t rec_size, uint32_t suf_size, uint32_t counter_size, uint64_t min_count,
+                          uint64_t max_count, unsigned long long *d_bits, pk_stream_t s) {
+    if (!n) return;
+    count_bits_kernel<<<grid_for(n), 256, 0, s>>>(d_recs, n, rec_size, suf_size, counter_size, min_count, max_count, d_bits);
+}
+
 // ------------------------------------------------------------------ group tables (derived at finalize)
 // Merge one per-genome table into its group table: every stored k-mer is re-derived from its slot (S64: the slot
 // is the k-mer; S32: low 28 bits from the slot, the other bits from the HOME bucket = bucket - displacement, by
@@ -356,6 +392,67 @@ void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p
         if (n_local <= 4) probe_kernel<4, PK_FMT_S64><<<grid, 256, 0, s>>>(d_words, m64, p0, n, ks, d_tables, n_local, d_rows, row_stride, col_offset);
         else probe_kernel<8, PK_FMT_S64><<<grid, 256, 0, s>>>(d_words, m64, p0, n, ks, d_tables, n_local, d_rows, row_stride, col_offset);
     }
+}
+
+// Direct probe out of the GROUP tables (one bucket read answers 8 genomes): used for small batches whenever the
+// group tables exist, and the only direct path once the per-genome tables have been freed (group_only).
+// Row byte u = membership mask of group u.
+__global__ void __launch_bounds__(256) probe_group_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ mask64,
+                                                          uint64_t p0, uint64_t n, PkKeySpec ks, const PkTable *__restrict__ utables,
+                                                          uint32_t n_local, uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t col_offset) {
+    const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
+    if (i >= n) return;
+    uint64_t canon = 0;
+    const bool valid = pk_window(words, mask64, p0 + i, ks.k, canon);
+    const uint32_t h = pk_key_hash(canon, ks);
+    uint8_t *dst = rows + i * row_stride + col_offset;
+    const uint32_t n_groups = (n_local + PK_U_GROUP - 1) / PK_U_GROUP;
+    for (uint32_t u = 0; u < n_groups; u++) {
+        uint32_t m = 0;
+        if (valid) m = pk_u_lookup(utables[u], canon, h, PK_U_GROUP * u, min(PK_U_GROUP, n_local - PK_U_GROUP * u), ks);
+        dst[u] = (uint8_t)m;
+    }
+}
+void pk_launch_probe_group(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
+                           const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, pk_stream_t s) {
+    if (!n) return;
+    probe_group_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_words, (const uint64_t *)d_mask, p0, n, ks, d_utables, n_local, d_rows,
+                                                                   row_stride, col_offset);
+}
+// (hash, position) items of the partitioned probe answered out of the group tables through L1/L2, rows written
+// directly (such a position appears in no un-permute list). Two uses: the SPILL list (counts == NULL: one flat
+// list of *flat_total items — items beyond a region's capacity, repeat-rich sequence), and whole REGIONS when a
+// partition's table window is too large to be staged in shared memory piece by piece (short batches against
+// large tables) — the probes of a region still fall inside one window of each table, so they hit L2.
+__global__ void __launch_bounds__(256) items_group_kernel(const uint2 *__restrict__ buf, const uint32_t *__restrict__ counts,
+                                                          const unsigned long long *__restrict__ flat_total, uint32_t n_regions, uint64_t cap,
+                                                          const uint64_t *__restrict__ words, uint64_t p0, PkKeySpec ks,
+                                                          const PkTable *__restrict__ utables, uint32_t n_local, uint8_t *__restrict__ rows,
+                                                          uint32_t row_stride, uint32_t col_offset) {
+    const uint32_t n_groups = (n_local + PK_U_GROUP - 1) / PK_U_GROUP;
+    auto one = [&](const uint2 it) {
+        const uint64_t canon = pk_canon_at(words, p0 + it.y, ks.k);
+        uint8_t *dst = rows + (uint64_t)it.y * row_stride + col_offset;
+        for (uint32_t u = 0; u < n_groups; u++)
+            dst[u] = (uint8_t)pk_u_lookup(utables[u], canon, it.x, PK_U_GROUP * u, min(PK_U_GROUP, n_local - PK_U_GROUP * u), ks);
+    };
+    if (!counts) {
+        const unsigned long long n = min(*flat_total, (unsigned long long)cap);
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n; q += stride) one(buf[q]);
+    } else {
+        for (uint64_t r = blockIdx.x; r < n_regions; r += gridDim.x) {
+            const uint32_t cnt = (uint32_t)min((uint64_t)counts[r], cap);
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) one(buf[r * cap + i]);
+        }
+    }
+}
+void pk_launch_items_group(const void *d_buf, const uint32_t *d_counts, const unsigned long long *d_flat_total, uint32_t n_regions, uint64_t cap,
+                           const uint64_t *d_words, uint64_t p0, PkKeySpec ks, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
+                           uint32_t row_stride, uint32_t col_offset, pk_stream_t s) {
+    const unsigned grid = d_counts ? (n_regions < 148u * 8 ? (n_regions ? n_regions : 1) : 148u * 8) : 148u * 2;
+    items_group_kernel<<<grid, 256, 0, s>>>((const uint2 *)d_buf, d_counts, d_flat_total, n_regions, cap, d_words, p0, ks, d_utables, n_local, d_rows,
+                                            row_stride, col_offset);
 }
 
 // ------------------------------------------------------------------ reduce
@@ -674,6 +771,41 @@ int pk_launch_gather_interleave(const void *const *planes, uint32_t n_ranks, uin
     const uint64_t ntiles = (n + tile - 1) / tile;
     const unsigned grid = (unsigned)(ntiles < 148ull * 6 ? ntiles : 148ull * 6);
     gather_interleave_kernel<<<grid, 256, shmem, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// Position-split exchange (pk_gather.cuh): this rank's slice of the rows out of all ranks' planes, read in place
+// over NVLink. One thread per 16-byte chunk of plane bytes, grid-stride; no shared memory.
+template <int RMAX, int W>
+__global__ void __launch_bounds__(256) gather_slice_kernel(const __grid_constant__ PkgArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < a.n_chunks; t += stride) pkg_gather_chunk<RMAX, W>(a, t);
+}
+template <int RMAX>
+static void gather_slice_launch(const PkgArgs &a, unsigned grid, pk_stream_t s) {
+    switch (a.w) {
+        case 1: gather_slice_kernel<RMAX, 1><<<grid, 256, 0, s>>>(a); break;
+        case 2: gather_slice_kernel<RMAX, 2><<<grid, 256, 0, s>>>(a); break;
+        case 4: gather_slice_kernel<RMAX, 4><<<grid, 256, 0, s>>>(a); break;
+        case 8: gather_slice_kernel<RMAX, 8><<<grid, 256, 0, s>>>(a); break;
+        case 16: gather_slice_kernel<RMAX, 16><<<grid, 256, 0, s>>>(a); break;
+        default: gather_slice_kernel<RMAX, 0><<<grid, 256, 0, s>>>(a); break;
+    }
+}
+int pk_launch_gather_slice(const void *const *planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w, const void *d_segs,
+                           uint32_t n_segs, uint64_t n_chunks, uint8_t *d_rows, uint32_t row_stride, uint32_t row_bytes, pk_stream_t s) {
+    if (!n_chunks) return 0;
+    if (n_ranks > PKG_MAX_RANKS) return -1;
+    PkgArgs a{};
+    for (uint32_t r = 0; r < n_ranks; r++) a.planes[r] = (const uint8_t *)planes[r];
+    a.n_ranks = n_ranks; a.w = w; a.plane_rows = plane_rows; a.segs = (const PkgSeg *)d_segs; a.n_segs = n_segs;
+    a.row_stride = row_stride; a.row_bytes = row_bytes; a.rows = d_rows; a.n_chunks = n_chunks;
+    const uint64_t nb = (n_chunks + 255) / 256;
+    const unsigned grid = (unsigned)(nb < 148ull * 8 ? nb : 148ull * 8);
+    if (n_ranks <= 2) gather_slice_launch<2>(a, grid, s);
+    else if (n_ranks <= 4) gather_slice_launch<4>(a, grid, s);
+    else if (n_ranks <= 8) gather_slice_launch<8>(a, grid, s);
+    else gather_slice_launch<16>(a, grid, s);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -780,10 +780,9 @@ static const K3Variant k3_variants[] = {
 // -1 = auto: per launch (group of <= 32 genomes), bucket-sorted blocks once the sort is amortised over
 // >= 16 genomes (configs[2]: 18.9 vs 19.9 ms), unsorted below (configs[1]: 5.5 vs 6.3 ms). Variants 0 and 1
 // share the block capacity, hence the partition plan.
-static int g_k3_variant = -1;
-void pk_part_set_variant(int v) { if (v >= -1 && v < (int)(sizeof k3_variants / sizeof k3_variants[0])) g_k3_variant = v; }
-static const K3Variant &k3_pick(uint32_t n_genomes_in_launch) {
-    if (g_k3_variant >= 0) return k3_variants[g_k3_variant];
+int pk_part_n_variants(void) { return (int)(sizeof k3_variants / sizeof k3_variants[0]); }
+static const K3Variant &k3_pick(const PkPartTune &tu, uint32_t n_genomes_in_launch) {
+    if (tu.variant >= 0 && tu.variant < pk_part_n_variants()) return k3_variants[tu.variant];
     return k3_variants[n_genomes_in_launch >= 16 ? 1 : 0];
 }
 
@@ -800,22 +799,13 @@ static const K3WinVariant k3w_variants[] = {
 };
 #define PW_MAX_GROUP_STAGE_BYTES 32768u
 #define PW_GROUP_STAGE_TARGET 24576u          // pieces of a group-table window are at most this large
-static int g_k3_window = 1;          // 0: never use the window kernels
-static int g_k3_last_window = 0;     // did the last K3 launch use a window kernel?
-int pk_part_last_window(void) { return g_k3_last_window; }
-static int g_k3w_variant = -1;       // -1 auto
-static int g_k3w_group = 0;          // genomes per window group (2 * group stage buffers); 0 = by window size
-void pk_part_set_window(int enable, int variant, int stages) {
-    g_k3_window = enable;
-    if (variant >= -1 && variant < (int)(sizeof k3w_variants / sizeof k3w_variants[0])) g_k3w_variant = variant;
-    if (stages == 0 || stages == 1 || stages == 2 || stages == 4) g_k3w_group = stages;      // 2 * group stages: a power of two
-}
+int pk_part_n_wvariants(void) { return (int)(sizeof k3w_variants / sizeof k3w_variants[0]); }
 // auto: per-genome tables 6 blocks/SM (profiles/r1e_sweep.json: 5.14 vs 5.32 ms), group tables 4 blocks/SM with up to
 // 64 registers (profiles/r1l_sweep.json: 2.29 vs 3.62 ms — one 20 KB window per block, the probe loop is short and
 // the item registers matter more than occupancy)
-static const K3WinVariant &k3w_pick(uint32_t n_genomes_in_launch, bool group_tables = false) {
+static const K3WinVariant &k3w_pick(const PkPartTune &tu, uint32_t n_genomes_in_launch, bool group_tables = false) {
     (void)n_genomes_in_launch;
-    return k3w_variants[g_k3w_variant >= 0 ? g_k3w_variant : (group_tables ? 0 : 3)];
+    return k3w_variants[tu.wvariant >= 0 && tu.wvariant < pk_part_n_wvariants() ? tu.wvariant : (group_tables ? 0 : 3)];
 }
 // bytes one stage must hold for every table of the launch, or 0 when some window does not fit a stage
 static uint32_t k3w_stage_bytes(const PkTable *tabs, uint32_t ng, uint32_t pb, uint32_t limit) {
@@ -853,9 +843,9 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const uint2 *__restrict_
 // ------------------------------------------------------------------ host orchestration
 static uint32_t ceil_log2(uint64_t v) { uint32_t b = 0; while ((1ull << b) < v) b++; return b; }
 
-void pk_part_plan(uint64_t n, PkPartPlan *pl) {
+void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl) {
     // mean fill <= 5/6 of the K3 block capacity (>= 20% head-room for the Poisson spread)
-    const uint32_t cap = (uint32_t)k3_pick(1).cap;
+    const uint32_t cap = (uint32_t)k3_pick(tune, 1).cap;
     const uint64_t fill = (uint64_t)cap * 5 / 6;
     uint32_t pb = ceil_log2((n + fill - 1) / fill);
     if (pb > 18) pb = 18;
@@ -911,10 +901,13 @@ void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0
 
 // K2 + K3 (+ spill drain) over everything appended so far
 void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, PkKeySpec ks, const PkTable *h_tables,
-                   const PkTable *h_utables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
+                   const PkTable *h_utables, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,
                    const PkPartScratch &sc, int prefetch, pk_stream_t s, cudaEvent_t *evs) {
     const int fi = ks.fmt == PK_FMT_S32 ? 1 : 0;
     const uint32_t n_groups = (n_local + 31) / 32;
+    const PkPartTune &tu = *sc.tune;
+    int lw_dummy = 0;
+    int &last_window = sc.last_window ? *sc.last_window : lw_dummy;
     PartArgs a = make_part_args(d_words, d_mask, p0, ks, n_local, d_rows, row_stride, col_offset, pl, sc);
     if (pl.pb2) {
         dim3 grid((pl.cap1 + PT_TILE - 1) / PT_TILE, pl.n_regions1);
@@ -933,11 +926,12 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     p.out_cursor = sc.out_cursor;
     p.out_shift = pl.out_shift;
     if (evs) cudaEventRecord(evs[2], s);
-    for (uint32_t grp = 0; grp < n_groups; grp++) {       // one launch per group of 32 genomes
+    bool regions_done = false;         // the regions have been answered for ALL genomes by the L1/L2 group kernel
+    for (uint32_t grp = 0; grp < n_groups && !regions_done; grp++) {       // one launch per group of 32 genomes
         const uint32_t ngen = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         p.grp = grp; p.g_first = 32 * grp; p.n_genomes = ngen;
-        g_k3_last_window = 0;
-        if (g_k3_window && h_utables && k3_pick(ngen).cap == k3w_pick(ngen).cap) {
+        last_window = 0;
+        if (tu.window && h_utables && k3_pick(tu, ngen).cap == k3w_pick(tu, ngen).cap) {
             // group tables: one probe per 8 genomes; the launch walks the (<= 4) group tables of its 32 genomes. A
             // window larger than PW_GROUP_STAGE_TARGET is cut into equal pieces that pass through the stages one
             // after the other (every item probes the piece its home bucket lies in).
@@ -959,43 +953,56 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
                     p.t_of[np] = (uint8_t)u; p.c_of[np] = (uint8_t)c; np++;
                 }
             if (ok && np) {
-                const K3WinVariant &wv = k3w_pick(ngen, true);
+                const K3WinVariant &wv = k3w_pick(tu, ngen, true);
                 const uint32_t stage_bytes = (uint32_t)cb * 32, n_stages = np == 1 ? 1 : 2;
                 p.ng = np; p.tbits = PK_U_GROUP; p.chunk_buckets = nch > 1 ? (uint32_t)cb : 0;
                 const int fk = nch > 1 ? 3 : 2;
                 cudaFuncSetAttribute(wv.fn[fk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
                 wv.fn[fk]<<<p.n_regions, wv.threads, (size_t)n_stages * stage_bytes, s>>>(p, stage_bytes, 1, n_stages);
-                g_k3_last_window = 2;
+                last_window = 2;
                 continue;
             }
+        }
+        if (h_utables && d_utables) {
+            // group tables, but this launch's windows cannot be staged (more than 32 pieces: a short batch against
+            // large tables) or the window kernels are switched off: probe the regions through L1/L2, all genomes at once
+            pk_launch_items_group(p.buf, p.counts, nullptr, p.n_regions, p.cap, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset, s);
+            last_window = 3;
+            regions_done = true;
+            continue;
         }
         p.chunk_buckets = 0;
         for (uint32_t g = 0; g < 32; g++) { p.t_of[g] = (uint8_t)g; p.c_of[g] = 0; }
         p.ng = ngen; p.tbits = 1;
         for (uint32_t g = 0; g < p.ng; g++) p.tabs[g] = h_tables[32 * grp + g];
-        const uint32_t stage_bytes = g_k3_window && k3_pick(p.ng).cap == k3w_pick(p.ng).cap ? k3w_stage_bytes(p.tabs, p.ng, p.pb, PW_MAX_STAGE_BYTES) : 0;
+        const uint32_t stage_bytes = tu.window && k3_pick(tu, p.ng).cap == k3w_pick(tu, p.ng).cap ? k3w_stage_bytes(p.tabs, p.ng, p.pb, PW_MAX_STAGE_BYTES) : 0;
         if (stage_bytes) {
-            const K3WinVariant &wv = k3w_pick(p.ng);
+            const K3WinVariant &wv = k3w_pick(tu, p.ng);
             // two genomes per group while four windows stay under ~24 KB (6 blocks/SM), else one: measured on
             // configs[1] (4.1 KB windows: 5.14 vs 5.81 ms) and on k=31 tables (9.2 KB windows: 9.42 vs 7.86 ms)
-            const uint32_t gsz = g_k3w_group ? g_k3w_group : (4 * stage_bytes <= 24576 ? 2 : 1);
+            const uint32_t gsz = tu.wgroup ? tu.wgroup : (4 * stage_bytes <= 24576 ? 2 : 1);
             const size_t dyn = (size_t)2 * gsz * stage_bytes;
             cudaFuncSetAttribute(wv.fn[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
             wv.fn[fi]<<<p.n_regions, wv.threads, dyn, s>>>(p, stage_bytes, gsz, 2 * gsz);
-            g_k3_last_window = 1;
+            last_window = 1;
         } else {
-            const K3Variant &kv = k3_pick(p.ng);
+            const K3Variant &kv = k3_pick(tu, p.ng);
             kv.fn[fi]<<<p.n_regions, kv.threads, 0, s>>>(p);
         }
     }
     if (evs) cudaEventRecord(evs[3], s);
+    if (h_utables && d_utables) {      // drain the spill list (normally empty) out of the group tables
+        pk_launch_items_group(sc.spill, nullptr, sc.spill_cursor, 0, pl.spill_items, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset, s);
+        if (evs) cudaEventRecord(evs[4], s);
+        return;
+    }
     ProbeArgs sp = p;          // drain the spill list (normally empty: the blocks exit at once)
-    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = k3_pick(1).cap; sp.pb = 0;
+    sp.buf = (const uint2 *)sc.spill; sp.counts = nullptr; sp.flat_total = sc.spill_cursor; sp.cap = k3_pick(tu, 1).cap; sp.pb = 0;
     for (uint32_t grp = 0; grp < n_groups; grp++) {
         sp.grp = grp; sp.ng = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         sp.tbits = 1; sp.g_first = 32 * grp; sp.n_genomes = sp.ng;
         for (uint32_t g = 0; g < sp.ng; g++) sp.tabs[g] = h_tables[32 * grp + g];
-        const K3Variant &kv = k3_pick(sp.ng);
+        const K3Variant &kv = k3_pick(tu, sp.ng);
         kv.fn[fi]<<<148 * 2, kv.threads, 0, s>>>(sp);
     }
     if (evs) cudaEventRecord(evs[4], s);
@@ -1011,7 +1018,7 @@ void pk_part_unpermute(uint32_t bin0, uint32_t bin1, uint32_t n_local, uint8_t *
 }
 
 int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
-                                const PkTable *d_tables, const PkTable *h_tables, const PkTable *h_utables, uint32_t n_local, uint8_t *d_rows,
+                                const PkTable *d_tables, const PkTable *h_tables, const PkTable *h_utables, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
                                 uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc,
                                 int prefetch, pk_stream_t s, cudaEvent_t *evs) {
     if (!n) return 0;
@@ -1020,7 +1027,7 @@ int pk_launch_probe_partitioned(const uint64_t *d_words, const uint32_t *d_mask,
     if (evs) cudaEventRecord(evs[0], s);
     pk_part_append(d_words, d_mask, p0, 0, n, ks, n_local, d_rows, row_stride, col_offset, pl, sc, s);
     if (evs) cudaEventRecord(evs[1], s);
-    pk_part_probe(d_words, d_mask, p0, ks, h_tables, h_utables, n_local, d_rows, row_stride, col_offset, pl, sc, prefetch, s, evs);
+    pk_part_probe(d_words, d_mask, p0, ks, h_tables, h_utables, d_utables, n_local, d_rows, row_stride, col_offset, pl, sc, prefetch, s, evs);
     pk_part_unpermute(0, pl.out_bins, n_local, d_rows, row_stride, col_offset, pl, sc, s);
     if (evs) cudaEventRecord(evs[5], s);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -91,6 +91,11 @@ class Engine:
     def finalize(self):
         check(self._L.pk_engine_finalize(self._h))
 
+    def seal_group(self, group: int):
+        """Build the group table of local genomes [8*group, 8*group+8) now; with tune(group_only=1) their
+        per-genome tables are freed (pk_engine_seal_group)."""
+        check(self._L.pk_engine_seal_group(self._h, group))
+
     def table_stats(self, genome: int) -> dict:
         s = PkTableStats()
         check(self._L.pk_engine_table_stats(self._h, genome, C.byref(s)))
@@ -228,14 +233,35 @@ class Engine:
         return {"chroms": chroms, "col_sums": cs, "gz": bufs["gz"][0][:sizes[0]], "gzi": bufs["gzi"][0][:sizes[1]],
                 "gz_low": bufs["gz"][1][:sizes[2]], "gzi_low": bufs["gzi"][1][:sizes[3]], "_bufs": bufs}
 
+    def anchor_layout(self, lens) -> tuple[list[int], int]:
+        """The concatenated row numbering pk_anchor_genome_plane uses: ([first row of every chromosome], rows a
+        plane needs) (pk_anchor_layout)."""
+        n = len(lens)
+        arr = (C.c_uint64 * n)(*[int(l) for l in lens])
+        off = (C.c_uint64 * n)()
+        total = int(self._L.pk_anchor_layout(n, arr, off))
+        return [int(x) for x in off], total
+
+    def anchor_genome_plane(self, seqs, d_plane: int, plane_rows: int) -> list[int]:
+        """H2D + pack + probe of all chromosomes of one anchor into a caller-owned device plane
+        [plane_rows][row_bytes] (pk_anchor_genome_plane: the rank-local half of the genome-sharded path).
+        Returns nkmers per chromosome; complete on return."""
+        arrs = [_u8(s) for s in seqs]
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_uint64 * n)(*[a.size for a in arrs])
+        nko = (C.c_uint64 * n)()
+        check(self._L.pk_anchor_genome_plane(self._h, n, ptrs, lens, d_plane, plane_rows, nko))
+        return [int(x) for x in nko]
+
     def bgzf_bound(self, nbytes: int) -> tuple[int, int]:
         return int(self._L.pk_bgzf_bound(nbytes)), int(self._L.pk_bgzf_gzi_bound(nbytes))
 
     def bgzf_compress_device(self, d_in: int, nbytes: int, match_dist: int, d_gz: int, d_gzi: int, d_totals: int,
-                             stream: int = 0):
+                             stream: int | None = None):
         """Device bytes -> BGZF .gz image + .gzi image + totals (2 x uint64), all on the device."""
         check(self._L.pk_bgzf_compress_device(self._h, d_in or None, nbytes, match_dist, d_gz, d_gzi, d_totals,
-                                              stream or None))
+                                              self._st(stream)))
 
     def get_counters_for_read(self, dbi: int, read) -> np.ndarray | None:
         """uint32 counters of bitvec database `dbi` for every k-mer of `read`
@@ -260,22 +286,32 @@ class Engine:
             check(self._L.pk_engine_tune(self._h, name.encode(), int(value)))
 
     # ---- hot path, device pointers (ints; e.g. torch.Tensor.data_ptr()) ------
+    # `stream`: a cudaStream_t handle as an int (torch.cuda.Stream.cuda_stream). None = the engine's own stream.
+    # 0 is the handle of CUDA's legacy default stream — torch's default stream — and is passed on as such
+    # (cudaStreamLegacy), never silently replaced by the engine's stream: work a caller orders on torch's default
+    # stream stays ordered with the library's kernels.
+    @staticmethod
+    def _st(stream):
+        if stream is None:
+            return None
+        return 1 if stream == 0 else stream          # cudaStreamLegacy == (cudaStream_t)0x1
+
     def packed_words(self, length: int) -> int:
         return int(self._L.pk_packed_words(length))
 
-    def pack_device(self, d_ascii: int, length: int, d_words: int, d_mask: int, stream: int = 0):
-        check(self._L.pk_pack_device(self._h, d_ascii, length, d_words, d_mask, stream or None))
+    def pack_device(self, d_ascii: int, length: int, d_words: int, d_mask: int, stream: int | None = None):
+        check(self._L.pk_pack_device(self._h, d_ascii, length, d_words, d_mask, self._st(stream)))
 
     def probe_device(self, d_words: int, d_mask: int, p0: int, n: int, d_rows: int, row_stride: int,
-                     col_offset: int = 0, stream: int = 0):
+                     col_offset: int = 0, stream: int | None = None):
         check(self._L.pk_probe_device(self._h, d_words, d_mask, p0, n, d_rows, row_stride, col_offset,
-                                      stream or None))
+                                      self._st(stream)))
 
     def reduce_device(self, d_rows: int, row_stride: int, n_cols: int, p_first: int, n: int, binlen: int,
-                      d_hist: int = 0, d_colsums: int = 0, d_low: int = 0, stream: int = 0):
+                      d_hist: int = 0, d_colsums: int = 0, d_low: int = 0, stream: int | None = None):
         check(self._L.pk_reduce_device(self._h, d_rows, row_stride, n_cols, p_first, n, binlen,
                                        d_hist or None, d_colsums or None, d_low or None,
-                                       self.lowres_step, stream or None))
+                                       self.lowres_step, self._st(stream)))
 
     # ---- peer memory (genome-sharded exchange without NCCL) ---------------------
     def device_alloc(self, nbytes: int) -> int:
@@ -301,12 +337,21 @@ class Engine:
         check(self._L.pk_ipc_close(self._h, d_ptr))
 
     def gather_interleave_device(self, plane_ptrs: list[int], n: int, w: int, d_rows: int, row_stride: int,
-                                 stream: int = 0):
+                                 stream: int | None = None):
         arr = (C.c_void_p * len(plane_ptrs))(*plane_ptrs)
         check(self._L.pk_gather_interleave_device(self._h, arr, len(plane_ptrs), n, w, d_rows, row_stride,
-                                                  stream or None))
+                                                  self._st(stream)))
+
+    def gather_slice_device(self, plane_ptrs: list[int], plane_rows: int, w: int, segments, d_rows: int,
+                            row_stride: int, row_bytes: int, stream: int | None = None):
+        """This rank's slice of the rows out of every rank's plane (pk_gather_slice_device).
+        segments: [(src_row, n_rows, dst_row)]."""
+        arr = (C.c_void_p * len(plane_ptrs))(*plane_ptrs)
+        segs = (_lib.PkSegment * len(segments))(*[_lib.PkSegment(int(a), int(b), int(c)) for a, b, c in segments])
+        check(self._L.pk_gather_slice_device(self._h, arr, len(plane_ptrs), plane_rows, w, segs, len(segments),
+                                             d_rows, row_stride, row_bytes, self._st(stream)))
 
     def interleave_device(self, d_planes: int, n_ranks: int, n: int, w: int, d_rows: int, row_stride: int,
-                          stream: int = 0):
+                          stream: int | None = None):
         check(self._L.pk_interleave_device(self._h, d_planes, n_ranks, n, w, d_rows, row_stride,
-                                           stream or None))
+                                           self._st(stream)))

@@ -108,11 +108,8 @@ class Index:
             return "fasta", s["fasta"]
         raise ValueError(f"genome {s['name']}: no FASTA and no KMC database under {kmc}")
 
-    def build_engine(self, genome_begin: int = 0, genome_end: int | None = None, log=print) -> Engine:
-        n = len(self.samples)
-        eng = Engine(self.cfg.k, n, genome_begin, genome_end, device=self.device,
-                     lowres_step=self.cfg.lowres_step, max_bin_kbp=self.cfg.max_bin_kbp,
-                     min_bin_count=self.cfg.min_bin_count, load_factor=self.load_factor)
+    def populate(self, eng: Engine, log=print) -> Engine:
+        """Fill the engine's tables with the k-mer sets of the genomes of its shard, then finalize."""
         done_bitvec = set()
         for s in self.samples:
             if not (eng.genome_begin <= s["id"] < eng.genome_end):
@@ -135,23 +132,64 @@ class Index:
         eng.finalize()
         return eng
 
-    def run(self, log=print) -> dict:
+    def _engine_kw(self) -> dict:
+        return dict(lowres_step=self.cfg.lowres_step, max_bin_kbp=self.cfg.max_bin_kbp,
+                    min_bin_count=self.cfg.min_bin_count, load_factor=self.load_factor)
+
+    def build_engine(self, genome_begin: int = 0, genome_end: int | None = None, log=print) -> Engine:
+        eng = Engine(self.cfg.k, len(self.samples), genome_begin, genome_end, device=self.device, **self._engine_kw())
+        return self.populate(eng, log)
+
+    def run(self, log=print, genome_ranks: int | None = None) -> dict:
         """Index.run (index.py:172-191): config, then — unless --prepare — the anchor rule for every
-        anchor genome."""
-        self.write_config()
+        anchor genome (workflow/Snakefile:33-48; cpp/Snakefile:35-55 runs them in one process,
+        `#pragma omp parallel for` over anchors, cpp/anchor.cpp:217).
+
+        Under torch.distributed (one process per GPU, `python -m panagram_b200 index --gpus R`) the run is
+        genome-sharded: world = Rg x Rp, every group of Rg ranks holds the tables of all genomes between them
+        (rank g the g-th shard) and the Rp groups take the anchors round-robin. Every rank returns the summaries
+        of the anchors its group handled."""
+        import os
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        dist = None
+        if world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("WORLD_SIZE > 1 but torch.distributed is not initialised (use `index --gpus R`)")
+        rank = dist.get_rank() if dist else 0
+        if rank == 0:
+            self.write_config()
         if self.cfg.prepare:
             return {}
-        eng = self.build_engine(log=log)
         names = [s["name"] for s in self.samples]
+        anchors = [s for s in self.samples if s["anchor"]]
         out = {}
-        for s in self.samples:
-            if not s["anchor"]:
+        if not dist:
+            eng = self.build_engine(log=log)
+            for s in anchors:
+                t0 = time.perf_counter()
+                out[s["name"]] = anchor_mod.anchor_fasta(eng, s["name"], s["fasta"], self.prefix / "anchor" / s["name"],
+                                                         genome_names=names, threads=max(1, self.cfg.cores))
+                log(f"Anchored {s['name']}: {out[s['name']]['positions']} positions ({time.perf_counter() - t0:.2f}s)")
+            eng.close()
+            return out
+        from . import sharded
+        sh = sharded.ShardedAnchorer(self.cfg.k, len(self.samples), rank, world, self.device, genome_ranks=genome_ranks,
+                                     **self._engine_kw())
+        qlog = log if sh.gi == 0 else (lambda m: None)
+        self.populate(sh.engine, qlog)
+        dist.barrier()                                   # rank 0 has written the config; every shard is built
+        for j, s in enumerate(anchors):
+            if j % sh.rp != sh.pi:
                 continue
             t0 = time.perf_counter()
-            out[s["name"]] = anchor_mod.anchor_fasta(eng, s["name"], s["fasta"], self.prefix / "anchor" / s["name"],
-                                                     genome_names=names, threads=max(1, self.cfg.cores))
-            log(f"Anchored {s['name']}: {out[s['name']]['positions']} positions ({time.perf_counter() - t0:.2f}s)")
-        eng.close()
+            out[s["name"]] = sharded.anchor_fasta_sharded(sh, s["name"], s["fasta"], self.prefix / "anchor" / s["name"],
+                                                          genome_names=names)
+            qlog(f"Anchored {s['name']} on ranks {sh.pi * sh.rg}..{sh.pi * sh.rg + sh.rg - 1}: "
+                 f"{out[s['name']]['positions']} positions ({time.perf_counter() - t0:.2f}s; {sh.last})")
+        sh.close_p2p()
+        dist.barrier()
+        sh.engine.close()
         return out
 
 

@@ -51,15 +51,17 @@ class BgzfWriter:
         self.pending = bytearray()
         self.coff = 0
         self.uoff = 0
-        self.index: list[tuple[int, int]] = []   # start of every block after the first
+        self.index: list[tuple[int, int]] = []   # start of every block after the first (htslib's write-mode index,
+                                                 # cpp/anchor.cpp:47,102: no entry for the EOF member)
 
     def _emit(self, view: memoryview):
         chunks = [bytes(view[o:o + BGZF_PAYLOAD]) for o in range(0, len(view), BGZF_PAYLOAD)]
         for payload, blk in zip(chunks, self.pool.map(lambda c: _bgzf_block(c, self.level), chunks)):
+            if self.coff:
+                self.index.append((self.coff, self.uoff))
             self.fh.write(blk)
             self.coff += len(blk)
             self.uoff += len(payload)
-            self.index.append((self.coff, self.uoff))
 
     def write(self, data):
         mv = memoryview(data).cast("B")

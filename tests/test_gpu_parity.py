@@ -318,6 +318,159 @@ def test_fused_gather_interleave_kernel(n_ranks, w):
         assert (rows.cpu().numpy() == want).all(), (n_ranks, w, n)
 
 
+@pytest.mark.parametrize("n_ranks,w", [(1, 1), (2, 1), (4, 1), (8, 1), (16, 1), (3, 1), (2, 2), (8, 2), (5, 3), (2, 4), (4, 8), (2, 16)])
+def test_gather_slice_kernel(n_ranks, w):
+    """pk_gather_slice_device (the position-split exchange): rows[dst + i][q*w:(q+1)*w] = planes[q][src + i] for every
+    segment. The planes are ordinary device buffers here — the kernel does not care whether a pointer is peer-mapped
+    — so every store shape runs on one GPU: ragged segments, padded strides, a narrow last shard, the planes' last
+    chunk. (The same per-chunk code runs on the host in tests/test_sharding.py.)"""
+    import torch
+    eng = Engine(21, 1)
+    eng.add_keys(0, np.array([1], dtype=np.uint64))
+    eng.finalize()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(n_ranks * 100 + w)
+    for n in (1, 17, 4096, 100_003, 1_000_000):
+        planes_h = [rng.integers(0, 256, size=(n, w), dtype=np.uint8) for _ in range(n_ranks)]
+        planes = [torch.from_numpy(p).to(dev) for p in planes_h]
+        for variant in range(3):
+            nseg = int(rng.integers(1, 5))
+            cuts = np.sort(rng.integers(0, n + 1, size=2 * nseg))
+            segs, dst = [], 0
+            for j in range(nseg):
+                a, b = int(cuts[2 * j]), int(cuts[2 * j + 1])
+                if variant == 2 and j == nseg - 1:
+                    b = n                                  # reach the planes' last row
+                segs.append((a, b - a, dst))
+                dst += b - a
+            rb = n_ranks * w
+            if variant == 1 and w > 1:
+                rb -= 1                                    # narrow last shard: the row is shorter than n_ranks * w
+            stride = rb + (3 if variant == 1 else 0)
+            rows = torch.full((max(dst, 1), stride), 0xAB, dtype=torch.uint8, device=dev)
+            eng.gather_slice_device([p.data_ptr() for p in planes], n, w, segs, rows.data_ptr(), stride, rb, st)
+            torch.cuda.synchronize()
+            want = np.full((max(dst, 1), stride), 0xAB, dtype=np.uint8)
+            cat = np.concatenate(planes_h, axis=1)[:, :rb]
+            for a, m, d in segs:
+                want[d:d + m, :rb] = cat[a:a + m]
+            assert (rows.cpu().numpy() == want).all(), (n_ranks, w, n, variant, segs)
+
+
+def _shard_engines(genomes, k, n, bounds, **kw):
+    engs = [Engine(k, n, b, e, **kw) for b, e in bounds]
+    for g, chroms in enumerate(genomes):
+        for e in engs:
+            if e.genome_begin <= g < e.genome_end:
+                e.reserve(g, sum(s.size for _, s in chroms))
+                for _, s in chroms:
+                    e.add_sequence(g, s)
+    for e in engs:
+        e.finalize()
+    return engs
+
+
+@pytest.mark.parametrize("n,k,world", [(16, 21, 2), (35, 31, 2), (64, 21, 4)])
+def test_position_split_exchange_on_one_gpu_equals_single_engine(n, k, world):
+    """The genome-sharded product path with the ranks played by shard engines on ONE GPU (no NCCL, no IPC — those
+    are covered by tests/test_multigpu.py on >= 2 GPUs): every shard probes the whole anchor into its plane
+    (pk_anchor_genome_plane), every 'rank' assembles ITS slice out of all planes (pk_gather_slice_device), reduces the
+    chromosome pieces inside it (pk_reduce_device), and deflates it (pk_bgzf_compress_device); the parts are merged
+    with the host logic of sharded.py. Equal to what one engine holding all genomes delivers — the .gz byte for byte."""
+    import torch
+    from panagram_b200 import sharded, synth
+    anc = synth.ancestor_codes(1_500_000 if n <= 35 else 700_000, 77)
+    genomes = [synth.genome_chroms(anc, g, 77, n_chroms=3, n_run=300, lower_run=1000) for g in range(n)]
+    full = _shard_engines(genomes, k, n, [(0, n)])[0]
+    seqs = [s for _, s in genomes[1]]
+    want = full.anchor_genome_bgzf(seqs)
+    want_raw = full.anchor_genome(seqs)
+    bounds = sharded.shard_bounds(n, world)
+    shards = _shard_engines(genomes, k, n, bounds)
+    w, rb, step = sharded.plane_width(n, world), (n + 7) // 8, 100
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    lens = [s.size for s in seqs]
+    cat_off, plane_rows = full.anchor_layout(lens)
+    nks = [l - k + 1 for l in lens]
+    planes = [torch.zeros((plane_rows, w), dtype=torch.uint8, device=dev) for _ in range(world)]
+    for e, pl in zip(shards, planes):
+        assert e.anchor_genome_plane(seqs, pl.data_ptr(), plane_rows) == nks
+    sb = sharded.slice_bounds(sum(nks), rb, world)
+    binlen = [full.bin_len(nk) for nk in nks]
+    nbins = [(nk + b - 1) // b for nk, b in zip(nks, binlen)]
+    hoff = np.concatenate(([0], np.cumsum([nb * (n + 1) for nb in nbins])))
+    nlow = [(nk + step - 1) // step for nk in nks]
+    loff = np.concatenate(([0], np.cumsum(nlow)))
+    red = torch.zeros(int(hoff[-1]) + n, dtype=torch.int64, device=dev)
+    low = torch.zeros((int(loff[-1]), rb), dtype=torch.uint8, device=dev)
+    parts = []
+    with torch.cuda.stream(stream):
+        st = stream.cuda_stream
+        for r, e in enumerate(shards):
+            s0, s1 = sb[r], sb[r + 1]
+            rows = torch.zeros((max(s1 - s0, 1), rb), dtype=torch.uint8, device=dev)
+            segs = sharded.stream_segments(cat_off, nks, s0, s1)
+            if segs:
+                e.gather_slice_device([p.data_ptr() for p in planes], plane_rows, w, segs, rows.data_ptr(), rb, rb, st)
+            for c, p_first, m, r0 in sharded.slice_pieces(nks, s0, s1):
+                l0 = (p_first + step - 1) // step
+                e.reduce_device(rows.data_ptr() + r0 * rb, rb, n, p_first, m, binlen[c], red.data_ptr() + 8 * int(hoff[c]),
+                                red.data_ptr() + 8 * int(hoff[-1]), low.data_ptr() + (int(loff[c]) + l0) * rb, st)
+            nb = (s1 - s0) * rb
+            cap_gz, cap_gzi = e.bgzf_bound(nb)
+            gz = torch.empty(cap_gz, dtype=torch.uint8, device=dev)
+            gzi = torch.empty(cap_gzi // 8 + 1, dtype=torch.int64, device=dev)
+            tot = torch.zeros(2, dtype=torch.int64, device=dev)
+            e.bgzf_compress_device(rows.data_ptr(), nb, rb, gz.data_ptr(), gzi.data_ptr(), tot.data_ptr(), st)
+            t = tot.cpu()
+            parts.append((gz[: int(t[0])].cpu().numpy(), gzi.view(torch.uint8)[: int(t[1])].cpu().numpy(), s0 * rb, nb,
+                          rows[: s1 - s0].cpu().numpy()))
+    torch.cuda.synchronize()
+    rows_all = np.concatenate([p[4] for p in parts])
+    assert rows_all.tobytes() == b"".join(c["bitmap1"].tobytes() for c in want_raw["chroms"])
+    live = [r for r in range(world) if parts[r][3] > 0]
+    offs, total = sharded.merge_bgzf_parts([(parts[r][0].size, parts[r][1].size) for r in live], [parts[r][2] for r in live])
+    out = bytearray(total)
+    for j, r in enumerate(live):
+        d = parts[r][0] if j == len(live) - 1 else parts[r][0][:-sharded.BGZF_EOF_LEN]
+        out[offs[j]:offs[j] + d.size] = d.tobytes()
+    assert bytes(out) == want["gz"].tobytes()
+    gzi = sharded.merge_gzi([parts[r][1].tobytes() for r in live], offs, [parts[r][2] for r in live], [parts[r][3] for r in live])
+    assert gzi == want["gzi"].tobytes()
+    red_h = red.cpu().numpy().astype(np.uint64)
+    for c in range(len(nks)):
+        assert (red_h[int(hoff[c]):int(hoff[c + 1])].reshape(nbins[c], n + 1) == want_raw["chroms"][c]["bin_hist"]).all()
+    assert (red_h[int(hoff[-1]):] == want_raw["col_sums"]).all()
+    assert low.cpu().numpy().tobytes() == b"".join(c["low"].tobytes() for c in want_raw["chroms"])
+
+
+def test_sharded_anchorer_world1_directory_equals_anchor_fasta(pan3, tmp_path):
+    """sharded.anchor_fasta_sharded with a world of one rank (plane -> slice gather -> piece-wise reduce -> BGZF of
+    the slice -> collective file assembly) writes the directory anchor.anchor_fasta writes, which equals the
+    reference's (golden) outputs."""
+    from panagram_b200 import sharded
+    sh = sharded.ShardedAnchorer(pan3["k"], 3, 0, 1, 0)
+    sh.engine.add_bitvec(0, pan3["dir"] / "kmc" / "bitvec0")
+    sh.engine.finalize()
+    eng = Engine(pan3["k"], 3)
+    eng.add_bitvec(0, pan3["dir"] / "kmc" / "bitvec0")
+    eng.finalize()
+    for a in pan3["anchors"]:
+        sharded.anchor_fasta_sharded(sh, a, pan3["fasta"][a], tmp_path / "sh" / a, genome_names=pan3["names"])
+        anchor.anchor_fasta(eng, a, pan3["fasta"][a], tmp_path / "one" / a, genome_names=pan3["names"])
+        files = sorted(p.name for p in (tmp_path / "one" / a).iterdir())
+        assert sorted(p.name for p in (tmp_path / "sh" / a).iterdir()) == files
+        for f in files:
+            assert (tmp_path / "sh" / a / f).read_bytes() == (tmp_path / "one" / a / f).read_bytes(), f
+        exp = pan3["expected"][a]
+        assert layout.read_bgzf(tmp_path / "sh" / a / "bitmap.1.gz") == exp["bitmap.1"]
+        assert layout.read_bgzf(tmp_path / "sh" / a / "bitmap.100.gz") == exp["bitmap.100"]
+        assert (tmp_path / "sh" / a / "bitsum.bins.tsv").read_text() == exp["bitsum.bins.tsv"]
+    sh.close_p2p()
+
+
 def big_case(n_genomes, k, length, seed, repeats=False):
     """A seeded pan-genome too large for the Python oracle loops but fine for the C oracle."""
     from panagram_b200 import synth
