@@ -134,6 +134,17 @@ def make_genome(anc, g, seed):
     return [s for _, s in synth.genome_chroms(anc, g, seed)]
 
 
+REF_MAX_BASES = 1_100_000_000      # the reference arm builds KMC databases for at most this many bases in total
+
+
+def reference_workload(wl, n):
+    """The workload the reference arm runs: the same generator, the same genome count; the genome length is the
+    workload's own while n x length stays within REF_MAX_BASES (configs[1]: 8 x 135 Mbp, in full), shortened beyond
+    that (the KMC build alone would take tens of minutes and ~1 GB of /tmp per genome)."""
+    length = min(wl["length"], REF_MAX_BASES // n)
+    return dict(wl, length=length), length == wl["length"]
+
+
 def n_genomes_of(wl, world):
     return wl["n_total"] if "n_total" in wl else wl["n_per_gpu"] * max(1, world)
 
@@ -392,10 +403,13 @@ def main():
         if rank != 0:
             return
         n = n_genomes_of(wl, args.gpus)
-        r = run_reference(args.steps, args.warmup, wl, n, cores)
+        rwl, full = reference_workload(wl, n)
+        r = run_reference(args.steps, args.warmup, rwl, n, cores)
         if "unavailable" in r:
             print(json.dumps(r)); return
-        cfg = workload_config(wl, args, args.gpus)
+        cfg = workload_config(rwl, args, args.gpus)
+        if not full:
+            r["sample"] = f"genomes shortened from {wl['length'] / 1e6:g} to {rwl['length'] / 1e6:g} Mbp (bounded KMC build); " + r["sample"]
         cfg["positions_per_step"] = r["positions"]
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -540,6 +554,13 @@ def main():
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[-1])
     ks = eng.stats()            # kernels of the last probe launch, CUDA events on the launching stream
+    per_rank = None
+    if world > 1:
+        mine = {"rank": rank, "genomes": [g_begin, g_end], "group_table_bytes": sum((g or {"bytes": 0})["bytes"] for g in gstats),
+                "kernels_ms": {x: round(ks[x], 4) for x in ("k_partition_ms", "k_fine_ms", "k_probe_ms", "k_spill_ms", "k_unpermute_ms")},
+                "step_ms_median": statistics.median(step_ms)}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     exch = None
     if rg > 1 and args.exchange == "slice" and packed:
         p = packed[-1]
@@ -688,7 +709,10 @@ def main():
                                          "probe": ks["k_probe_ms"], "spill": ks["k_spill_ms"], "unpermute": ks["k_unpermute_ms"]}}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = run_reference(1, 0, wl, n_total, cores)
+            rwl, full = reference_workload(wl, n_total)
+            r = run_reference(1, 0, rwl, n_total, cores)
+            if "unavailable" not in r and not full:
+                r["sample"] = f"genomes shortened from {wl['length'] / 1e6:g} to {rwl['length'] / 1e6:g} Mbp (bounded KMC build); " + r["sample"]
             if "unavailable" not in r:
                 cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"],
                        "ms": r["ms_per_step"]}
@@ -714,7 +738,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": cfg, "run": run, "e2e": e2e, "e2e_files": e2e_files, "gpu_launches": int(launches), "roofline": roof,
-                "exchange": exch, "cpu_baseline": cpu, "clocks": clocks, "step_ms": step_ms,
+                "exchange": exch, "per_rank": per_rank, "cpu_baseline": cpu, "clocks": clocks, "step_ms": step_ms,
                 "value_excludes": "pack (ASCII -> 2-bit), reduce and low-res kernels (~0.4 ms per 135 M positions): SURVEY §8d (i) "
                                   "times the probe stage; they are inside `e2e`",
                 "tables": {"keys": [t["n_keys"] for t in tstats], "per_genome_table_bytes": sum(t["bytes"] for t in tstats),

@@ -180,11 +180,12 @@ int pk_anchor_chrom(pk_engine *e, const char *ascii, uint64_t len,
  * genome in one process). pk_anchor_layout: the concatenated ("cat") row numbering one call uses — chromosome c's
  * k-mer p is row cat_off[c] + p; returns the number of rows a plane must hold. pk_anchor_genome_plane: H2D + pack +
  * probe of all chromosomes, pipelined exactly as pk_anchor_genome, with the shard's row bytes written to the
- * caller-owned DEVICE plane [plane_rows][ceil(N_local/8)] (e.g. from pk_device_alloc, IPC-exported to the peers);
- * rows between chromosomes are zero or unwritten. Complete when the call returns. */
+ * caller-owned DEVICE plane [plane_rows][row_stride] (e.g. from pk_device_alloc, IPC-exported to the peers;
+ * row_stride >= ceil(N_local/8): the plane width all ranks share, a narrow last shard leaves its padding bytes
+ * untouched); rows between chromosomes are zero or unwritten. Complete when the call returns. */
 uint64_t pk_anchor_layout(uint32_t n_chroms, const uint64_t *lens, uint64_t *cat_off);
 int pk_anchor_genome_plane(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
-                           void *d_plane, uint64_t plane_rows, uint64_t *nkmers_out);
+                           void *d_plane, uint64_t plane_rows, uint32_t row_stride, uint64_t *nkmers_out);
 
 /* Replaces CKMCFile::GetCountersForRead as the anchoring path calls it on
  * bitvec database `dbi` (cpp/anchor.cpp:148; index.py:932-938):
@@ -289,7 +290,10 @@ int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *se
  * "k3w_variant" (-1 auto, or a kernel variant index), "k3w_group" (0 = by window size, or 1, 2, 4 genomes per window group; two groups of windows are staged per block),
  * "k3_variant" (-1 auto; variant of the L1/L2 kernel), "l2_prefetch" (0/1), "group_tables" (0/1;
  * takes effect at the next pk_engine_finalize), "group_only" (0/1: free a group's per-genome tables once its
- * group table is built; see pk_engine_seal_group), "unpermute" (0/1: applies to
+ * group table is built; see pk_engine_seal_group), "group_g32" (slot format of the group tables: 0 = 64-bit slots,
+ * 1 = 32-bit slots [membership mask 8 | key remainder 20 | displacement 4] when k <= 23 and the table has at least
+ * 2^(2k-20) buckets, which any genome-scale table has — default; 2 = 32-bit slots wherever k allows, small tables
+ * padded to that size), "unpermute" (0/1: applies to
  * scratch allocated afterwards), "e2e_batches" (1..8: batches of whole chromosomes per pk_anchor_genome call;
  * copies of one batch overlap the kernels of the other), "e2e_batch_min" (positions from which a genome is
  * split into batches; default 32 Mi). Unknown names return PK_EINVAL. */

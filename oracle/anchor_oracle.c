@@ -262,6 +262,29 @@ int pko_get_counters_for_read(const pko_db *db, const char *read, uint64_t len, 
     return 1;
 }
 
+/* Every canonical k-mer of a sequence, window by window — what `kmc -ci1 -fm` counts for a FASTA record
+   (kmc_core/splitter.cpp:44-47: only ACGTacgt are symbols, every other byte ends the current super-k-mer; canonical
+   form = min(kmer, reverse complement), kmer_api.h:373-386) — with the same fill/slide structure as
+   pko_get_counters_for_read above. Windows holding a non-ACGT byte yield nothing. out may be NULL to only count;
+   duplicates are NOT removed (the caller sorts and uniques). Returns the number of k-mers written. */
+uint64_t pko_kmers_of_seq(const char *seq, uint64_t len, uint32_t k, uint64_t *out) {
+    if (len < k) return 0;
+    const uint64_t mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    uint64_t kmer = 0, rev = 0, n = 0;
+    uint32_t pos = 0;
+    for (uint64_t i = 0; i < len; i++) {
+        int c = code_of((unsigned char)seq[i]);
+        if (c < 0) { pos = 0; kmer = 0; rev = 0; continue; }
+        kmer = ((kmer << 2) | (uint64_t)c) & mask;
+        rev = (rev >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
+        if (++pos >= k) {
+            if (out) out[n] = kmer < rev ? kmer : rev;
+            n++;
+        }
+    }
+    return n;
+}
+
 /* Listing of every (canonical k-mer, counter) record, as CKMCFile::ReadNextKmer
    decodes them (kmc_file.cpp:421-490) with the LUT slot -> prefix mapping of
    kmc_file.h:89 / CPrefixFileBufferForListingMode (prefix = slot mod 4^lut for

@@ -44,6 +44,8 @@ def lib():
         L.pko_get_counters_for_read.argtypes = [vp, C.c_char_p, C.c_uint64, u32p]
         L.pko_db_list.restype = C.c_uint64
         L.pko_db_list.argtypes = [vp, u64p, u32p]
+        L.pko_kmers_of_seq.restype = C.c_uint64
+        L.pko_kmers_of_seq.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, u64p]
         L.pko_binlen.restype = C.c_uint64
         L.pko_binlen.argtypes = [C.c_uint64]
         L.pko_anchor_chrom.restype = C.c_uint64
@@ -117,6 +119,28 @@ class OracleDB:
         counts = np.empty(self.total_kmers, dtype=np.uint32)
         n = lib().pko_db_list(self.h, _p(kmers, C.c_uint64), _p(counts, C.c_uint32))
         return kmers[:n], counts[:n]
+
+
+def canonical_kmers(seqs, k: int) -> np.ndarray:
+    """Sorted distinct canonical k-mer integers of a list of sequences (bytes / uint8 arrays): the set K_g that
+    `kmc -k -ci1 -fm` produces for a FASTA (pko_kmers_of_seq in C, then sort + unique). ctypes releases the GIL."""
+    parts = []
+    for s in seqs:
+        b = s.tobytes() if isinstance(s, np.ndarray) else bytes(s)
+        if len(b) < k:
+            continue
+        out = np.empty(len(b) - k + 1, dtype=np.uint64)
+        n = lib().pko_kmers_of_seq(b, len(b), k, _p(out, C.c_uint64))
+        parts.append(out[:n])
+    if not parts:
+        return np.zeros(0, dtype=np.uint64)
+    x = np.sort(np.concatenate(parts))            # np.unique's hash path is ~50x slower than sort + compare here
+    if x.size == 0:
+        return x
+    keep = np.empty(x.size, dtype=bool)
+    keep[0] = True
+    np.not_equal(x[1:], x[:-1], out=keep[1:])
+    return x[keep]
 
 
 def binlen(nkmers: int) -> int:

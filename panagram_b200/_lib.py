@@ -87,7 +87,7 @@ SIGNATURES = {
     "pk_anchor_genome": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pk_anchor_chrom": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _pu64]),
     "pk_anchor_layout": (_u64, [_u32, _vp, _vp]),
-    "pk_anchor_genome_plane": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _u64, _vp]),
+    "pk_anchor_genome_plane": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _u64, _u32, _vp]),
     "pk_get_counters_for_read": (C.c_int, [_vp, _u32, _vp, _u64, _vp, _pu64]),
     "pk_host_alloc": (C.c_int, [_pp, _sz]),
     "pk_host_free": (C.c_int, [_vp]),

@@ -192,6 +192,82 @@ __device__ __forceinline__ uint32_t pk_u_lookup(const PkTable t, uint64_t canon,
         b = b + 1 == t.n_buckets ? 0 : b + 1;
     }
 }
+// ---- G32: the compact group-table format for short k-mers --------------------------------------------------
+// slot = 32 bits = [membership mask 8][key remainder 20][displacement 4], 8 slots per 32 B bucket, EMPTY = ~0.
+// The other eb = 2k - 20 key bits are implied by the home bucket, as in the S32 per-genome format: the group
+// tables are then indexed by their OWN hash (pk_g32_hash: top eb bits = hi ^ f(lo20)), which needs n_buckets >=
+// 2^eb — true for any genome-scale table at the default k = 21 (eb = 22: >= 4 Mi buckets = 128 MB). Half the bytes
+// per key of the 64-bit slots: the probe kernel, which streams its table once per launch, reads half as much.
+// PkTable.fmt says which format a group table has (all group tables of an engine share it); PkKeySpec.ghash != 0
+// tells the kernels of a launch that positions are hashed with pk_g32_hash.
+#define PK_G32_REM_BITS 20
+#define PK_G32_REM_MASK 0x000FFFFFu
+#define PK_G32_KEY_MASK 0x00FFFFFFu
+#define PK_G32_MASK_SHIFT 24
+#define PK_TFMT_G64 0u
+#define PK_TFMT_G32 1u
+__device__ __forceinline__ uint32_t pk_g32_hash(uint64_t canon, uint32_t k) {
+    const uint32_t lo = (uint32_t)canon & PK_G32_REM_MASK, m = pk_mix32(lo);
+    const uint32_t eb = 2 * k > PK_G32_REM_BITS ? 2 * k - PK_G32_REM_BITS : 0;
+    if (eb == 0) return m;
+    const uint32_t hi = (uint32_t)(canon >> PK_G32_REM_BITS);
+    return ((hi ^ ((m * 0x9E3779B1u) >> (32 - eb))) << (32 - eb)) | (eb < 32 ? m >> eb : 0u);
+}
+// the hash the positions of a probe launch are partitioned and probed by
+__device__ __forceinline__ uint32_t pk_probe_hash(uint64_t canon, const PkKeySpec ks) {
+    return ks.ghash ? pk_g32_hash(canon, ks.k) : pk_key_hash(canon, ks);
+}
+__device__ __forceinline__ uint32_t pk_g32_key(uint64_t canon, uint32_t r) { return (((uint32_t)canon & PK_G32_REM_MASK) << PK_S32_DISP_BITS) | r; }
+__device__ __forceinline__ uint32_t pk_g32_bucket_mask(const u64x4 &v, uint32_t key24) {
+    const uint32_t s[8] = {(uint32_t)v.a, (uint32_t)(v.a >> 32), (uint32_t)v.b, (uint32_t)(v.b >> 32),
+                           (uint32_t)v.c, (uint32_t)(v.c >> 32), (uint32_t)v.d, (uint32_t)(v.d >> 32)};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if ((s[i] & PK_G32_KEY_MASK) == key24) m |= s[i] >> PK_G32_MASK_SHIFT;
+    return m;
+}
+__device__ __forceinline__ uint32_t pk_g32_lookup(const PkTable t, uint64_t canon, uint32_t h, uint32_t g0, uint32_t ng, const PkKeySpec ks) {
+    uint32_t b = __umulhi(h, t.n_buckets);
+    const uint32_t maxd = pk_u_max_disp(t.n_buckets);
+    for (uint32_t r = 0;; r++) {
+        const u64x4 v = pk_ld_bucket_ca((const char *)t.slots + 32ull * b);
+        const uint32_t m = pk_g32_bucket_mask(v, pk_g32_key(canon, r));
+        if (m) return m;
+        if ((uint32_t)(v.d >> 32) == PK_EMPTY32) return 0;
+        if (r == maxd) {
+            uint32_t sm = 0;
+            for (uint32_t g = 0; g < ng; g++) sm |= (uint32_t)pk_stash_contains(ks, g0 + g, canon) << g;
+            return sm;
+        }
+        b = b + 1 == t.n_buckets ? 0 : b + 1;
+    }
+}
+// as pk_u_insert
+__device__ __forceinline__ int pk_g32_insert(const PkTable t, uint64_t canon, uint32_t h, uint32_t bit) {
+    uint32_t b = __umulhi(h, t.n_buckets);
+    const uint32_t maxd = pk_u_max_disp(t.n_buckets);
+    const uint32_t mbit = 1u << (PK_G32_MASK_SHIFT + bit);
+    for (uint32_t r = 0; r <= maxd; r++) {
+        const uint32_t key24 = pk_g32_key(canon, r);
+        uint32_t *slot = (uint32_t *)t.slots + 8ull * b;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t cur = *(volatile uint32_t *)(slot + i);
+            if (cur == PK_EMPTY32) {
+                cur = atomicCAS(slot + i, PK_EMPTY32, key24 | mbit);
+                if (cur == PK_EMPTY32) return r == 0 ? 2 : 3;
+            }
+            if ((cur & PK_G32_KEY_MASK) == key24) return (atomicOr(slot + i, mbit) & mbit) ? 0 : 1;
+        }
+        b = b + 1 == t.n_buckets ? 0 : b + 1;
+    }
+    return 4;
+}
+// format-dispatching forms (t.fmt)
+__device__ __forceinline__ uint32_t pk_group_lookup(const PkTable t, uint64_t canon, uint32_t h, uint32_t g0, uint32_t ng, const PkKeySpec ks);
+__device__ __forceinline__ int pk_group_insert(const PkTable t, uint64_t canon, uint32_t h, uint32_t bit);
+
 // set genome bit `bit` (0..7) of `canon` in group table t. 0 = bit was already set, 1 = set in an existing slot,
 // 2 = new slot in the home bucket, 3 = new slot in a later bucket, 4 = no room within 15 buckets (caller stashes)
 __device__ __forceinline__ int pk_u_insert(const PkTable t, uint64_t canon, uint32_t h, uint32_t bit) {
@@ -213,5 +289,11 @@ __device__ __forceinline__ int pk_u_insert(const PkTable t, uint64_t canon, uint
         b = b + 1 == t.n_buckets ? 0 : b + 1;
     }
     return 4;
+}
+__device__ __forceinline__ uint32_t pk_group_lookup(const PkTable t, uint64_t canon, uint32_t h, uint32_t g0, uint32_t ng, const PkKeySpec ks) {
+    return t.fmt == PK_TFMT_G32 ? pk_g32_lookup(t, canon, h, g0, ng, ks) : pk_u_lookup(t, canon, h, g0, ng, ks);
+}
+__device__ __forceinline__ int pk_group_insert(const PkTable t, uint64_t canon, uint32_t h, uint32_t bit) {
+    return t.fmt == PK_TFMT_G32 ? pk_g32_insert(t, canon, h, bit) : pk_u_insert(t, canon, h, bit);
 }
 #endif

@@ -54,6 +54,8 @@ struct pk_engine {
     PkTable *d_utables = nullptr;               // the same descriptors on the device (direct probe, spill)
     int union_tables = 1;
     int group_only = 0;                         // free the per-genome tables once their group table is built
+    int allow_g32 = 1;                          // 32-bit group slots where k and the table size allow (pk_device.cuh, G32)
+    int gfmt = -1;                              // format of this engine's group tables: -1 undecided, 0 G64, 1 G32
     unsigned long long *d_ucounters = nullptr;  // [4]
     unsigned long long *d_counters = nullptr;   // [3 * n_local]
     bool finalized = false;
@@ -79,6 +81,7 @@ struct pk_engine {
     PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
     PkPartPlan sc_plan{};
     int l2_prefetch = 1;
+    int rows_persist = 0;                       // direct row scatter (unpermute 0): keep the rows of a launch in persisting L2
     unsigned long long *d_colsums = nullptr;    // [n_local]
     // staging for KMC ingestion
     uint8_t *h_stage = nullptr, *d_stage = nullptr;
@@ -162,6 +165,7 @@ extern "C" int pk_engine_create(const pk_config *cfg, pk_engine **out) {
     if (const char *pf = getenv("PK_L2_PREFETCH")) e->l2_prefetch = atoi(pf);
     if (const char *up = getenv("PK_UNPERMUTE")) e->unpermute = atoi(up);
     if (const char *ut = getenv("PK_GROUP_TABLES")) e->union_tables = atoi(ut) ? 1 : 0;
+    if (const char *g3 = getenv("PK_GROUP_G32")) e->allow_g32 = atoi(g3) ? 1 : 0;
     if (const char *kv = getenv("PK_K3_VARIANT")) { const int v = atoi(kv); if (v >= -1 && v < pk_part_n_variants()) e->tune.variant = v; }
     {
         const char *we = getenv("PK_K3_WINDOW"), *wv = getenv("PK_K3W_VARIANT"), *ws = getenv("PK_K3W_GROUP");
@@ -257,6 +261,9 @@ static int touch_genome(pk_engine *e, uint32_t g_local) {
         cudaFree(e->utabs[gi].dev.slots);
         e->utabs[gi] = HostTable{};
         e->h_utables.clear();
+        bool any = false;
+        for (auto &u : e->utabs) any = any || u.reserved;
+        if (!any) e->gfmt = -1;
     }
     e->finalized = false;
     return PK_OK;
@@ -451,6 +458,13 @@ static void drop_group_tables(pk_engine *e) {
     for (auto &t : e->utabs) cudaFree(t.dev.slots);
     e->utabs.clear();
     e->h_utables.clear();
+    e->gfmt = -1;
+}
+// the key spec of a probe launch: positions are hashed for the tables the launch probes
+static PkKeySpec probe_ks(const pk_engine *e) {
+    PkKeySpec ks = e->ks;
+    ks.ghash = (!e->h_utables.empty() && e->gfmt == 1) ? 20u : 0u;
+    return ks;
 }
 static int refresh_counts(pk_engine *e) {
     std::vector<unsigned long long> c(3 * e->n_local);
@@ -508,11 +522,21 @@ static int build_group(pk_engine *e, uint32_t gi) {
         if (er != cudaSuccess) return fail("estimate");
         distinct = std::min<uint64_t>(sum, std::max<uint64_t>(mx, (uint64_t)((double)(c[0] + c[3]) * 64 * 1.03) + 65536));
     }
-    uint64_t nb = (uint64_t)((double)distinct / (4.0 * load)) + 2;
-    nb = std::max<uint64_t>(nb, std::max<uint64_t>(1ull << ebu, 16));
+    // slot format, one for all group tables of the engine (they share the hash of a launch): G32 (32-bit slots, 8 per
+    // bucket, 2k - 20 key bits implied by the home bucket) when the first group's table has at least 2^(2k-20) buckets
+    // at its natural size — any genome-scale table at k <= 23 — or k is so short that the minimum is tiny; later
+    // (smaller) groups are padded to that minimum
+    const uint32_t ebg = 2 * e->cfg.k > 20 ? 2 * e->cfg.k - 20 : 0;
+    const uint64_t nb32 = (uint64_t)((double)distinct / (8.0 * std::min(0.5, (double)e->cfg.load_factor))) + 2;
+    if (e->gfmt < 0)
+        e->gfmt = (e->allow_g32 && use_stash && ebg <= 26 && (ebg <= 12 || nb32 >= (1ull << ebg) || e->allow_g32 == 2)) ? 1 : 0;
+    uint64_t nb;
+    if (e->gfmt == 1) nb = std::max<uint64_t>(nb32, std::max<uint64_t>(1ull << ebg, 16));
+    else nb = std::max<uint64_t>((uint64_t)((double)distinct / (4.0 * load)) + 2, std::max<uint64_t>(1ull << ebu, 16));
     if (nb >= 0xFFFFFFFFull) return fail("too many buckets");
     if (cudaMalloc(&u.dev.slots, nb * 32) != cudaSuccess) { u.dev.slots = nullptr; return fail("allocation"); }
     u.dev.n_buckets = (uint32_t)nb;
+    u.dev.fmt = (uint32_t)e->gfmt;
     u.capacity = distinct;
     pk_launch_fill_empty(u.dev.slots, nb * 4, e->stream);
     cudaMemsetAsync(e->d_ucounters, 0, sizeof c, e->stream);
@@ -779,7 +803,7 @@ static int ensure_scratch(pk_engine *e, const PkPartPlan &pl) {
     CU(cudaMemset(e->sc.err, 0, sizeof(uint32_t)));
     if (out_items) {
         CU(cudaMalloc(&e->sc.out_list, out_items * 8));
-        CU(cudaMalloc(&e->sc.out_cursor, sizeof(uint32_t) * n_groups * pk_part_obins()));
+        CU(cudaMalloc(&e->sc.out_cursor, sizeof(uint32_t) * n_groups * pk_part_ocursor_words()));
     }
     e->sc.out_items = out_items;
     e->sc_plan = pl;
@@ -798,7 +822,25 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
             PkPartPlan pl;
             pk_part_plan(m, e->tune, &pl);
             int rc = ensure_scratch(e, pl); if (rc) return rc;
-            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->h_tables.data(),
+            if (e->rows_persist && !e->unpermute) {
+                // experiment: the launch's rows (m * row_stride bytes, scattered byte by byte by K3) as a persisting-L2
+                // window, so that a 32-byte sector is written to DRAM once, complete, instead of once per byte
+                int dev = e->cfg.device, maxp = 0, maxw = 0;
+                cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+                cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
+                cudaStreamAttrValue av{};
+                const size_t nbytes = std::min<size_t>((size_t)m * row_stride, (size_t)maxw);
+                av.accessPolicyWindow.base_ptr = d_rows + o * row_stride;
+                av.accessPolicyWindow.num_bytes = nbytes;
+                av.accessPolicyWindow.hitRatio = nbytes <= (size_t)maxp ? 1.0f : (float)maxp / (float)nbytes;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+                static bool said = false;
+                if (!said) { fprintf(stderr, "[pkanchor] rows_persist: max persisting L2 %d MB, max window %d MB, window %zu MB, hit ratio %.2f\n", maxp >> 20, maxw >> 20, nbytes >> 20, av.accessPolicyWindow.hitRatio); said = true; }
+            }
+            if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, probe_ks(e), e->d_tables, e->h_tables.data(),
                                             e->h_utables.empty() ? nullptr : e->h_utables.data(), e->h_utables.empty() ? nullptr : e->d_utables, e->n_local,
                                             d_rows + o * row_stride, row_stride, col_offset, pl, e->sc, e->l2_prefetch, s, e->pev)) {
                 pk_set_error("partitioned probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -809,7 +851,7 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
             e->pev_valid = true;
         } else {
             if (!e->h_utables.empty())
-                pk_launch_probe_group(d_words, d_mask, p0 + o, m, e->ks, e->d_utables, e->n_local, d_rows + o * row_stride, row_stride, col_offset, s);
+                pk_launch_probe_group(d_words, d_mask, p0 + o, m, probe_ks(e), e->d_utables, e->n_local, d_rows + o * row_stride, row_stride, col_offset, s);
             else
                 pk_launch_probe(d_words, d_mask, p0 + o, m, e->ks, e->d_tables, e->n_local, d_rows + o * row_stride,
                                 row_stride, col_offset, s);
@@ -865,7 +907,7 @@ static int ensure_bgzf_tables(pk_engine *e) {
 
 // rank-local half of the genome-sharded path (pk_anchor_genome_plane): rows go to a caller-owned device plane in
 // the concatenated numbering, nothing is reduced or copied back
-struct PlaneOut { uint8_t *d_plane; uint64_t plane_rows; };
+struct PlaneOut { uint8_t *d_plane; uint64_t plane_rows; uint32_t row_stride; };
 
 // destroys the per-chromosome events of one anchor_genome_impl call on every way out
 struct EventBag {
@@ -964,6 +1006,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
         rc = grow(e->g_rows, e->g_rows_cap, ltot * rb); if (rc) return rc;
     }
     uint8_t *const rows_all = plane ? plane->d_plane : e->g_rows;
+    const uint32_t rs = plane ? plane->row_stride : rb;         // bytes between rows of rows_all
     rc = grow(e->g_low, e->g_low_cap, (lowtot + 1) * rb); if (rc) return rc;
     rc = grow(e->d_hist, e->hist_cap, histtot + 1); if (rc) return rc;
     if (!e->ev[0]) for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
@@ -1034,7 +1077,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     bool first = true;
     for (const Batch &bt : batches) {
         const PkPartPlan &pl = bt.pl;
-        uint8_t *rows_b = rows_all + bt.base * rb;
+        uint8_t *rows_b = rows_all + bt.base * rs;
         if (pipelined) pk_part_begin(N, pl, e->sc, s);
         // ---- pack (+ K1 of the partitioned probe) per chromosome as soon as its bytes are on the device
         for (uint32_t c = bt.c0; c < bt.c1; c++) {
@@ -1043,18 +1086,18 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
             pk_launch_pack(e->g_ascii + off[c], ltot + 64 - off[c], w1 - w0, e->g_words + w0, e->g_mask + w0, s);
             e->stats.kernel_launches += 1;
             if (pipelined && nk[c]) {
-                pk_part_append(e->g_words, e->g_mask, bt.base, off[c] - bt.base, nk[c], e->ks, N, rows_b, rb, 0, pl, e->sc, s);
+                pk_part_append(e->g_words, e->g_mask, bt.base, off[c] - bt.base, nk[c], probe_ks(e), N, rows_b, rs, 0, pl, e->sc, s);
                 e->stats.kernel_launches += 1;
             }
         }
         if (first) { CU(cudaEventRecord(e->ev[1], s)); CU(cudaEventRecord(e->ev[2], s)); }
         if (pipelined) {
-            pk_part_probe(e->g_words, e->g_mask, bt.base, e->ks, e->h_tables.data(), e->h_utables.empty() ? nullptr : e->h_utables.data(),
-                          e->h_utables.empty() ? nullptr : e->d_utables, N, rows_b, rb, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
+            pk_part_probe(e->g_words, e->g_mask, bt.base, probe_ks(e), e->h_tables.data(), e->h_utables.empty() ? nullptr : e->h_utables.data(),
+                          e->h_utables.empty() ? nullptr : e->d_utables, N, rows_b, rs, 0, pl, e->sc, e->l2_prefetch, s, nullptr);
             e->stats.kernel_launches += (pl.pb2 ? 1 : 0) + 2 * ((N + 31) / 32);
             e->stats.probe_launches += 1;
         } else {
-            rc = probe_any(e, e->g_words, e->g_mask, 0, npos, rows_all, rb, 0, s); if (rc) return rc;
+            rc = probe_any(e, e->g_words, e->g_mask, 0, npos, rows_all, rs, 0, s); if (rc) return rc;
         }
         if (first) CU(cudaEventRecord(e->ev[3], s));
         first = false;
@@ -1065,7 +1108,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
             if (pipelined && e->sc.out_list) {
                 const uint32_t b1 = (uint32_t)((off[c] - bt.base + nk[c] - 1) >> pl.out_shift) + 1;
                 if (b1 > next_bin) {
-                    pk_part_unpermute(next_bin, b1, N, rows_b, rb, 0, pl, e->sc, s);
+                    pk_part_unpermute(next_bin, b1, N, rows_b, rs, 0, pl, e->sc, s);
                     e->stats.kernel_launches += 1;
                     next_bin = b1;
                 }
@@ -1151,9 +1194,10 @@ extern "C" int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char
 }
 
 extern "C" int pk_anchor_genome_plane(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
-                                      void *d_plane, uint64_t plane_rows, uint64_t *nkmers_out) {
-    if (!d_plane) { pk_set_error("null argument"); return PK_EINVAL; }
-    const PlaneOut p{(uint8_t *)d_plane, plane_rows};
+                                      void *d_plane, uint64_t plane_rows, uint32_t row_stride, uint64_t *nkmers_out) {
+    if (!e || !d_plane) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (row_stride < e->row_bytes) { pk_set_error("row_stride %u below the shard's %u row bytes", row_stride, e->row_bytes); return PK_EINVAL; }
+    const PlaneOut p{(uint8_t *)d_plane, plane_rows, row_stride};
     return anchor_genome_impl(e, n_chroms, seqs, lens, nullptr, nullptr, nullptr, nullptr, nkmers_out, nullptr, &p);
 }
 
@@ -1228,11 +1272,20 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     if (n == "k3_window") { e->tune.window = value; return PK_OK; }
     else if (n == "k3w_variant") { if (value >= -1 && value < pk_part_n_wvariants()) e->tune.wvariant = value; return PK_OK; }
     else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } e->tune.wgroup = value; return PK_OK; }
+    else if (n == "k3_rank_atomic") { e->tune.rank_atomic = value ? 1 : 0; return PK_OK; }
+    else if (n == "rows_persist") { e->rows_persist = value ? 1 : 0; return PK_OK; }
     else if (n == "k3_variant") { if (value >= -1 && value < pk_part_n_variants()) e->tune.variant = value; return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
     else if (n == "group_tables") {        // 0: per-genome tables only; takes effect at the next pk_engine_finalize
+        if (!value)
+            for (auto &t : e->tabs)
+                if (t.sealed) { pk_set_error("per-genome tables were freed (group_only): the group tables cannot be dropped"); return PK_ESTATE; }
         e->union_tables = value ? 1 : 0;
-        if (!value) drop_group_tables(e);
+        if (!value) drop_group_tables(e);       // the per-genome tables answer from here on
+        return PK_OK;
+    }
+    else if (n == "group_g32") {           // 0: 64-bit group slots whatever k; 1: 32-bit slots where k and the table size allow; 2: wherever k
+        e->allow_g32 = value < 0 ? 0 : value > 2 ? 2 : value;   // allows, small tables padded to 2^(2k-20) buckets (tests). Takes effect when the group tables are next built from scratch
         return PK_OK;
     }
     else if (n == "group_only") {          // free per-genome tables once their group table is built (finalize / seal_group)

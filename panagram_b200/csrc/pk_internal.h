@@ -30,7 +30,7 @@ void pk_kmcdb_close_impl(pk_kmcdb *db);
 struct PkTable {
     unsigned long long *slots;
     uint32_t n_buckets;
-    uint32_t _pad;
+    uint32_t fmt;               // group tables: 0 = 64-bit slots (G64), 1 = 32-bit slots (G32, pk_device.cuh); 0 for per-genome tables
 };
 
 #define PK_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -54,7 +54,7 @@ struct PkKeySpec {
     uint32_t k;
     uint32_t fmt;       // PK_FMT_*
     uint32_t eb;        // S32: key bits embedded in the bucket index = max(0, 2k - 28)
-    uint32_t _pad;
+    uint32_t ghash;     // != 0: this launch hashes positions with pk_g32_hash (its group tables are G32)
     unsigned long long *stash;      // [PK_STASH_SLOTS], EMPTY-initialised (S32 only)
     unsigned int *stash_n;          // number of stashed keys
 };
@@ -138,6 +138,7 @@ struct PkPartTune {
     int window = 1;         // 0: never use the window kernels
     int wvariant = -1;      // window kernel variant, -1 auto
     int wgroup = 0;         // genomes per window group (2 * group stage buffers); 0 = by window size
+    int rank_atomic = 0;    // window kernel: shared-memory-atomic ranking of the results (1) or warp match_any (0)
     int last_window = 0;    // K3 of the last launch: 2 window kernel on group tables, 1 on per-genome tables, 3 L1/L2 on group tables, 0 L1/L2 kernel
 };
 struct PkPartScratch {
@@ -152,6 +153,7 @@ struct PkPartScratch {
     uint64_t out_items;
 };
 uint32_t pk_part_obins(void);
+uint32_t pk_part_ocursor_words(void);
 int pk_part_n_variants(void);
 int pk_part_n_wvariants(void);
 void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl);

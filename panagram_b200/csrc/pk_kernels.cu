@@ -290,7 +290,10 @@ __global__ void __launch_bounds__(256) union_merge_kernel(PkTable src, uint32_t 
             h = pk_key_hash(canon, ks);
         }
         (void)i;
-        const int r = pk_u_insert(dst, canon, h << hshift, bit);      // hshift: a 2^-hshift prefix of the hash range fills all of dst
+        // hshift: a 2^-hshift prefix of the (per-genome) hash range fills all of dst. A G32 table has its own hash: the
+        // prefix of the source buckets is then simply a uniform sample of the keys (the same one in every genome)
+        const uint32_t hd = dst.fmt == PK_TFMT_G32 ? pk_g32_hash(canon, ks.k) : h << hshift;
+        const int r = pk_group_insert(dst, canon, hd, bit);
         created += r >= 2 && r <= 3; set += r >= 1 && r <= 3;
         if (r == 4) {
             // counted by union_merge_stash_kernel, which runs after all table merges and sees every stash entry
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(256) union_merge_stash_kernel(PkKeySpec ks, Pk
     const uint32_t g = (uint32_t)(e >> 48);
     if (g < g0 || g >= g0 + ng) return;
     const uint64_t canon = e & 0x0000FFFFFFFFFFFFull;
-    const int r = pk_u_insert(dst, canon, pk_key_hash(canon, ks), g - g0);
+    const int r = pk_group_insert(dst, canon, dst.fmt == PK_TFMT_G32 ? pk_g32_hash(canon, ks.k) : pk_key_hash(canon, ks), g - g0);
     if (r == 2 || r == 3) atomicAdd(counters, 1ull);
     if (r >= 1 && r <= 3) atomicAdd(counters + 1, 1ull);
     if (r == 4) atomicAdd(counters + 2, 1ull);                // stays in the stash, found there by pk_u_lookup
@@ -404,12 +407,12 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const uint64_t *__rest
     if (i >= n) return;
     uint64_t canon = 0;
     const bool valid = pk_window(words, mask64, p0 + i, ks.k, canon);
-    const uint32_t h = pk_key_hash(canon, ks);
+    const uint32_t h = pk_probe_hash(canon, ks);
     uint8_t *dst = rows + i * row_stride + col_offset;
     const uint32_t n_groups = (n_local + PK_U_GROUP - 1) / PK_U_GROUP;
     for (uint32_t u = 0; u < n_groups; u++) {
         uint32_t m = 0;
-        if (valid) m = pk_u_lookup(utables[u], canon, h, PK_U_GROUP * u, min(PK_U_GROUP, n_local - PK_U_GROUP * u), ks);
+        if (valid) m = pk_group_lookup(utables[u], canon, h, PK_U_GROUP * u, min(PK_U_GROUP, n_local - PK_U_GROUP * u), ks);
         dst[u] = (uint8_t)m;
     }
 }
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(256) items_group_kernel(const uint2 *__restric
         const uint64_t canon = pk_canon_at(words, p0 + it.y, ks.k);
         uint8_t *dst = rows + (uint64_t)it.y * row_stride + col_offset;
         for (uint32_t u = 0; u < n_groups; u++)
-            dst[u] = (uint8_t)pk_u_lookup(utables[u], canon, it.x, PK_U_GROUP * u, min(PK_U_GROUP, n_local - PK_U_GROUP * u), ks);
+            dst[u] = (uint8_t)pk_group_lookup(utables[u], canon, it.x, PK_U_GROUP * u, min(PK_U_GROUP, n_local - PK_U_GROUP * u), ks);
     };
     if (!counts) {
         const unsigned long long n = min(*flat_total, (unsigned long long)cap);

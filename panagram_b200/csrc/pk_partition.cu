@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_seq_kernel(PartArgs a
         if (i < a.off + a.n) {
             uint64_t canon;
             if (pk_window(a.words, a.mask64, a.p0 + i, a.ks.k, canon)) {
-                h[j] = pk_key_hash(canon, a.ks);
+                h[j] = pk_probe_hash(canon, a.ks);
                 valid |= 1u << j;
             } else {
                 uint8_t *dst = a.rows + i * a.row_stride + a.col_offset;
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs 
 
 // ------------------------------------------------------------------ K3: probe one partition per block
 #define PP_OBINS 128                      // position bins of the un-permute lists
+#define PP_OCS 32                         // the bins' cursors sit 128 bytes apart: 2^18 blocks add to each of them
 #define PS_BINS 1024                      // counting-sort bins of the bucket-sorted variant
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
@@ -217,6 +218,8 @@ struct ProbeArgs {
     uint2 *out_list;                  // [(grp * PP_OBINS + bin) << out_shift]
     uint32_t *out_cursor;             // [n_groups * PP_OBINS]
     uint32_t out_shift;
+    uint32_t rank_atomic;             // window kernel: rank the results inside their position bin by one shared-memory atomicAdd per
+                                      // item (1) or by warp match_any + per-warp counters (0)
     PkTable tabs[32];
 };
 
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(T, MINB) probe_part_kernel(const __grid_consta
                     o_wc[ww][b] = (uint16_t)run;
                     run += tt;
                 }
-                if (run) o_gb[b] = atomicAdd(&a.out_cursor[a.grp * PP_OBINS + b], run);
+                if (run) o_gb[b] = atomicAdd(&a.out_cursor[(a.grp * PP_OBINS + b) * PP_OCS], run);
             }
             __syncthreads();
 #pragma unroll
@@ -516,7 +519,22 @@ template <int FMT> struct PwKey { typedef uint64_t type; };
 template <> struct PwKey<PK_FMT_S32> { typedef uint32_t type; };      // S32 compares 32-bit slots: keep 32 bits per item
 // group tables (pk_device.cuh): slot = [mask 8][key 56]; membership mask of key56 in a bucket read as two halves
 #define PK_FMT_GROUP 2
+#define PK_FMT_GROUP32 3      // group tables with 32-bit slots (G32, pk_device.cuh)
 template <> struct PwKey<PK_FMT_GROUP> { typedef uint64_t type; };
+template <> struct PwKey<PK_FMT_GROUP32> { typedef uint32_t type; };
+// G32: slot = [mask 8][key 24]; membership mask of key24 in a bucket read as two halves
+__device__ __forceinline__ uint32_t pw_umask32(const uint4 &A, const uint4 &B, uint32_t key24) {
+    uint32_t m = 0;
+    if ((A.x & PK_G32_KEY_MASK) == key24) m |= A.x >> PK_G32_MASK_SHIFT;
+    if ((A.y & PK_G32_KEY_MASK) == key24) m |= A.y >> PK_G32_MASK_SHIFT;
+    if ((A.z & PK_G32_KEY_MASK) == key24) m |= A.z >> PK_G32_MASK_SHIFT;
+    if ((A.w & PK_G32_KEY_MASK) == key24) m |= A.w >> PK_G32_MASK_SHIFT;
+    if ((B.x & PK_G32_KEY_MASK) == key24) m |= B.x >> PK_G32_MASK_SHIFT;
+    if ((B.y & PK_G32_KEY_MASK) == key24) m |= B.y >> PK_G32_MASK_SHIFT;
+    if ((B.z & PK_G32_KEY_MASK) == key24) m |= B.z >> PK_G32_MASK_SHIFT;
+    if ((B.w & PK_G32_KEY_MASK) == key24) m |= B.w >> PK_G32_MASK_SHIFT;
+    return m;
+}
 __device__ __forceinline__ uint32_t pw_umask(const uint4 &A, const uint4 &B, uint64_t key56) {
     const uint32_t lo = (uint32_t)key56, hi = (uint32_t)(key56 >> 32);
     uint32_t m = 0;
@@ -539,9 +557,10 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
     __shared__ uint32_t q_pos[PW_QCAP], q_h[PW_QCAP], q_meta[PW_QCAP];   //   position, hash, (item << 5 | genome)
     __shared__ uint32_t q_n[2];
     __shared__ uint16_t o_wc[T / 32][PP_OBINS];
-    __shared__ uint32_t o_gb[PP_OBINS];
+    __shared__ uint32_t o_gb[PP_OBINS], o_cnt[PP_OBINS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr bool GRP = FMT == PK_FMT_GROUP;       // group tables: a probe returns an 8-bit membership mask
+    constexpr bool GRP = FMT == PK_FMT_GROUP || FMT == PK_FMT_GROUP32;       // group tables: a probe returns an 8-bit membership mask
+    constexpr bool G32 = FMT == PK_FMT_GROUP32;
     const uint32_t win0 = pw_smem(s_win), bar0 = pw_smem(s_bar);
     const uint32_t xoff = (lane & 1) * 16;          // odd lanes read the bucket halves in the other order: spreads the banks
     // thread s initialises the mbarrier of stage s and issues the first copy into it straight away (other threads
@@ -584,6 +603,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
         if (tid == 0) { q_n[0] = 0; q_n[1] = 0; }
         for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
         for (uint32_t i = tid; i < (T / 32) * PP_OBINS / 2; i += T) ((uint32_t *)&o_wc[0][0])[i] = 0;
+        for (uint32_t i = tid; i < PP_OBINS; i += T) o_cnt[i] = 0;
         key_t key[IPT];          // S64: the canonical k-mer; S32: the slot value it has in its home bucket
         uint32_t h[IPT], pos[IPT], bits[IPT];
 #pragma unroll
@@ -591,7 +611,8 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
             key[j] = 0; h[j] = it[j].x; pos[j] = it[j].y; bits[j] = 0;
             if (tid + j * T < cnt) {
                 const uint64_t canon = pk_canon_at(a.words, a.p0 + it[j].y, a.ks.k);
-                if constexpr (GRP) key[j] = pk_u_key(canon, 0);
+                if constexpr (G32) key[j] = pk_g32_key(canon, 0);
+                else if constexpr (GRP) key[j] = pk_u_key(canon, 0);
                 else key[j] = (key_t)pk_target<GRP ? PK_FMT_S64 : FMT>(canon, 0);
             }
         }
@@ -600,7 +621,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
         auto full_lookup = [&](const PkTable &t, uint64_t canon, uint32_t hh, uint32_t g) -> uint32_t {
             if constexpr (GRP) {
                 const uint32_t ngg = min(PK_U_GROUP, a.n_genomes - PK_U_GROUP * g);
-                return pk_u_lookup(t, canon, hh, a.g_first + PK_U_GROUP * g, ngg, a.ks) << (PK_U_GROUP * g);
+                return pk_group_lookup(t, canon, hh, a.g_first + PK_U_GROUP * g, ngg, a.ks) << (PK_U_GROUP * g);
             } else {
                 return (uint32_t)pk_lookup<GRP ? PK_FMT_S64 : FMT>(t, canon, hh, a.g_first + g, a.ks) << g;
             }
@@ -640,7 +661,11 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
                         if (i < cnt && (!CHUNKED || b - cs < nbp)) {  // the item's home bucket lies in this piece
                             const uint32_t wa = wbase + b * 32;
                             const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
-                            if constexpr (GRP) {
+                            if constexpr (G32) {
+                                const uint32_t m = pw_umask32(A, B, key[j]);
+                                if (m) bits[j] |= m << gsh;
+                                else if (pw_full<PK_FMT_S32>(xoff ? A : B)) defer(j, i, g, t);
+                            } else if constexpr (GRP) {
                                 const uint32_t m = pw_umask(A, B, key[j]);
                                 if (m) bits[j] |= m << gsh;
                                 else if (pw_full<PK_FMT_S64>(xoff ? A : B)) defer(j, i, g, t);
@@ -657,7 +682,11 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
                         const uint32_t i = tid + j * T;
                         if (i < cnt) {
                             const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * __umulhi(h[j], t.n_buckets));
-                            if constexpr (GRP) {
+                            if constexpr (G32) {
+                                const uint32_t m = pk_g32_bucket_mask(v, key[j]);
+                                if (m) bits[j] |= m << gsh;
+                                else if ((uint32_t)(v.d >> 32) != PK_EMPTY32) defer(j, i, g, t);
+                            } else if constexpr (GRP) {
                                 const uint32_t m = pk_u_bucket_mask(v, key[j]);
                                 if (m) bits[j] |= m << gsh;
                                 else if (v.d != PK_EMPTY) defer(j, i, g, t);
@@ -687,7 +716,11 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
                             const uint32_t wa = wb + (off + r) * 32;
                             const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
                             // S32 / group: the slot value at displacement r is the home value + r; S64: the k-mer itself
-                            if constexpr (GRP) {
+                            if constexpr (G32) {
+                                const uint32_t m = pw_umask32(A, B, (uint32_t)kk + r);
+                                if (m) { found = m << (PK_U_GROUP * u); decided = true; break; }
+                                if (!pw_full<PK_FMT_S32>(xoff ? A : B)) { decided = true; break; }
+                            } else if constexpr (GRP) {
                                 const uint32_t m = pw_umask(A, B, (uint64_t)kk + r);
                                 if (m) { found = m << (PK_U_GROUP * u); decided = true; break; }
                                 if (!pw_full<PK_FMT_S64>(xoff ? A : B)) { decided = true; break; }
@@ -710,7 +743,28 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < IPT; j++)
             if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
-        if (a.out_list) {
+        if (a.out_list && a.rank_atomic) {
+            // rank inside (block, bin) by one shared-memory atomicAdd per item; one global atomicAdd per (block, bin)
+            // reserves the run in the bin's list
+            uint32_t rk[IPT];
+#pragma unroll
+            for (int j = 0; j < IPT; j++)
+                rk[j] = tid + j * T < cnt ? atomicAdd(&o_cnt[pos[j] >> a.out_shift], 1u) : 0u;
+            __syncthreads();
+            for (uint32_t b = tid; b < PP_OBINS; b += T) {
+                const uint32_t c = o_cnt[b];
+                if (c) o_gb[b] = atomicAdd(&a.out_cursor[(a.grp * PP_OBINS + b) * PP_OCS], c);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; j++) {
+                if (tid + j * T < cnt) {
+                    const uint32_t bin = pos[j] >> a.out_shift;
+                    const uint64_t slot = (((uint64_t)a.grp * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + rk[j];
+                    a.out_list[slot] = make_uint2(pos[j], bits[j]);
+                }
+            }
+        } else if (a.out_list) {
             uint16_t rank[IPT];
 #pragma unroll
             for (int j = 0; j < IPT; j++) {
@@ -736,7 +790,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
                     o_wc[ww][b] = (uint16_t)run;
                     run += tt;
                 }
-                if (run) o_gb[b] = atomicAdd(&a.out_cursor[a.grp * PP_OBINS + b], run);
+                if (run) o_gb[b] = atomicAdd(&a.out_cursor[(a.grp * PP_OBINS + b) * PP_OCS], run);
             }
             __syncthreads();
 #pragma unroll
@@ -787,15 +841,20 @@ static const K3Variant &k3_pick(const PkPartTune &tu, uint32_t n_genomes_in_laun
 }
 
 // window (TMA-staged) variants of K3; same block capacity as variants 0/1, so the partition plan is shared.
-// fn[0] / fn[1]: per-genome S64 / S32 tables, fn[2] / fn[3]: group tables, whole windows / windows in pieces
-struct K3WinVariant { int threads, cap; void (*fn[4])(ProbeArgs, uint32_t, uint32_t, uint32_t); };
+// fn[0] / fn[1]: per-genome S64 / S32 tables, fn[2] / fn[3]: group tables with 64-bit slots, whole windows / windows in pieces,
+// fn[4] / fn[5]: group tables with 32-bit slots (G32)
+struct K3WinVariant { int threads, cap; void (*fn[6])(ProbeArgs, uint32_t, uint32_t, uint32_t); };
 #define K3W(T, IPT, MINB) {T, T * IPT, {probe_win_kernel<T, IPT, PK_FMT_S64, MINB, 0>, probe_win_kernel<T, IPT, PK_FMT_S32, MINB, 0>, \
-                                        probe_win_kernel<T, IPT, PK_FMT_GROUP, MINB, 0>, probe_win_kernel<T, IPT, PK_FMT_GROUP, MINB, 1>}}
+                                        probe_win_kernel<T, IPT, PK_FMT_GROUP, MINB, 0>, probe_win_kernel<T, IPT, PK_FMT_GROUP, MINB, 1>, \
+                                        probe_win_kernel<T, IPT, PK_FMT_GROUP32, MINB, 0>, probe_win_kernel<T, IPT, PK_FMT_GROUP32, MINB, 1>}}
 static const K3WinVariant k3w_variants[] = {
     K3W(256, 3, 4),      // 0: <= 64 registers
     K3W(256, 3, 5),      // 1: <= 48 registers
     K3W(256, 3, 3),      // 2: <= 80 registers
     K3W(256, 3, 6),      // 3: <= 40 registers
+    K3W(256, 3, 8),      // 4: <= 32 registers
+    K3W(128, 6, 12),     // 5: 128-thread blocks
+    K3W(128, 6, 16),     // 6
 };
 #define PW_MAX_GROUP_STAGE_BYTES 32768u
 #define PW_GROUP_STAGE_TARGET 24576u          // pieces of a group-table window are at most this large
@@ -825,7 +884,7 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const uint2 *__restrict_
                                                         uint32_t out_shift, uint32_t bin0, uint8_t *__restrict__ rows,
                                                         uint32_t row_stride, uint32_t col_offset, uint32_t nbl) {
     const uint32_t bin = bin0 + blockIdx.y, grp = blockIdx.z;
-    const uint32_t cnt = cursor[grp * PP_OBINS + bin];
+    const uint32_t cnt = cursor[(grp * PP_OBINS + bin) * PP_OCS];
     const uint32_t t0 = blockIdx.x * UP_TILE;
     if (t0 >= cnt) return;
     const uint2 *src = list + (((uint64_t)grp * PP_OBINS + bin) << out_shift);
@@ -865,6 +924,7 @@ void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl) {
     pl->out_bins = (uint32_t)((n + (1ull << pl->out_shift) - 1) >> pl->out_shift);
 }
 uint32_t pk_part_obins(void) { return PP_OBINS; }
+uint32_t pk_part_ocursor_words(void) { return PP_OBINS * PP_OCS; }
 
 // The stages of one partitioned batch. A batch may be fed in pieces (pk_part_append per chromosome, as
 // its bytes arrive) and drained in pieces (pk_part_unpermute per range of position bins).
@@ -885,7 +945,7 @@ void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &
     cudaMemsetAsync(sc.cursor1, 0, sizeof(uint32_t) * pl.n_regions1, s);
     if (pl.n_regions2) cudaMemsetAsync(sc.cursor2, 0, sizeof(uint32_t) * pl.n_regions2, s);
     cudaMemsetAsync(sc.spill_cursor, 0, sizeof(unsigned long long), s);
-    if (sc.out_list) cudaMemsetAsync(sc.out_cursor, 0, sizeof(uint32_t) * ((n_local + 31) / 32) * PP_OBINS, s);
+    if (sc.out_list) cudaMemsetAsync(sc.out_cursor, 0, sizeof(uint32_t) * ((n_local + 31) / 32) * PP_OBINS * PP_OCS, s);
 }
 
 // K1 over positions [p0 + off, p0 + off + n) of the batch that starts at p0 (pos = off + i)
@@ -925,6 +985,7 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     p.out_list = (uint2 *)sc.out_list;
     p.out_cursor = sc.out_cursor;
     p.out_shift = pl.out_shift;
+    p.rank_atomic = (uint32_t)tu.rank_atomic;
     if (evs) cudaEventRecord(evs[2], s);
     bool regions_done = false;         // the regions have been answered for ALL genomes by the L1/L2 group kernel
     for (uint32_t grp = 0; grp < n_groups && !regions_done; grp++) {       // one launch per group of 32 genomes
@@ -956,7 +1017,7 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
                 const K3WinVariant &wv = k3w_pick(tu, ngen, true);
                 const uint32_t stage_bytes = (uint32_t)cb * 32, n_stages = np == 1 ? 1 : 2;
                 p.ng = np; p.tbits = PK_U_GROUP; p.chunk_buckets = nch > 1 ? (uint32_t)cb : 0;
-                const int fk = nch > 1 ? 3 : 2;
+                const int fk = (nch > 1 ? 3 : 2) + (p.tabs[0].fmt == PK_TFMT_G32 ? 2 : 0);
                 cudaFuncSetAttribute(wv.fn[fk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
                 wv.fn[fk]<<<p.n_regions, wv.threads, (size_t)n_stages * stage_bytes, s>>>(p, stage_bytes, 1, n_stages);
                 last_window = 2;

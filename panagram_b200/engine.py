@@ -242,16 +242,16 @@ class Engine:
         total = int(self._L.pk_anchor_layout(n, arr, off))
         return [int(x) for x in off], total
 
-    def anchor_genome_plane(self, seqs, d_plane: int, plane_rows: int) -> list[int]:
+    def anchor_genome_plane(self, seqs, d_plane: int, plane_rows: int, row_stride: int | None = None) -> list[int]:
         """H2D + pack + probe of all chromosomes of one anchor into a caller-owned device plane
-        [plane_rows][row_bytes] (pk_anchor_genome_plane: the rank-local half of the genome-sharded path).
-        Returns nkmers per chromosome; complete on return."""
+        [plane_rows][row_stride] (pk_anchor_genome_plane: the rank-local half of the genome-sharded path;
+        row_stride defaults to this shard's row bytes). Returns nkmers per chromosome; complete on return."""
         arrs = [_u8(s) for s in seqs]
         n = len(arrs)
         ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
         lens = (C.c_uint64 * n)(*[a.size for a in arrs])
         nko = (C.c_uint64 * n)()
-        check(self._L.pk_anchor_genome_plane(self._h, n, ptrs, lens, d_plane, plane_rows, nko))
+        check(self._L.pk_anchor_genome_plane(self._h, n, ptrs, lens, d_plane, plane_rows, row_stride or self.row_bytes, nko))
         return [int(x) for x in nko]
 
     def bgzf_bound(self, nbytes: int) -> tuple[int, int]:

@@ -109,8 +109,13 @@ class Index:
         raise ValueError(f"genome {s['name']}: no FASTA and no KMC database under {kmc}")
 
     def populate(self, eng: Engine, log=print) -> Engine:
-        """Fill the engine's tables with the k-mer sets of the genomes of its shard, then finalize."""
+        """Fill the engine's tables with the k-mer sets of the genomes of its shard, then finalize. The per-genome
+        tables are build intermediates: each group of 8 genomes is sealed into its group table (one probe answers
+        8 genomes) as soon as it is complete and its per-genome tables are freed (pk_engine_seal_group), so the
+        resident footprint is the group tables + one group under construction."""
         done_bitvec = set()
+        eng.tune(group_only=1)
+        filled = set()
         for s in self.samples:
             if not (eng.genome_begin <= s["id"] < eng.genome_end):
                 continue
@@ -129,6 +134,11 @@ class Index:
                 for _, q in recs:
                     eng.add_sequence(s["id"], q)
             log(f"k-mer set of {s['name']} from {kind} ({time.perf_counter() - t0:.2f}s)")
+            filled.add(s["id"])
+            gl = s["id"] - eng.genome_begin
+            u0 = eng.genome_begin + gl // 8 * 8
+            if kind != "bitvec" and all(g in filled for g in range(u0, min(u0 + 8, eng.genome_end))):
+                eng.seal_group(gl // 8)
         eng.finalize()
         return eng
 

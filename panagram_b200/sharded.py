@@ -174,6 +174,7 @@ class ShardedAnchorer:
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._planes = None          # [2] ping-pong: {"rows", "own", "peers"}
         self._host_rows = None       # page-locked staging of anchor_genome(rows_to_host=True), grow-only
+        self._host_gz = None         # page-locked staging of the BGZF image of the slice
         self._i = 0
         self.last = {}               # timings of the last anchor_genome call (ms)
 
@@ -286,7 +287,7 @@ class ShardedAnchorer:
         with torch.cuda.stream(self.stream):
             ev[0].record(self.stream)
             # H2D + pack + probe, pipelined inside the library on its own streams; complete on return
-            eng.anchor_genome_plane(arrs, pl["own"], pl["rows"])
+            eng.anchor_genome_plane(arrs, pl["own"], pl["rows"], self.w)
             ev[1].record(self.stream)
             self.barrier()
             rows = torch.empty((max(s1 - s0, 1), rb), dtype=torch.uint8, device=self.dev)
@@ -322,8 +323,14 @@ class ShardedAnchorer:
                 eng.bgzf_compress_device(rows.data_ptr(), nb, rb, gz.data_ptr(), gzi.data_ptr(), tot.data_ptr(),
                                          self.stream.cuda_stream)
                 t = tot.cpu()                                     # synchronises self.stream
-                out["gz"] = gz[: int(t[0])].cpu().numpy()
-                out["gzi"] = gzi.view(torch.uint8)[: int(t[1])].cpu().numpy()
+                ngz, ngzi = int(t[0]), int(t[1])
+                if self._host_gz is None or self._host_gz.numel() < ngz + ngzi:
+                    self._host_gz = torch.empty(cap_gz + cap_gzi + 16, dtype=torch.uint8, pin_memory=True)
+                self._host_gz[:ngz].copy_(gz[:ngz], non_blocking=True)
+                self._host_gz[ngz:ngz + ngzi].copy_(gzi.view(torch.uint8)[:ngzi], non_blocking=True)
+                self.stream.synchronize()
+                out["gz"] = self._host_gz[:ngz].numpy()           # page-locked staging, valid until the next call
+                out["gzi"] = self._host_gz[ngz:ngz + ngzi].numpy()
             if rows_to_host:
                 nb = (s1 - s0) * rb
                 if self._host_rows is None or self._host_rows.numel() < nb:

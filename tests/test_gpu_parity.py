@@ -396,7 +396,7 @@ def test_position_split_exchange_on_one_gpu_equals_single_engine(n, k, world):
     nks = [l - k + 1 for l in lens]
     planes = [torch.zeros((plane_rows, w), dtype=torch.uint8, device=dev) for _ in range(world)]
     for e, pl in zip(shards, planes):
-        assert e.anchor_genome_plane(seqs, pl.data_ptr(), plane_rows) == nks
+        assert e.anchor_genome_plane(seqs, pl.data_ptr(), plane_rows, w) == nks
     sb = sharded.slice_bounds(sum(nks), rb, world)
     binlen = [full.bin_len(nk) for nk in nks]
     nbins = [(nk + b - 1) // b for nk, b in zip(nks, binlen)]
@@ -585,6 +585,42 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
         eng.tune(k3_window=1, group_tables=1)
         eng.finalize()
         assert eng.group_stats(0)["n_keys"] >= max(eng.table_stats(g)["n_keys"] for g in range(min(8, n_genomes)))
+        bytes64 = eng.group_stats(0)["bytes"]
+        # the compact 32-bit slot format of the group tables, forced at this (small) table size: where k allows it
+        # (k <= 23) the group table's own hash partitions the positions; window kernel, L1/L2 kernel, direct kernel
+        eng.tune(group_tables=0)
+        eng.tune(group_tables=1, group_g32=2)
+        eng.finalize()
+        if k <= 23:
+            assert eng.group_stats(0)["n_buckets"] >= 1 << (2 * k - 20)
+        else:
+            assert eng.group_stats(0)["bytes"] == bytes64
+        for knobs in (dict(k3_window=1), dict(k3_window=0)):
+            eng.tune(**knobs)
+            got = eng.anchor_genome(seqs)
+            gz = eng.anchor_genome_bgzf(seqs)
+            assert (got["col_sums"] == want["col_sums"]).all() and (gz["col_sums"] == want["col_sums"]).all(), knobs
+            for a, b in zip(got["chroms"], want["chroms"]):
+                assert (a["bitmap1"] == b["bitmap1"]).all() and (a["bin_hist"] == b["bin_hist"]).all(), knobs
+        short = seqs[0][:30_000]
+        assert (eng.anchor_chrom(short, hist=False)["bitmap1"] == engd.anchor_chrom(short, hist=False)["bitmap1"]).all()
+        for dbi in range((n_genomes + 31) // 32):
+            assert (eng.get_counters_for_read(dbi, short) == engd.get_counters_for_read(dbi, short)).all()
+        # ... and with the per-genome tables freed once the group tables hold their keys (group_only)
+        eng.tune(k3_window=1, group_tables=0)
+        eng.tune(group_tables=1, group_only=1)
+        eng.finalize()
+        assert all(eng.table_stats(g)["bytes"] == 0 for g in range(n_genomes))
+        assert eng.table_stats(1)["n_keys"] == engd.table_stats(1)["n_keys"]
+        for knobs in (dict(k3_window=1), dict(k3_window=0)):
+            eng.tune(**knobs)
+            got = eng.anchor_genome(seqs)
+            for a, b in zip(got["chroms"], want["chroms"]):
+                assert (a["bitmap1"] == b["bitmap1"]).all() and (a["bin_hist"] == b["bin_hist"]).all(), knobs
+        assert (eng.anchor_chrom(short, hist=False)["bitmap1"] == engd.anchor_chrom(short, hist=False)["bitmap1"]).all()
+        with pytest.raises(_lib.PkError):
+            eng.add_sequence(0, seqs[0])             # sealed: its k-mers live in the group table only
+        eng.tune(k3_window=1)
         # the same genome as 2 and 3 batches of whole chromosomes (copies of one batch under the kernels of the other)
         eng.tune(k3_window=1, k3w_variant=-1, k3w_group=0, unpermute=1, e2e_batch_min=0)
         for nb in (2, 3, 8):
@@ -649,6 +685,68 @@ def test_panagram_index_cli_end_to_end(pan3, tmp_path, capsys):
 
 
 # ---- S32 slot format: quotienting must stay exact -------------------------------------------------
+@pytest.mark.parametrize("n_genomes,k,length", [(32, 21, 20_000_000), (64, 31, 20_000_000)])
+def test_many_genomes_at_20mbp_vs_c_oracle(n_genomes, k, length):
+    """The default path (group tables — four of them at N=32, eight at N=64; partitioned probe; BGZF on the GPU) at
+    a size where every table holds ~20 M k-mers, against the C oracle: per genome the k-mer set `kmc -ci1` would
+    count (pko_kmers_of_seq) as an in-memory KMC1 database, queried with the restatement of
+    CKMCFile::GetCountersForRead (kmc_file.cpp:954-1027) for EVERY position of the anchor. Bit-exact rows, column
+    sums and popcount histograms."""
+    import gzip
+    from concurrent.futures import ThreadPoolExecutor
+    from panagram_b200 import synth
+    anc = synth.ancestor_codes(length, 4242 + n_genomes)
+    anchor_g = 5
+    eng = Engine(k, n_genomes)
+    eng.tune(group_only=1)
+    anchor_chroms = None
+    dbs = [None] * n_genomes
+
+    def build(g):
+        chroms = synth.genome_chroms(anc, g, 4242 + n_genomes, n_chroms=3, n_run=700, lower_run=3000)
+        keys = oracle.canonical_kmers([s for _, s in chroms], k)
+        dbs[g] = oracle.OracleDB.from_kmers(k, keys, lut_prefix_len=11 if k == 31 else 9)     # (k - lut) % 4 == 0
+        return chroms
+
+    with ThreadPoolExecutor(8) as pool:
+        for g0 in range(0, n_genomes, 8):
+            for g, chroms in zip(range(g0, g0 + 8), pool.map(build, range(g0, min(g0 + 8, n_genomes)))):
+                if g == anchor_g:
+                    anchor_chroms = chroms
+                eng.reserve(g, sum(s.size for _, s in chroms))
+                for _, s in chroms:
+                    eng.add_sequence(g, s)
+                assert eng.table_stats(g) is not None
+            eng.seal_group(g0 // 8)
+    eng.finalize()
+    for g in (0, 7, n_genomes - 1):
+        assert eng.table_stats(g)["n_keys"] == dbs[g].total_kmers and eng.table_stats(g)["bytes"] == 0
+    seqs = [s for _, s in anchor_chroms]
+    got = eng.anchor_genome(seqs)
+    gz = eng.anchor_genome_bgzf(seqs)
+    rb = (n_genomes + 7) // 8
+    col = np.zeros(n_genomes, dtype=np.uint64)
+    for ci, s in enumerate(seqs):
+        b = s.tobytes()
+        with ThreadPoolExecutor(16) as pool:
+            cols = list(pool.map(lambda g: dbs[g].get_counters_for_read(b), range(n_genomes)))
+        bits = np.stack([(c != 0) for c in cols], axis=1)
+        want = np.packbits(bits, axis=1, bitorder="little")
+        assert want.shape == (s.size - k + 1, rb)
+        rows = got["chroms"][ci]["bitmap1"]
+        assert (rows == want).all(), f"chromosome {ci}: {int((rows != want).any(axis=1).sum())} rows differ from the C oracle"
+        assert (got["chroms"][ci]["low"] == want[::100]).all()
+        pc = bits.sum(axis=1)
+        bl = got["chroms"][ci]["binlen"]
+        nb = (pc.size + bl - 1) // bl
+        hist = np.bincount((np.arange(pc.size) // bl) * (n_genomes + 1) + pc, minlength=nb * (n_genomes + 1)).reshape(nb, n_genomes + 1)
+        assert (got["chroms"][ci]["bin_hist"] == hist.astype(np.uint64)).all()
+        col += bits.sum(axis=0).astype(np.uint64)
+        del bits, want, cols
+    assert (got["col_sums"] == col).all() and (gz["col_sums"] == col).all()
+    assert gzip.decompress(gz["gz"].tobytes()) == b"".join(c["bitmap1"].tobytes() for c in got["chroms"])
+
+
 def _kmer_str(v: int, k: int) -> bytes:
     return bytes(b"ACGT"[(v >> (2 * (k - 1 - i))) & 3] for i in range(k))
 
