@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--out", default="")
+    ap.add_argument("--chunk-positions", type=int, default=0, help="max positions per probe launch (pk_config.chunk_positions)")
     ap.add_argument("settings", nargs="*")
     args = ap.parse_args()
     import torch
@@ -37,7 +38,7 @@ def main():
     k, n = wl["k"], wl["n_per_gpu"]
     t0 = time.perf_counter()
     anc = synth.ancestor_codes(wl["length"], wl["seed"])
-    eng = Engine(k, n, load_factor=args.load_factor)
+    eng = Engine(k, n, load_factor=args.load_factor, chunk_positions=args.chunk_positions)
     anchor = None
     for g in range(n):
         chroms = B.make_genome(anc, g, wl["seed"])

@@ -142,6 +142,16 @@ int pk_engine_table_stats(const pk_engine *e, uint32_t genome, pk_table_stats *o
  * switched off (pk_engine_tune "group_tables" 0) or could not be built. group = local genome index / 8. */
 int pk_engine_group_stats(const pk_engine *e, uint32_t group, pk_table_stats *out);
 
+/* pk_engine_sample_kmers: a uniform sample of the engine's k-mers with their genomes — every canonical k-mer x of any
+ * local genome with hash32(x) < hmax (hmax = 0: every k-mer), each once per group of 8 local genomes:
+ * keys[i] = x, tags[i] = (local_group << 8) | membership mask of the group's 8 genomes. The hash depends on x
+ * alone, so the engines of a sharded run sample the same k-mers: a FracMinHash sketch whose pairwise
+ * intersection / union counts give the Jaccard indices and Mash distances of genome_dist.tsv — what rules
+ * mash_sample / mash_triangle compute with `mash sketch -s 10000` + `mash triangle -C -E`
+ * (panagram/workflow/Snakefile:124-149; read by figs.py:50-59). HOST buffers of `cap` entries; *n_out = entries the
+ * sample holds (PK_ENOMEM when that exceeds cap: call again with more room). Reads the group tables. */
+int pk_engine_sample_kmers(pk_engine *e, uint32_t hmax, uint64_t *keys, uint32_t *tags, uint64_t cap, uint64_t *n_out);
+
 /* ---- the hot path, host buffers ---------------------------------------------
  * pk_bin_len: the bin-length rule of KMCdb::write_bits (cpp/anchor.cpp:114-118) /
  *   Genome.bin_bitsum (index.py:1169-1172). 0 when nkmers < min_bin_count.
@@ -283,6 +293,17 @@ int pk_bgzf_compress_device(pk_engine *e, const void *d_in, uint64_t n_bytes, ui
 int pk_anchor_genome_bgzf(pk_engine *e, uint32_t n_chroms, const char *const *seqs, const uint64_t *lens,
                           uint8_t *const *gz, const uint64_t *gz_cap, uint8_t *const *gzi, const uint64_t *gzi_cap,
                           uint64_t *sizes, uint64_t *const *bin_hist, uint64_t *col_sums, uint64_t *nkmers_out);
+
+/* Pair-count bins: per bin of bin_positions consecutive positions of one chromosome (rows_per_bin =
+ * ceil(bin_positions / lowres_step) low-res rows), the number of low-res rows in which each genome's bit is set —
+ * Index.bitmap_to_paircount_bins (panagram/index.py:454-459), the input of chrom_umaps.csv / genome_umap.csv
+ * (Genome.write_umaps, index.py:1107-1131). pk_paircount_bins_device: any device rows, counts[bins][n_cols] uint32 on the
+ * device. pk_anchor_paircount_bins: the anchor the last pk_anchor_genome / pk_anchor_genome_bgzf call processed, from
+ * its low-res rows still resident on the device, into HOST counts[sum_c bins_c][N_local], chromosome after chromosome
+ * (nkmers = that call's nkmers_out; PK_ESTATE when it does not match). */
+int pk_paircount_bins_device(pk_engine *e, const void *d_rows_low, uint32_t row_stride, uint32_t n_cols, uint64_t n_rows,
+                             uint32_t rows_per_bin, void *d_counts, void *stream);
+int pk_anchor_paircount_bins(pk_engine *e, uint32_t n_chroms, const uint64_t *nkmers, uint32_t bin_positions, uint32_t *counts);
 
 /* Tuning knobs of the partitioned probe (per engine; no reference counterpart). Results never depend on
  * them; tests run the parity suite under several settings. name = "k3_window" (1: probe out of table

@@ -83,6 +83,7 @@ SIGNATURES = {
     "pk_engine_seal_group": (C.c_int, [_vp, _u32]),
     "pk_engine_table_stats": (C.c_int, [_vp, _u32, C.POINTER(PkTableStats)]),
     "pk_engine_group_stats": (C.c_int, [_vp, _u32, C.POINTER(PkTableStats)]),
+    "pk_engine_sample_kmers": (C.c_int, [_vp, _u32, _vp, _vp, _u64, _pu64]),
     "pk_bin_len": (_u64, [C.POINTER(PkConfig), _u64]),
     "pk_anchor_genome": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pk_anchor_chrom": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _pu64]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "pk_probe_device": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _vp, _u32, _u32, _vp]),
     "pk_reduce_device": (C.c_int, [_vp, _vp, _u32, _u32, _u64, _u64, _u64, _vp, _vp, _vp, _u32, _vp]),
     "pk_interleave_device": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _vp, _u32, _vp]),
+    "pk_paircount_bins_device": (C.c_int, [_vp, _vp, _u32, _u32, _u64, _u32, _vp, _vp]),
+    "pk_anchor_paircount_bins": (C.c_int, [_vp, _u32, _vp, _u32, _vp]),
     "pk_engine_stats": (C.c_int, [_vp, C.POINTER(PkStats)]),
     "pk_engine_tune": (C.c_int, [_vp, _cp, C.c_int]),
     "pk_bgzf_bound": (_u64, [_u64]),

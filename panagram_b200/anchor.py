@@ -91,17 +91,16 @@ def parse_fasta_numpy(path, strip_cr: bool = False) -> list[tuple[str, np.ndarra
 
 
 def write_text_files(outdir, name: str, chrom_names: list[str], nks: list[int], binlens: list[int], hists: list,
-                     col_sums, low_all: np.ndarray, n_genomes: int, step: int, genome_names: list[str] | None,
+                     col_sums, pc_counts: list, n_genomes: int, step: int, genome_names: list[str] | None,
                      umap_bin_size: int = 100000) -> None:
     """Everything of an anchor directory but the bitmaps: chrs.tsv, bitsum.bins.tsv (cpp/anchor.cpp:57-69,84-85,
     184-189), total_paircounts.csv (index.py:1068-1074) and chrom_umaps.csv / genome_umap.csv (Genome.write_umaps,
-    index.py:1107-1131) from the low-res rows `low_all` [sum(ceil(nk/step)), row_bytes] of all chromosomes."""
+    index.py:1107-1131) from the pair-count bins `pc_counts` (per chromosome [bins, N] counts of low-res rows with
+    each genome's bit set, reduced on the GPU: Engine.anchor_paircount_bins)."""
     outdir = Path(outdir)
-    chrom_rows, genome_parts, lo = [], [], 0
-    for cname, nk in zip(chrom_names, nks):
-        n_low = (nk + step - 1) // step
-        starts, frac = layout.paircount_bins(low_all[lo:lo + n_low], n_genomes, step, umap_bin_size)
-        lo += n_low
+    chrom_rows, genome_parts = [], []
+    for cname, cnt in zip(chrom_names, pc_counts):
+        starts, frac = layout.paircount_frac(cnt, umap_bin_size)
         chrom_rows += layout.umap_rows(cname, starts, frac, umap_bin_size)
         genome_parts.append((cname, starts, frac))
     (outdir / "chrom_umaps.csv").write_text(layout.umaps_csv(chrom_rows))
@@ -154,7 +153,6 @@ def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[st
                         ("gzi_low", f"bitmap.{step}.gzi")):
             with open(outdir / fn, "wb") as fh:
                 fh.write(res[key].data)
-        low_all = np.frombuffer(gzip.decompress(res["gz_low"].tobytes()), dtype=np.uint8).reshape(-1, engine.row_bytes)
     elif bgzf == "zlib":
         w1 = layout.BgzfWriter(outdir / "bitmap.1.gz", bgzf_level, threads)
         wl = layout.BgzfWriter(outdir / f"bitmap.{step}.gz", bgzf_level, threads)
@@ -164,14 +162,14 @@ def anchor_fasta(engine: Engine, name: str, fasta, outdir, genome_names: list[st
             wl.write(r["low"])
         w1.close(outdir / "bitmap.1.gzi")
         wl.close(outdir / f"bitmap.{step}.gzi")
-        low_all = np.concatenate([r["low"] for r in res["chroms"]]) if res["chroms"] else np.zeros((0, engine.row_bytes), np.uint8)
     else:
         shutil.rmtree(outdir)
         raise ValueError(f"bgzf={bgzf!r}: expected 'gpu' or 'zlib'")
     col = res["col_sums"]
     nks = [r["nkmers"] for r in res["chroms"]]
+    pc_counts = engine.anchor_paircount_bins(nks, umap_bin_size)      # from the low-res rows still on the device
     write_text_files(outdir, name, [c for c, _ in recs], nks, [r["binlen"] for r in res["chroms"]],
-                     [r["bin_hist"] for r in res["chroms"]], col, low_all, engine.n_local, step, genome_names, umap_bin_size)
+                     [r["bin_hist"] for r in res["chroms"]], col, pc_counts, engine.n_local, step, genome_names, umap_bin_size)
     if final.exists():
         shutil.rmtree(final)
     os.replace(outdir, final)

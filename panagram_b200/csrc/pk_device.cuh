@@ -264,6 +264,42 @@ __device__ __forceinline__ int pk_g32_insert(const PkTable t, uint64_t canon, ui
     }
     return 4;
 }
+// Slot q (bucket q / slots-per-bucket) of a group table back to (canonical k-mer, its hash, membership mask): the
+// remainder comes from the slot, the key bits the slot does not store from the HOME bucket (bucket - displacement),
+// by inverting the table's hash — (X << sh) | low for the one X that maps to the home bucket (n_buckets >= 2^eb
+// makes it unique). false for an empty slot.
+__device__ __forceinline__ bool pk_group_slot_decode(const PkTable t, const PkKeySpec ks, uint64_t q, uint64_t &canon, uint32_t &h, uint32_t &mask) {
+    uint32_t b, disp, eb, m;
+    uint64_t rem;
+    if (t.fmt == PK_TFMT_G32) {
+        const uint32_t v = ((const uint32_t *)t.slots)[q];
+        if (v == PK_EMPTY32) return false;
+        b = (uint32_t)(q >> 3); disp = v & 15u; mask = v >> PK_G32_MASK_SHIFT;
+        rem = (v >> PK_S32_DISP_BITS) & PK_G32_REM_MASK;
+        eb = 2 * ks.k > PK_G32_REM_BITS ? 2 * ks.k - PK_G32_REM_BITS : 0;
+        m = pk_mix32((uint32_t)rem);
+        if (eb == 0) { canon = rem; h = m; return true; }
+    } else {
+        const unsigned long long v = t.slots[q];
+        if (v == PK_EMPTY) return false;
+        b = (uint32_t)(q >> 2); disp = (uint32_t)v & 15u; mask = (uint32_t)(v >> PK_U_MASK_SHIFT);
+        rem = (v >> PK_S32_DISP_BITS) & PK_U_REM_MASK;
+        if (2 * ks.k <= PK_U_REM_BITS) { canon = rem; h = pk_key_hash(canon, ks); return true; }
+        // 2k > 52: only the S64 per-genome format reaches here (S32 covers k <= 24), hash = pk_key_hash's S64 branch
+        eb = 2 * ks.k - PK_U_REM_BITS;
+        m = pk_hash64(rem);
+    }
+    const uint32_t home = b >= disp ? b - disp : b + t.n_buckets - disp;
+    const uint32_t sh = 32 - eb, low = eb < 32 ? m >> eb : 0u;
+    const uint32_t hmin = (uint32_t)((((uint64_t)home << 32) + t.n_buckets - 1) / t.n_buckets);    // smallest hash of the home bucket
+    uint32_t X = hmin >> sh;
+    h = (X << sh) | low;
+    if (__umulhi(h, t.n_buckets) != home) { X = (X + 1) & (eb < 32 ? (1u << eb) - 1 : 0xffffffffu); h = (X << sh) | low; }
+    const uint32_t hi = X ^ ((m * 0x9E3779B1u) >> sh);
+    canon = ((uint64_t)hi << (t.fmt == PK_TFMT_G32 ? PK_G32_REM_BITS : PK_U_REM_BITS)) | rem;
+    return true;
+}
+
 // format-dispatching forms (t.fmt)
 __device__ __forceinline__ uint32_t pk_group_lookup(const PkTable t, uint64_t canon, uint32_t h, uint32_t g0, uint32_t ng, const PkKeySpec ks);
 __device__ __forceinline__ int pk_group_insert(const PkTable t, uint64_t canon, uint32_t h, uint32_t bit);

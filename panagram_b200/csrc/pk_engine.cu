@@ -70,12 +70,14 @@ struct pk_engine {
     uint8_t *g_rows = nullptr; uint64_t g_rows_cap = 0;
     uint8_t *g_low = nullptr; uint64_t g_low_cap = 0;
     uint32_t *g_u32 = nullptr; uint64_t g_u32_cap = 0;
+    uint64_t last_lowtot = 0;                   // low-res rows the last anchoring call left in g_low
     unsigned long long *d_hist = nullptr;       // per-chromosome bin histograms
     uint64_t hist_cap = 0;
     cudaEvent_t pev[6] = {};                    // around K1 / K2 / K3 / spill / K4 of the last partitioned launch
     int unpermute = 1;
     int e2e_batches = 2;                        // batches of whole chromosomes per pk_anchor_genome call (copy/compute overlap)
     uint64_t e2e_batch_min = 32ull << 20;       // ... for genomes of at least this many positions
+    int e2e_batch_force = 0;                    // set by an explicit "e2e_batches" knob: skip the table-size rule
     bool pev_valid = false;
     PkPartTune tune{};                          // tuning state of the partitioned probe (pk_engine_tune / PK_K3* environment)
     PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
@@ -682,6 +684,36 @@ extern "C" int pk_interleave_device(pk_engine *e, const void *d_planes, uint32_t
     return PK_OK;
 }
 
+// ------------------------------------------------------------------ k-mer sample for genome distances
+extern "C" int pk_engine_sample_kmers(pk_engine *e, uint32_t hmax, uint64_t *keys, uint32_t *tags, uint64_t cap, uint64_t *n_out) {
+    NEED_FINAL(e);
+    if (!n_out || (cap && (!keys || !tags))) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (e->h_utables.empty()) { pk_set_error("k-mer sampling reads the group tables: they are switched off or could not be built"); return PK_ESTATE; }
+    int rc = set_device(e); if (rc) return rc;
+    unsigned long long *d_keys = nullptr, *d_n = nullptr;
+    uint32_t *d_tags = nullptr;
+    struct Freer { void *p; ~Freer() { cudaFree(p); } };
+    CU(cudaMalloc(&d_keys, std::max<uint64_t>(cap, 1) * 8)); Freer f1{d_keys};
+    CU(cudaMalloc(&d_tags, std::max<uint64_t>(cap, 1) * 4)); Freer f2{d_tags};
+    CU(cudaMalloc(&d_n, 8)); Freer f3{d_n};
+    CU(cudaMemsetAsync(d_n, 0, 8, e->stream));
+    const int take_all = hmax == 0;
+    for (uint32_t u = 0; u < e->h_utables.size(); u++)
+        pk_launch_sample_group(e->h_utables[u], e->ks, u, hmax, take_all, d_keys, d_tags, cap, d_n, e->stream);
+    pk_launch_sample_stash(e->ks, e->gfmt == 1, hmax, take_all, d_keys, d_tags, cap, d_n, e->stream);
+    CU(cudaGetLastError());
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, d_n, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *n_out = n;
+    if (n > cap) { pk_set_error("sample holds %llu k-mers, the buffers %llu", n, (unsigned long long)cap); return PK_ENOMEM; }
+    if (n) {
+        CU(cudaMemcpy(keys, d_keys, n * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(tags, d_tags, n * 4, cudaMemcpyDeviceToHost));
+    }
+    return PK_OK;
+}
+
 // ------------------------------------------------------------------ peer memory (multi-GPU, process per GPU)
 extern "C" int pk_device_alloc(pk_engine *e, void **d_ptr, size_t bytes) {
     if (!e || !d_ptr) { pk_set_error("null argument"); return PK_EINVAL; }
@@ -1039,7 +1071,15 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     struct Batch { uint32_t c0, c1; uint64_t base, npos; PkPartPlan pl; };
     std::vector<Batch> batches;
     uint32_t nb = 1;
-    if (pipelined && e->e2e_batches > 1 && npos >= e->e2e_batch_min) nb = (uint32_t)e->e2e_batches;
+    if (pipelined && e->e2e_batches > 1 && npos >= e->e2e_batch_min) {
+        // every batch streams the tables once more (~5 TB/s) and hides about half of the PCIe copies (~52 GB/s):
+        // worth it while table bytes < ~48 x copied bytes (configs[1]: 2.6 GB vs 13 GB; 64 genomes at k=31: 114 vs 65 GB)
+        double table_bytes = 0;
+        if (!e->h_utables.empty()) for (const PkTable &t : e->h_utables) table_bytes += 32.0 * t.n_buckets;
+        else for (const HostTable &t : e->tabs) table_bytes += 32.0 * t.dev.n_buckets;
+        const double copied = (double)ltot + (plane ? 0.0 : (double)postot * rb);
+        if (table_bytes < 48.0 * copied || e->e2e_batch_force) nb = (uint32_t)e->e2e_batches;
+    }
     if (pipelined && npos > sub) nb = std::max<uint32_t>(nb, (uint32_t)((npos + sub - 1) / sub));
     for (int attempt = 0; attempt < 4; attempt++) {
         batches.clear();
@@ -1177,6 +1217,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     CU(cudaEventElapsedTime(&e->stats.total_ms, e->ev[0], e->ev[5]));
     e->stats.positions = postot;
     e->stats.probes = postot * N;
+    e->last_lowtot = (!plane && ((bitmap_low != nullptr) || z)) ? lowtot : 0;
     return PK_OK;
 }
 
@@ -1199,6 +1240,45 @@ extern "C" int pk_anchor_genome_plane(pk_engine *e, uint32_t n_chroms, const cha
     if (row_stride < e->row_bytes) { pk_set_error("row_stride %u below the shard's %u row bytes", row_stride, e->row_bytes); return PK_EINVAL; }
     const PlaneOut p{(uint8_t *)d_plane, plane_rows, row_stride};
     return anchor_genome_impl(e, n_chroms, seqs, lens, nullptr, nullptr, nullptr, nullptr, nkmers_out, nullptr, &p);
+}
+
+extern "C" int pk_paircount_bins_device(pk_engine *e, const void *d_rows_low, uint32_t row_stride, uint32_t n_cols, uint64_t n_rows,
+                                        uint32_t rows_per_bin, void *d_counts, void *stream) {
+    if (!e || !d_rows_low || !d_counts) { pk_set_error("null argument"); return PK_EINVAL; }
+    if (n_cols == 0 || n_cols > 8 * row_stride || n_cols > 8192 || rows_per_bin == 0) { pk_set_error("bad n_cols %u / rows_per_bin %u", n_cols, rows_per_bin); return PK_EINVAL; }
+    int rc = set_device(e); if (rc) return rc;
+    pk_launch_paircount_bins((const uint8_t *)d_rows_low, row_stride, n_cols, n_rows, rows_per_bin, (uint32_t *)d_counts,
+                             stream ? (pk_stream_t)stream : e->stream);
+    CU(cudaGetLastError());
+    return PK_OK;
+}
+
+// Pair-count bins of the anchor the last pk_anchor_genome / pk_anchor_genome_bgzf call processed, from its low-res rows
+// (still resident on the device): counts[sum_c ceil(n_low_c / rows_per_bin)][N_local], chromosome after chromosome.
+extern "C" int pk_anchor_paircount_bins(pk_engine *e, uint32_t n_chroms, const uint64_t *nkmers, uint32_t bin_positions, uint32_t *counts) {
+    NEED_FINAL(e);
+    if (!nkmers || !counts) { pk_set_error("null argument"); return PK_EINVAL; }
+    const uint32_t step = e->cfg.lowres_step, rb = e->row_bytes, N = e->n_local;
+    if (bin_positions < step) { pk_set_error("bin of %u positions is shorter than the low-res step %u", bin_positions, step); return PK_EINVAL; }
+    const uint32_t rpb = (bin_positions + step - 1) / step;
+    uint64_t lowtot = 0, bins = 0;
+    for (uint32_t c = 0; c < n_chroms; c++) { const uint64_t nl = (nkmers[c] + step - 1) / step; lowtot += nl; bins += (nl + rpb - 1) / rpb; }
+    if (!e->g_low || e->last_lowtot != lowtot) { pk_set_error("the last anchoring call left %llu low-res rows, the chromosome list describes %llu", (unsigned long long)e->last_lowtot, (unsigned long long)lowtot); return PK_ESTATE; }
+    if (!bins) return PK_OK;
+    int rc = set_device(e); if (rc) return rc;
+    uint32_t *d_counts = nullptr;
+    CU(cudaMalloc(&d_counts, bins * N * sizeof(uint32_t)));
+    struct Freer { void *p; ~Freer() { cudaFree(p); } } f{d_counts};
+    uint64_t lo = 0, bo = 0;
+    for (uint32_t c = 0; c < n_chroms; c++) {
+        const uint64_t nl = (nkmers[c] + step - 1) / step;
+        pk_launch_paircount_bins(e->g_low + lo * rb, rb, N, nl, rpb, d_counts + bo * N, e->stream);
+        lo += nl; bo += (nl + rpb - 1) / rpb;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts, d_counts, bins * N * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return PK_OK;
 }
 
 extern "C" uint64_t pk_bgzf_bound(uint64_t n_bytes) { return pk_bgzf_bound_impl(n_bytes); }
@@ -1293,7 +1373,7 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
         return PK_OK;
     }
     else if (n == "e2e_batch_min") { e->e2e_batch_min = value < 0 ? 0 : (uint64_t)value; return PK_OK; }
-    else if (n == "e2e_batches") { if (value < 1 || value > 8) { pk_set_error("e2e_batches %d out of 1..8", value); return PK_EINVAL; } e->e2e_batches = value; return PK_OK; }
+    else if (n == "e2e_batches") { if (value < 1 || value > 8) { pk_set_error("e2e_batches %d out of 1..8", value); return PK_EINVAL; } e->e2e_batches = value; e->e2e_batch_force = 1; return PK_OK; }
     else if (n == "unpermute") {
         if (e->unpermute != value) {       // the scratch layout depends on it: drop it, the next launch re-allocates
             int rc = set_device(e); if (rc) return rc;

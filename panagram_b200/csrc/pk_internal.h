@@ -92,6 +92,10 @@ void pk_launch_count_bits(const uint8_t *d_recs, uint64_t n, uint32_t rec_size, 
 void pk_launch_union_merge(PkTable src, uint32_t n_src_buckets, uint32_t hshift, PkKeySpec ks, PkTable dst, uint32_t bit, uint32_t g_local,
                            int use_stash, unsigned long long *d_counters /*[4]*/, pk_stream_t s);
 void pk_launch_union_merge_stash(PkKeySpec ks, PkTable dst, uint32_t g0, uint32_t ng, unsigned long long *d_counters, pk_stream_t s);
+void pk_launch_sample_group(PkTable t, PkKeySpec ks, uint32_t group, uint32_t hmax, int take_all, unsigned long long *d_keys, uint32_t *d_tags,
+                            uint64_t cap, unsigned long long *d_n, pk_stream_t s);
+void pk_launch_sample_stash(PkKeySpec ks, int g32, uint32_t hmax, int take_all, unsigned long long *d_keys, uint32_t *d_tags, uint64_t cap,
+                            unsigned long long *d_n, pk_stream_t s);
 void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
                      const PkTable *d_tables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                      uint32_t col_offset, pk_stream_t s);
@@ -103,6 +107,8 @@ void pk_launch_items_group(const void *d_buf, const uint32_t *d_counts, const un
 void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
                       uint64_t binlen, unsigned long long *d_bin_hist, unsigned long long *d_col_sums,
                       uint8_t *d_rows_low, uint32_t step, pk_stream_t s);
+void pk_launch_paircount_bins(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t n_rows, uint32_t rows_per_bin,
+                              uint32_t *d_counts, pk_stream_t s);
 void pk_launch_interleave(const uint8_t *d_planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,
                           uint32_t row_stride, pk_stream_t s);
 int pk_launch_gather_interleave(const void *const *planes, uint32_t n_ranks, uint64_t n, uint32_t w, uint8_t *d_rows,

@@ -9,6 +9,8 @@
 //   interleave all-gathered column planes -> rows          (byte interleave of cpp/anchor.cpp:154-165 across ranks)
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "pk_internal.h"
 #include "pk_device.cuh"
 #include "pk_gather.cuh"
@@ -334,6 +336,47 @@ void pk_launch_union_merge(PkTable src, uint32_t n_src_buckets, uint32_t hshift,
     union_merge_kernel<<<grid_for(total), 256, 0, s>>>(src, n_src_buckets, hshift, ks, dst, bit, g_local, use_stash, d_counters);
 }
 
+// A uniform sample of the k-mers of a group table with their membership masks: every k-mer whose hash is below
+// `hmax` (a hash of the k-mer alone, so the SAME k-mers are sampled in every group table of every engine of a
+// sharded run: a FracMinHash sketch; take_all lists everything). Feeds the pairwise
+// Jaccard / Mash distances of genome_dist.tsv (workflow/Snakefile:124-149 runs `mash sketch -s 10000` +
+// `mash triangle` for that). out_keys/out_tags[cap]; tag = (group << 8) | mask; *n_out counts every hit (may exceed cap).
+__global__ void __launch_bounds__(256) sample_group_kernel(PkTable t, PkKeySpec ks, uint32_t group, uint32_t hmax, int take_all,
+                                                           uint64_t n_slots, unsigned long long *__restrict__ out_keys,
+                                                           uint32_t *__restrict__ out_tags, uint64_t cap, unsigned long long *__restrict__ n_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n_slots; q += stride) {
+        uint64_t canon; uint32_t h, mask;
+        if (!pk_group_slot_decode(t, ks, q, canon, h, mask)) continue;
+        if (!take_all && pk_hash64(canon) >= hmax) continue;        // a hash of the k-mer alone: the same sample whatever the slot format
+        const unsigned long long at = atomicAdd(n_out, 1ull);
+        if (at < cap) { out_keys[at] = canon; out_tags[at] = (group << 8) | mask; }
+    }
+}
+// the engine-wide stash (k-mers that found no room within 15 buckets of home): same sample rule, one bit per entry
+__global__ void __launch_bounds__(256) sample_stash_kernel(PkKeySpec ks, int g32, uint32_t hmax, int take_all, unsigned long long *__restrict__ out_keys,
+                                                           uint32_t *__restrict__ out_tags, uint64_t cap, unsigned long long *__restrict__ n_out) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= PK_STASH_SLOTS || !ks.stash) return;
+    const unsigned long long e = ks.stash[i];
+    if (e == PK_EMPTY) return;
+    const uint32_t g = (uint32_t)(e >> 48);
+    const uint64_t canon = e & 0x0000FFFFFFFFFFFFull;
+    (void)g32;
+    if (!take_all && pk_hash64(canon) >= hmax) return;
+    const unsigned long long at = atomicAdd(n_out, 1ull);
+    if (at < cap) { out_keys[at] = canon; out_tags[at] = ((g / PK_U_GROUP) << 8) | (1u << (g % PK_U_GROUP)); }
+}
+void pk_launch_sample_group(PkTable t, PkKeySpec ks, uint32_t group, uint32_t hmax, int take_all, unsigned long long *d_keys, uint32_t *d_tags,
+                            uint64_t cap, unsigned long long *d_n, pk_stream_t s) {
+    const uint64_t n_slots = (uint64_t)t.n_buckets * (t.fmt == PK_TFMT_G32 ? 8 : 4);
+    sample_group_kernel<<<grid_for(n_slots), 256, 0, s>>>(t, ks, group, hmax, take_all, n_slots, d_keys, d_tags, cap, d_n);
+}
+void pk_launch_sample_stash(PkKeySpec ks, int g32, uint32_t hmax, int take_all, unsigned long long *d_keys, uint32_t *d_tags, uint64_t cap,
+                            unsigned long long *d_n, pk_stream_t s) {
+    sample_stash_kernel<<<PK_STASH_SLOTS / 256, 256, 0, s>>>(ks, g32, hmax, take_all, d_keys, d_tags, cap, d_n);
+}
+
 // ------------------------------------------------------------------ probe (direct)
 // One thread per position; for each local genome one 32 B bucket load (LDG.256), U loads in
 // flight per thread. Row bits accumulate in a register and are stored once per 32 genomes.
@@ -647,6 +690,37 @@ void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_col
         if (l1 > l0)
             lowres_kernel<<<grid_for(l1 - l0), 256, 0, s>>>(d_rows, row_stride, (n_cols + 7) / 8, p_first, l0, l1 - l0, step, d_rows_low);
     }
+}
+
+// Pair-count bins (Index.bitmap_to_paircount_bins, panagram/index.py:454-459, the input of the UMAP CSVs): per bin of
+// `rows_per_bin` consecutive low-res rows of ONE chromosome, the number of rows in which each genome's bit is set.
+// One block per bin; counts[bin][g], uint32.
+__global__ void __launch_bounds__(256) paircount_bins_kernel(const uint8_t *__restrict__ rows, uint32_t row_stride, uint32_t n_cols,
+                                                             uint64_t n_rows, uint32_t rows_per_bin, uint32_t *__restrict__ counts) {
+    extern __shared__ unsigned int sh_cnt[];            // [n_cols]
+    for (uint32_t q = threadIdx.x; q < n_cols; q += blockDim.x) sh_cnt[q] = 0;
+    __syncthreads();
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_bin;
+    const uint64_t r1 = min(n_rows, r0 + rows_per_bin);
+    const uint32_t nbytes = (n_cols + 7) / 8;
+    for (uint64_t q = r0 * nbytes + threadIdx.x; q < r1 * nbytes; q += blockDim.x) {
+        const uint64_t r = q / nbytes;
+        const uint32_t b = (uint32_t)(q - r * nbytes);
+        uint32_t v = rows[r * row_stride + b];
+        while (v) {
+            const uint32_t j = __ffs(v) - 1;
+            v &= v - 1;
+            if (8 * b + j < n_cols) atomicAdd(&sh_cnt[8 * b + j], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < n_cols; q += blockDim.x) counts[(uint64_t)blockIdx.x * n_cols + q] = sh_cnt[q];
+}
+void pk_launch_paircount_bins(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t n_rows, uint32_t rows_per_bin,
+                              uint32_t *d_counts, pk_stream_t s) {
+    if (!n_rows) return;
+    const unsigned nbins = (unsigned)((n_rows + rows_per_bin - 1) / rows_per_bin);
+    paircount_bins_kernel<<<nbins, 256, n_cols * sizeof(unsigned int), s>>>(d_rows, row_stride, n_cols, n_rows, rows_per_bin, d_counts);
 }
 
 // ------------------------------------------------------------------ interleave / unpack

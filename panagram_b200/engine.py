@@ -109,6 +109,25 @@ class Engine:
             return None
         return {f: getattr(s, f) for f, _ in s._fields_}
 
+    def sample_kmers(self, frac: float = 1.0) -> tuple[np.ndarray, np.ndarray]:
+        """(keys uint64 [n], genome bit matrix rows as (local_group, mask8) tags uint32 [n]): the k-mers x of the local
+        genomes with hash32(x) < frac * 2^32 (frac >= 1: all of them), each once per group of 8 genomes
+        (pk_engine_sample_kmers)."""
+        hmax = 0 if frac >= 1.0 else max(1, int(frac * 2.0 ** 32))
+        total = sum((self.group_stats(u) or {"n_keys": 0})["n_keys"] for u in range((self.n_local + 7) // 8))
+        cap = int(total * min(frac, 1.0) * 1.1) + 70_000
+        for _ in range(3):
+            keys = np.empty(cap, dtype=np.uint64)
+            tags = np.empty(cap, dtype=np.uint32)
+            n = C.c_uint64(0)
+            rc = self._L.pk_engine_sample_kmers(self._h, hmax, keys.ctypes.data, tags.ctypes.data, cap, C.byref(n))
+            if rc == -4 and n.value > cap:              # PK_ENOMEM: the sample is larger than expected
+                cap = int(n.value) + 1024
+                continue
+            check(rc)
+            return keys[:n.value], tags[:n.value]
+        raise RuntimeError("pk_engine_sample_kmers: sample size kept growing")
+
     # ---- hot path, host buffers --------------------------------------------
     def bin_len(self, nkmers: int) -> int:
         return int(self._L.pk_bin_len(C.byref(self.cfg), nkmers))
@@ -253,6 +272,27 @@ class Engine:
         nko = (C.c_uint64 * n)()
         check(self._L.pk_anchor_genome_plane(self._h, n, ptrs, lens, d_plane, plane_rows, row_stride or self.row_bytes, nko))
         return [int(x) for x in nko]
+
+    def anchor_paircount_bins(self, nkmers: list[int], bin_positions: int) -> list[np.ndarray]:
+        """Per chromosome the [bins, N_local] counts of low-res rows with each genome's bit set, per bin of
+        `bin_positions` positions, for the anchor the last anchor_genome / anchor_genome_bgzf call processed — reduced
+        on the device from its low-res rows (pk_anchor_paircount_bins)."""
+        step = self.lowres_step
+        rpb = (bin_positions + step - 1) // step
+        nb = [(((nk + step - 1) // step) + rpb - 1) // rpb for nk in nkmers]
+        out = np.zeros((max(sum(nb), 1), self.n_local), dtype=np.uint32)
+        arr = (C.c_uint64 * len(nkmers))(*[int(x) for x in nkmers])
+        check(self._L.pk_anchor_paircount_bins(self._h, len(nkmers), arr, bin_positions, out.ctypes.data))
+        res, o = [], 0
+        for n in nb:
+            res.append(out[o:o + n])
+            o += n
+        return res
+
+    def paircount_bins_device(self, d_rows_low: int, row_stride: int, n_cols: int, n_rows: int, rows_per_bin: int,
+                              d_counts: int, stream: int | None = None):
+        check(self._L.pk_paircount_bins_device(self._h, d_rows_low, row_stride, n_cols, n_rows, rows_per_bin, d_counts,
+                                               self._st(stream)))
 
     def bgzf_bound(self, nbytes: int) -> tuple[int, int]:
         return int(self._L.pk_bgzf_bound(nbytes)), int(self._L.pk_bgzf_gzi_bound(nbytes))

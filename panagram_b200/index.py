@@ -150,6 +150,19 @@ class Index:
         eng = Engine(self.cfg.k, len(self.samples), genome_begin, genome_end, device=self.device, **self._engine_kw())
         return self.populate(eng, log)
 
+    def write_genome_dist(self, records, frac: float, log=print):
+        """genome_dist.tsv (rule mash_triangle, workflow/Snakefile:139-149; read at `panagram view` start-up,
+        view.py:64 -> figs.py:50-59) from the k-mer samples of all engines."""
+        from . import layout
+        t0 = time.perf_counter()
+        names = [s["name"] for s in self.samples]
+        inter = layout.pair_counts(records, len(names))
+        (self.prefix / "genome_dist.tsv").write_text(layout.genome_dist_tsv(names, inter, self.cfg.k))
+        log(f"genome_dist.tsv: Jaccard / Mash distances of {len(names)} genomes from {int(np.trace(inter))} sampled k-mer "
+            f"memberships (sampling fraction {frac:.3g}) ({time.perf_counter() - t0:.2f}s)")
+
+    DIST_SAMPLE_TARGET = 4_000_000       # distinct k-mers aimed for in the sample behind genome_dist.tsv (mash: 10000 per genome)
+
     def run(self, log=print, genome_ranks: int | None = None) -> dict:
         """Index.run (index.py:172-191): config, then — unless --prepare — the anchor rule for every
         anchor genome (workflow/Snakefile:33-48; cpp/Snakefile:35-55 runs them in one process,
@@ -176,6 +189,10 @@ class Index:
         out = {}
         if not dist:
             eng = self.build_engine(log=log)
+            total = sum((eng.group_stats(u) or {"n_keys": 0})["n_keys"] for u in range((eng.n_local + 7) // 8))
+            frac = min(1.0, self.DIST_SAMPLE_TARGET / max(total, 1))
+            keys, tags = eng.sample_kmers(frac)
+            self.write_genome_dist([(keys, tags, 0)], frac, log)
             for s in anchors:
                 t0 = time.perf_counter()
                 out[s["name"]] = anchor_mod.anchor_fasta(eng, s["name"], s["fasta"], self.prefix / "anchor" / s["name"],
@@ -189,6 +206,21 @@ class Index:
         qlog = log if sh.gi == 0 else (lambda m: None)
         self.populate(sh.engine, qlog)
         dist.barrier()                                   # rank 0 has written the config; every shard is built
+        # genome_dist.tsv: the ranks of genome group 0 sample their shards with one common fraction, rank 0 merges
+        import torch
+        eng = sh.engine
+        tot = torch.tensor([float(sum((eng.group_stats(u) or {"n_keys": 0})["n_keys"] for u in range((eng.n_local + 7) // 8)))
+                            if sh.pi == 0 else 0.0], dtype=torch.float64, device=sh.dev)
+        dist.all_reduce(tot)
+        frac = min(1.0, self.DIST_SAMPLE_TARGET / max(float(tot.item()), 1.0))
+        mine = None
+        if sh.pi == 0:
+            keys, tags = eng.sample_kmers(frac)
+            mine = (keys, tags, sh.begin)
+        allrec = [None] * world if rank == 0 else None
+        dist.gather_object(mine, allrec, dst=0)
+        if rank == 0:
+            self.write_genome_dist([r for r in allrec if r is not None], frac, qlog)
         for j, s in enumerate(anchors):
             if j % sh.rp != sh.pi:
                 continue

@@ -174,6 +174,16 @@ def paircount_bins(rows_low: np.ndarray, n_genomes: int, step: int, bin_size: in
     return bins[first] * bin_size, frac
 
 
+def paircount_frac(counts: np.ndarray, bin_size: int) -> tuple[np.ndarray, np.ndarray]:
+    """(bin starts, fractions) from per-bin per-genome counts [nbins, N] (pk_anchor_paircount_bins): every bin divided
+    by its maximum over genomes, 0/0 -> 0 (Index.bitmap_to_paircount_bins + the caller's fillna(0))."""
+    counts = np.asarray(counts, dtype=np.int64).reshape(len(counts), -1)
+    mx = counts.max(axis=1, keepdims=True) if counts.size else counts
+    with np.errstate(invalid="ignore", divide="ignore"):
+        frac = np.where(mx > 0, counts / np.maximum(mx, 1), 0.0)
+    return np.arange(counts.shape[0], dtype=np.int64) * bin_size, frac
+
+
 def umap_rows(chrom: str, starts: np.ndarray, frac: np.ndarray, bin_size: int, neighbors: int = 4, dist: float = 0.0,
               eps: float = 1.0, samples: int = 1) -> list[tuple]:
     """Genome.run_umap (index.py:1133-1156): UMAP(n_neighbors, min_dist, n_components=2, random_state=42) +
@@ -196,3 +206,87 @@ def umaps_csv(rows: list[tuple]) -> str:
     """chrom_umaps.csv (DataFrame.set_index("chrom").to_csv()) and genome_umap.csv (to_csv(index=False)) have the
     same text: header chrom,start,end,umap1,umap2,cluster (index.py:1128-1131)."""
     return "chrom,start,end,umap1,umap2,cluster\n" + "".join(",".join(map(str, r)) + "\n" for r in rows)
+
+
+# ---- genome_dist.tsv (SURVEY.md §8f N4) ----------------------------------------------------------------
+def kmer_sample_hash(keys: np.ndarray) -> np.ndarray:
+    """hash32 of pk_engine_sample_kmers' sampling rule (pk_hash64 in csrc/pk_device.cuh), restated for the tests and for
+    host-side sub-sampling."""
+    x = np.asarray(keys, dtype=np.uint64).copy()
+    x ^= x >> np.uint64(32)
+    x *= np.uint64(0x9E3779B97F4A7C15)
+    x ^= x >> np.uint64(29)
+    x *= np.uint64(0xBF58476D1CE4E5B9)
+    return (x >> np.uint64(32)).astype(np.uint32)
+
+
+def pair_counts(records: list[tuple[np.ndarray, np.ndarray, int]], n_genomes: int) -> np.ndarray:
+    """[N, N] intersection sizes (diagonal: set sizes) of the genomes' k-mer samples. records = one
+    (keys uint64 [n], tags uint32 [n], genome_begin) per engine as pk_engine_sample_kmers returns them: tag =
+    (local group << 8) | membership mask of genomes genome_begin + 8 * group + 0..7."""
+    keys = np.concatenate([r[0] for r in records]) if records else np.zeros(0, np.uint64)
+    tags = np.concatenate([r[1] for r in records]) if records else np.zeros(0, np.uint32)
+    base = np.concatenate([np.full(r[0].size, r[2], dtype=np.int64) for r in records]) if records else np.zeros(0, np.int64)
+    inter = np.zeros((n_genomes, n_genomes), dtype=np.float64)
+    if keys.size == 0:
+        return inter
+    order = np.argsort(keys, kind="stable")
+    ks = keys[order]
+    row = np.cumsum(np.r_[True, ks[1:] != ks[:-1]]) - 1            # index of the distinct k-mer of every record
+    n_rows = int(row[-1]) + 1
+    col0 = base[order] + 8 * (tags[order] >> 8).astype(np.int64)
+    mask = (tags[order] & 0xFF).astype(np.uint32)
+    chunk = 1 << 20
+    for r0 in range(0, n_rows, chunk):
+        lo, hi = np.searchsorted(row, [r0, r0 + chunk])
+        b = np.zeros((min(chunk, n_rows - r0), n_genomes), dtype=np.float32)
+        for bit in range(8):
+            sel = ((mask[lo:hi] >> bit) & 1).astype(bool)
+            cols = col0[lo:hi][sel] + bit
+            ok = cols < n_genomes
+            b[row[lo:hi][sel][ok] - r0, cols[ok]] = 1.0
+        inter += (b.T @ b).astype(np.float64)
+    return inter
+
+
+def mash_distance(jaccard: float, k: int) -> float:
+    """Mash distance of a Jaccard index j: -1/k * ln(2j / (1 + j)) (1 when j = 0) — Ondov et al. 2016, what `mash dist`
+    and `mash triangle` print."""
+    if jaccard <= 0:
+        return 1.0
+    if jaccard >= 1:
+        return 0.0
+    return max(0.0, -np.log(2.0 * jaccard / (1.0 + jaccard)) / k)
+
+
+def genome_dist_tsv(names: list[str], inter: np.ndarray, k: int) -> str:
+    """The edge list `mash triangle -C -E` writes (workflow/Snakefile:139-149) and make_all_genome_dend reads
+    (figs.py:50-59: f, t, d, p, x per line; only d is used): for every pair i > j one line
+    name_i, name_j, Mash distance, p-value, shared/total — here from the intersection / union sizes of the genomes'
+    k-mer samples instead of 10000-hash MinHash sketches. p-value: the probability of >= `shared` common k-mers among
+    `total` by chance, P[Binomial(total, r) >= shared] with r the expected Jaccard of two random k-mer sets of these
+    sizes (mash's own significance test); it is 0 for any pair of related genomes."""
+    try:
+        from scipy.stats import binom
+    except Exception:       # noqa: BLE001
+        binom = None
+    n = len(names)
+    size = np.diag(inter)
+    space = 4.0 ** k
+    lines = []
+    for i in range(1, n):
+        for j in range(i):
+            shared = inter[i, j]
+            total = size[i] + size[j] - shared
+            jac = shared / total if total > 0 else 0.0
+            d = mash_distance(jac, k)
+            px, py = 1.0 / (1.0 + space / max(size[i], 1.0)), 1.0 / (1.0 + space / max(size[j], 1.0))
+            r = px * py / (px + py - px * py)
+            if shared <= 0:
+                p = 1.0
+            elif binom is not None:
+                p = float(binom.sf(shared - 1, max(total, 1), r))
+            else:
+                p = 0.0
+            lines.append(f"{names[i]}\t{names[j]}\t{d:.6g}\t{p:.6g}\t{int(shared)}/{int(total)}\n")
+    return "".join(lines)

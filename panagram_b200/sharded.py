@@ -176,6 +176,7 @@ class ShardedAnchorer:
         self._host_rows = None       # page-locked staging of anchor_genome(rows_to_host=True), grow-only
         self._host_gz = None         # page-locked staging of the BGZF image of the slice
         self._i = 0
+        self.umap_bin_size = 100000  # positions per pair-count bin (Genome.write_umaps, index.py:1107)
         self.last = {}               # timings of the last anchor_genome call (ms)
 
     def owns(self, genome: int) -> bool:
@@ -312,6 +313,16 @@ class ShardedAnchorer:
             if self.rg > 1:
                 dist.all_reduce(red, group=self.group)
                 dist.all_reduce(low, group=self.group)           # disjoint supports: the sum is the union
+            # pair-count bins (the UMAP input) from the complete low-res rows, on the device
+            rpb = (self.umap_bin_size + step - 1) // step
+            pcn = [(nl + rpb - 1) // rpb for nl in nlow]
+            pc = torch.zeros((max(sum(pcn), 1), N), dtype=torch.int32, device=self.dev)
+            o = 0
+            for c, nl in enumerate(nlow):
+                if nl:
+                    eng.paircount_bins_device(low.data_ptr() + int(loff[c]) * rb, rb, N, nl, rpb, pc.data_ptr() + 4 * o * N,
+                                              self.stream.cuda_stream)
+                o += pcn[c]
             ev[3].record(self.stream)
             out = {"nkmers": nks, "slice": (s0, s1), "rows": rows[: s1 - s0], "binlen": binlen}
             if bgzf:
@@ -343,6 +354,8 @@ class ShardedAnchorer:
                            for c in range(len(nks))]
             out["col_sums"] = red_h[int(hoff[-1]):]
             out["low"] = low[: int(loff[-1])].cpu().numpy()
+            pc_h = pc.cpu().numpy().astype(np.uint32)
+            out["pc_counts"] = [pc_h[sum(pcn[:c]):sum(pcn[:c + 1])] for c in range(len(nks))]
         torch.cuda.synchronize(self.dev)
         self.last = {"probe_ms": ev[0].elapsed_time(ev[1]), "exchange_ms": ev[1].elapsed_time(ev[2]),
                      "reduce_ms": ev[2].elapsed_time(ev[3]), "bgzf_d2h_ms": ev[3].elapsed_time(ev[4])}
@@ -408,6 +421,7 @@ def anchor_fasta_sharded(sh: ShardedAnchorer, name: str, fasta, outdir, genome_n
         if nk < 1 or eng.bin_len(nk) == 0:
             raise ValueError(f"{fasta}: chromosome {cname!r} has {max(nk, 0)} k-mers; the reference "
                              "needs at least min_bin_count (cpp/anchor.cpp:116-120)")
+    sh.umap_bin_size = umap_bin_size
     res = sh.anchor_genome([s for _, s in recs], bgzf=True)
     lead = sh.gi == 0
     if lead:
@@ -435,7 +449,7 @@ def anchor_fasta_sharded(sh: ShardedAnchorer, name: str, fasta, outdir, genome_n
             (tmp / f"bitmap.{step}.gz").write_bytes(gz[: int(t[0])].cpu().numpy().tobytes())
             (tmp / f"bitmap.{step}.gzi").write_bytes(gzi.view(torch.uint8)[: int(t[1])].cpu().numpy().tobytes())
         anchor_mod.write_text_files(tmp, name, [c for c, _ in recs], res["nkmers"], res["binlen"], res["hist"],
-                                    res["col_sums"], low.reshape(-1, rb), sh.n_genomes, step, genome_names, umap_bin_size)
+                                    res["col_sums"], res["pc_counts"], sh.n_genomes, step, genome_names, umap_bin_size)
     if sh.rg > 1:
         dist.barrier(group=sh.group)                             # every rank's members are in the file
     if lead:

@@ -662,6 +662,15 @@ def test_panagram_index_cli_end_to_end(pan3, tmp_path, capsys):
         assert (d / "chrs.tsv").read_text() == exp["chrs.tsv"]
         assert (d / "bitsum.bins.tsv").read_text() == exp["bitsum.bins.tsv"]
         assert (d / "total_paircounts.csv").exists() and (d / "bitmap.1.gzi").exists()
+    # genome_dist.tsv (rule mash_triangle): exact Jaccard of the k-mer sets at this size -> Mash distance, lower triangle
+    sets = {n: set(oracle.canonical_kmers([q for _, q in anchor.parse_fasta(p, strip_cr=True)], 21).tolist()) for n, p in pan3["fasta"].items()}
+    lines = [l.split("\t") for l in (tmp_path / "idx" / "genome_dist.tsv").read_text().splitlines()]
+    names = list(pan3["fasta"])
+    assert [(l[0], l[1]) for l in lines] == [(names[i], names[j]) for i in range(1, 3) for j in range(i)]
+    for f, t, d, p, x in lines:
+        inter, union = len(sets[f] & sets[t]), len(sets[f] | sets[t])
+        assert x == f"{inter}/{union}"
+        assert abs(float(d) - layout.mash_distance(inter / union, 21)) < 1e-6 and 0.0 <= float(p) <= 1.0
     capsys.readouterr()
     assert main(["bitdump", str(tmp_path / "idx"), "g1", "chr2:100-110"]) == 0
     out = capsys.readouterr().out.split()
@@ -685,6 +694,49 @@ def test_panagram_index_cli_end_to_end(pan3, tmp_path, capsys):
 
 
 # ---- S32 slot format: quotienting must stay exact -------------------------------------------------
+@pytest.mark.parametrize("n_genomes,k,g32", [(3, 21, 0), (11, 13, 1), (20, 31, 0), (9, 21, 2), (8, 27, 0)])
+def test_kmer_sample_and_paircount_bins(n_genomes, k, g32):
+    """pk_engine_sample_kmers lists the k-mers of the group tables back — decoded from their slots, the key bits a slot
+    does not store recovered from the home bucket (64-bit slots at k <= 26 and k >= 27, 32-bit slots natural at k = 13
+    and forced at k = 21): all of them (== the sets the engine was given, with the right genome bits) and the
+    hash-threshold sample (== the subset below the threshold). pk_anchor_paircount_bins == the host restatement of
+    Index.bitmap_to_paircount_bins on the low-res rows."""
+    rng = np.random.default_rng(100 + n_genomes)
+    sb, ints, member, _ = random_case(rng, n_genomes, k, 60_000)
+    eng = Engine(k, n_genomes)
+    eng.tune(group_g32=g32)
+    for g in range(n_genomes):
+        eng.add_keys(g, ints[member[:, g]])
+    eng.finalize()
+    keys, tags = eng.sample_kmers(1.0)
+    got = {}
+    for x, t in zip(keys.tolist(), tags.tolist()):
+        for b in range(8):
+            if (t >> b) & 1:
+                got.setdefault(8 * (t >> 8) + b, set()).add(x)
+    for g in range(n_genomes):
+        assert got.get(g, set()) == set(ints[member[:, g]].tolist()), g
+    inter = layout.pair_counts([(keys, tags, 0)], n_genomes)
+    for i, j in ((0, 0), (1, 0), (n_genomes - 1, 1)):
+        assert inter[i, j] == int((member[:, i] & member[:, j]).sum())
+    frac = 0.3
+    k2, t2 = eng.sample_kmers(frac)
+    hmax = int(frac * 2.0 ** 32)
+    want = set(x for x in keys.tolist() if int(layout.kmer_sample_hash(np.array([x], dtype=np.uint64))[0]) < hmax)
+    assert set(k2.tolist()) == want and 0.2 * len(set(keys.tolist())) < len(want) < 0.4 * len(set(keys.tolist()))
+    # pair-count bins of the last anchored genome, reduced on the device
+    res = eng.anchor_genome([sb[:41_000], sb[41_000:]])
+    nks = [c["nkmers"] for c in res["chroms"]]
+    for bin_size in (100000, 1000):
+        pcs = eng.anchor_paircount_bins(nks, bin_size)
+        for c, pc in zip(res["chroms"], pcs):
+            starts, frac_h = layout.paircount_bins(c["low"], n_genomes, 100, bin_size)
+            s2, frac_d = layout.paircount_frac(pc, bin_size)
+            assert (starts == s2).all() and np.allclose(frac_h, frac_d)
+            bits = np.unpackbits(c["low"], axis=1, bitorder="little")[:, :n_genomes]
+            assert (pc.sum(axis=0) == bits.sum(axis=0)).all()
+
+
 @pytest.mark.parametrize("n_genomes,k,length", [(32, 21, 20_000_000), (64, 31, 20_000_000)])
 def test_many_genomes_at_20mbp_vs_c_oracle(n_genomes, k, length):
     """The default path (group tables — four of them at N=32, eight at N=64; partitioned probe; BGZF on the GPU) at

@@ -208,3 +208,55 @@ def test_s32_hash_is_invertible_from_slot_and_home_bucket():
         assert (((h3.astype(np.uint64) * np.uint64(nb)) >> np.uint64(32)) == home).all()
         back = ((X ^ f).astype(np.uint64) << np.uint64(28)) | lo.astype(np.uint64)
         assert (back == canon).all() and (h3 == h).all(), (k, nb)
+
+
+def test_genome_dist_from_kmer_samples():
+    """layout.pair_counts / genome_dist_tsv (genome_dist.tsv, rule mash_triangle, workflow/Snakefile:139-149; consumer
+    figs.py:50-59) against brute-force set arithmetic, records from two engines (genome shards [0,16) and [16,19))."""
+    rng = np.random.default_rng(1)
+    n = 19
+    univ = np.unique(rng.integers(0, 2 ** 42, size=5000, dtype=np.uint64))
+    sets = [set(univ[rng.random(univ.size) < p].tolist()) for p in rng.random(n)]
+    recs = []
+    for begin, end in ((0, 16), (16, 19)):
+        keys, tags = [], []
+        for grp in range((end - begin + 7) // 8):
+            gs = list(range(begin + 8 * grp, min(begin + 8 * grp + 8, end)))
+            for x in set().union(*[sets[g] for g in gs]):
+                keys.append(x)
+                tags.append((grp << 8) | sum(1 << b for b, g in enumerate(gs) if x in sets[g]))
+        recs.append((np.array(keys, dtype=np.uint64), np.array(tags, dtype=np.uint32), begin))
+    inter = layout.pair_counts(recs, n)
+    for i in range(n):
+        for j in range(n):
+            assert inter[i, j] == len(sets[i] & sets[j])
+    names = [f"g{i}" for i in range(n)]
+    lines = [l.split("\t") for l in layout.genome_dist_tsv(names, inter, 21).splitlines()]
+    assert len(lines) == n * (n - 1) // 2 and all(len(l) == 5 for l in lines)
+    assert [(l[0], l[1]) for l in lines[:3]] == [("g1", "g0"), ("g2", "g0"), ("g2", "g1")]       # mash triangle order
+    for f, t, d, p, x in lines:
+        i, j = names.index(f), names.index(t)
+        u = len(sets[i] | sets[j])
+        assert x == f"{len(sets[i] & sets[j])}/{u}"
+        jac = len(sets[i] & sets[j]) / u if u else 0.0
+        want = 1.0 if jac == 0 else -np.log(2 * jac / (1 + jac)) / 21
+        assert abs(float(d) - want) < 1e-5 and 0.0 <= float(p) <= 1.0
+    assert layout.mash_distance(1.0, 21) == 0.0 and layout.mash_distance(0.0, 21) == 1.0
+    # what make_all_genome_dend does with the file (figs.py:50-59)
+    dm = np.zeros((n, n))
+    for f, t, d, p, x in lines:
+        dm[names.index(f)][names.index(t)] = d
+        dm[names.index(t)][names.index(f)] = d
+    assert (dm == dm.T).all() and (np.diag(dm) == 0).all()
+
+
+def test_paircount_frac_matches_bitmap_to_paircount_bins():
+    rng = np.random.default_rng(9)
+    n_genomes, step, bin_size = 11, 100, 100000
+    rows = rng.integers(0, 256, size=(2503, 2), dtype=np.uint8)
+    starts, frac = layout.paircount_bins(rows, n_genomes, step, bin_size)
+    bits = np.unpackbits(rows, axis=1, bitorder="little")[:, :n_genomes]
+    rpb = bin_size // step
+    counts = np.stack([bits[b:b + rpb].sum(axis=0) for b in range(0, len(rows), rpb)])
+    s2, f2 = layout.paircount_frac(counts, bin_size)
+    assert (starts == s2).all() and np.allclose(frac, f2)
