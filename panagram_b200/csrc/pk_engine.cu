@@ -83,6 +83,7 @@ struct pk_engine {
     PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
     PkPartPlan sc_plan{};
     int l2_prefetch = 1;
+    int gather_dst_mode = 1;                    // narrow rows: output-aligned 16-byte stores in the exchange kernel (pk_gather.cuh)
     int rows_persist = 0;                       // direct row scatter (unpermute 0): keep the rows of a launch in persisting L2
     unsigned long long *d_colsums = nullptr;    // [n_local]
     // staging for KMC ingestion
@@ -798,6 +799,14 @@ extern "C" int pk_gather_slice_device(pk_engine *e, const void *const *d_planes,
         }
         CU(cudaMemcpy(e->d_segs, e->seg_host.data(), sizeof(PkgSeg) * n_segs, cudaMemcpyHostToDevice));
     }
+    uint64_t total_rows = 0;
+    if (e->gather_dst_mode && pkg_dst_mode_ok(e->seg_host.data(), n_segs, n_ranks, w, row_stride, row_bytes, d_rows, &total_rows)) {
+        if (pk_launch_gather_slice_dst(d_planes, n_ranks, plane_rows, w, e->d_segs, n_segs, total_rows, (uint8_t *)d_rows, s)) {
+            pk_set_error("gather_slice launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return PK_ECUDA;
+        }
+        return PK_OK;
+    }
     if (pk_launch_gather_slice(d_planes, n_ranks, plane_rows, w, e->d_segs, n_segs, e->seg_chunks, (uint8_t *)d_rows, row_stride, row_bytes, s)) {
         pk_set_error("gather_slice launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return PK_ECUDA;
@@ -1353,6 +1362,7 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     else if (n == "k3w_variant") { if (value >= -1 && value < pk_part_n_wvariants()) e->tune.wvariant = value; return PK_OK; }
     else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } e->tune.wgroup = value; return PK_OK; }
     else if (n == "k3_rank_atomic") { e->tune.rank_atomic = value ? 1 : 0; return PK_OK; }
+    else if (n == "gather_dst_mode") { e->gather_dst_mode = value ? 1 : 0; return PK_OK; }
     else if (n == "rows_persist") { e->rows_persist = value ? 1 : 0; return PK_OK; }
     else if (n == "k3_variant") { if (value >= -1 && value < pk_part_n_variants()) e->tune.variant = value; return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }

@@ -115,6 +115,8 @@ int pk_launch_gather_interleave(const void *const *planes, uint32_t n_ranks, uin
                                 uint32_t row_stride, pk_stream_t s);
 int pk_launch_gather_slice(const void *const *planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w, const void *d_segs,
                            uint32_t n_segs, uint64_t n_chunks, uint8_t *d_rows, uint32_t row_stride, uint32_t row_bytes, pk_stream_t s);
+int pk_launch_gather_slice_dst(const void *const *planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w, const void *d_segs,
+                               uint32_t n_segs, uint64_t total_rows, uint8_t *d_rows, pk_stream_t s);
 void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t byte_off, uint32_t n_bytes,
                            uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
 

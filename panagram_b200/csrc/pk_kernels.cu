@@ -869,6 +869,36 @@ static void gather_slice_launch(const PkgArgs &a, unsigned grid, pk_stream_t s) 
         default: gather_slice_kernel<RMAX, 0><<<grid, 256, 0, s>>>(a); break;
     }
 }
+template <int R, int W>
+__global__ void __launch_bounds__(256) gather_slice_dst_kernel(const __grid_constant__ PkgArgs a, const uint64_t total_rows) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < a.n_chunks; t += stride) pkg_gather_dst_chunk<R, W>(a, t, total_rows);
+}
+// narrow rows, segments back to back in the output: one 16-byte store per thread (pk_gather.cuh)
+int pk_launch_gather_slice_dst(const void *const *planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w, const void *d_segs,
+                               uint32_t n_segs, uint64_t total_rows, uint8_t *d_rows, pk_stream_t s) {
+    if (!total_rows) return 0;
+    PkgArgs a{};
+    for (uint32_t r = 0; r < n_ranks; r++) a.planes[r] = (const uint8_t *)planes[r];
+    a.n_ranks = n_ranks; a.w = w; a.plane_rows = plane_rows; a.segs = (const PkgSeg *)d_segs; a.n_segs = n_segs;
+    a.row_stride = n_ranks * w; a.row_bytes = n_ranks * w; a.rows = d_rows;
+    const uint32_t nr = 16 / (n_ranks * w);
+    a.n_chunks = (total_rows + nr - 1) / nr;
+    const uint64_t nb = (a.n_chunks + 255) / 256;
+    const unsigned grid = (unsigned)(nb < 148ull * 16 ? nb : 148ull * 16);
+    const uint32_t key = n_ranks * 100 + w;
+    switch (key) {
+        case 201: gather_slice_dst_kernel<2, 1><<<grid, 256, 0, s>>>(a, total_rows); break;
+        case 202: gather_slice_dst_kernel<2, 2><<<grid, 256, 0, s>>>(a, total_rows); break;
+        case 204: gather_slice_dst_kernel<2, 4><<<grid, 256, 0, s>>>(a, total_rows); break;
+        case 401: gather_slice_dst_kernel<4, 1><<<grid, 256, 0, s>>>(a, total_rows); break;
+        case 402: gather_slice_dst_kernel<4, 2><<<grid, 256, 0, s>>>(a, total_rows); break;
+        case 801: gather_slice_dst_kernel<8, 1><<<grid, 256, 0, s>>>(a, total_rows); break;
+        default: return -1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int pk_launch_gather_slice(const void *const *planes, uint32_t n_ranks, uint64_t plane_rows, uint32_t w, const void *d_segs,
                            uint32_t n_segs, uint64_t n_chunks, uint8_t *d_rows, uint32_t row_stride, uint32_t row_bytes, pk_stream_t s) {
     if (!n_chunks) return 0;

@@ -171,6 +171,7 @@ class ShardedAnchorer:
         self.k, self.step = k, self.engine.lowres_step
         self.dev = torch.device(f"cuda:{device}")
         self.stream = torch.cuda.Stream(device=self.dev)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._planes = None          # [2] ping-pong: {"rows", "own", "peers"}
         self._host_rows = None       # page-locked staging of anchor_genome(rows_to_host=True), grow-only
@@ -296,6 +297,15 @@ class ShardedAnchorer:
             if segs:
                 eng.gather_slice_device(pl["peers"], pl["rows"], self.w, segs, rows.data_ptr(), rb, rb, self.stream.cuda_stream)
             ev[2].record(self.stream)
+            if rows_to_host:
+                # the slice's rows go home on the copy stream while this stream reduces them
+                nb = (s1 - s0) * rb
+                if self._host_rows is None or self._host_rows.numel() < nb:
+                    self._host_rows = torch.empty(max(nb, 1), dtype=torch.uint8, pin_memory=True)
+                self.copy_stream.wait_stream(self.stream)
+                with torch.cuda.stream(self.copy_stream):
+                    self._host_rows[:nb].copy_(rows.view(-1)[:nb], non_blocking=True)
+                rows.record_stream(self.copy_stream)
             # reductions over this rank's rows, then summed over the group
             binlen = [eng.bin_len(nk) if nk else 0 for nk in nks]
             nbins = [(nk + b - 1) // b if b else 0 for nk, b in zip(nks, binlen)]
@@ -343,11 +353,8 @@ class ShardedAnchorer:
                 out["gz"] = self._host_gz[:ngz].numpy()           # page-locked staging, valid until the next call
                 out["gzi"] = self._host_gz[ngz:ngz + ngzi].numpy()
             if rows_to_host:
-                nb = (s1 - s0) * rb
-                if self._host_rows is None or self._host_rows.numel() < nb:
-                    self._host_rows = torch.empty(max(nb, 1), dtype=torch.uint8, pin_memory=True)
-                self._host_rows[:nb].copy_(rows.view(-1)[:nb], non_blocking=True)
-                out["rows_host"] = self._host_rows[:nb].numpy().reshape(s1 - s0, rb)
+                self.stream.wait_stream(self.copy_stream)
+                out["rows_host"] = self._host_rows[:(s1 - s0) * rb].numpy().reshape(s1 - s0, rb)
             ev[4].record(self.stream)
             red_h = red.cpu().numpy().astype(np.uint64)
             out["hist"] = [red_h[int(hoff[c]):int(hoff[c + 1])].reshape(nbins[c], N + 1) if nbins[c] else None
