@@ -84,7 +84,6 @@ struct pk_engine {
     PkPartPlan sc_plan{};
     int l2_prefetch = 1;
     int gather_dst_mode = 1;                    // narrow rows: output-aligned 16-byte stores in the exchange kernel (pk_gather.cuh)
-    int rows_persist = 0;                       // direct row scatter (unpermute 0): keep the rows of a launch in persisting L2
     unsigned long long *d_colsums = nullptr;    // [n_local]
     // staging for KMC ingestion
     uint8_t *h_stage = nullptr, *d_stage = nullptr;
@@ -827,10 +826,10 @@ static void free_scratch(pk_engine *e) {
 static int ensure_scratch(pk_engine *e, const PkPartPlan &pl) {
     const PkPartPlan &have = e->sc_plan;
     const uint32_t n_groups = (e->n_local + 31) / 32;
-    const uint64_t out_items = e->unpermute ? (uint64_t)n_groups * pk_part_obins() << pl.out_shift : 0;
+    const uint64_t out_bytes = e->unpermute ? pl.out_bytes : 0;
     if (e->sc.buf1 && have.buf1_items >= pl.buf1_items && have.buf2_items >= pl.buf2_items &&
         have.spill_items >= pl.spill_items && have.n_regions1 >= pl.n_regions1 && have.n_regions2 >= pl.n_regions2 &&
-        e->sc.out_items >= out_items)
+        e->sc.out_bytes >= out_bytes)
         return PK_OK;
     CU(cudaDeviceSynchronize());
     free_scratch(e);
@@ -842,13 +841,20 @@ static int ensure_scratch(pk_engine *e, const PkPartPlan &pl) {
     CU(cudaMalloc(&e->sc.spill_cursor, sizeof(unsigned long long)));
     CU(cudaMalloc(&e->sc.err, sizeof(uint32_t)));
     CU(cudaMemset(e->sc.err, 0, sizeof(uint32_t)));
-    if (out_items) {
-        CU(cudaMalloc(&e->sc.out_list, out_items * 8));
+    if (out_bytes) {
+        CU(cudaMalloc(&e->sc.out_list, out_bytes));
         CU(cudaMalloc(&e->sc.out_cursor, sizeof(uint32_t) * n_groups * pk_part_ocursor_words()));
     }
-    e->sc.out_items = out_items;
+    e->sc.out_bytes = out_bytes;
     e->sc_plan = pl;
     return PK_OK;
+}
+
+// one-byte rows written contiguously out of group tables: 4-byte result items in fine position bins, un-permuted through
+// shared-memory slices of the bitmap (pk_partition.cu)
+static int fine_out_ok(const pk_engine *e, uint32_t row_stride, uint32_t col_offset) {
+    if (!(e->unpermute && !e->h_utables.empty() && e->n_local <= 8 && row_stride == 1 && col_offset == 0)) return 0;
+    return e->gfmt == 1 ? 2 : 1;
 }
 
 // rows for positions [p0, p0+n): the partitioned path for large batches, the direct kernel otherwise
@@ -861,26 +867,8 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
         const bool part = mode == 2 || (mode == 0 && m >= (1ull << 20));
         if (part) {
             PkPartPlan pl;
-            pk_part_plan(m, e->tune, &pl);
+            pk_part_plan(m, e->tune, &pl, e->n_local, fine_out_ok(e, row_stride, col_offset));
             int rc = ensure_scratch(e, pl); if (rc) return rc;
-            if (e->rows_persist && !e->unpermute) {
-                // experiment: the launch's rows (m * row_stride bytes, scattered byte by byte by K3) as a persisting-L2
-                // window, so that a 32-byte sector is written to DRAM once, complete, instead of once per byte
-                int dev = e->cfg.device, maxp = 0, maxw = 0;
-                cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-                cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
-                cudaStreamAttrValue av{};
-                const size_t nbytes = std::min<size_t>((size_t)m * row_stride, (size_t)maxw);
-                av.accessPolicyWindow.base_ptr = d_rows + o * row_stride;
-                av.accessPolicyWindow.num_bytes = nbytes;
-                av.accessPolicyWindow.hitRatio = nbytes <= (size_t)maxp ? 1.0f : (float)maxp / (float)nbytes;
-                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-                static bool said = false;
-                if (!said) { fprintf(stderr, "[pkanchor] rows_persist: max persisting L2 %d MB, max window %d MB, window %zu MB, hit ratio %.2f\n", maxp >> 20, maxw >> 20, nbytes >> 20, av.accessPolicyWindow.hitRatio); said = true; }
-            }
             if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, probe_ks(e), e->d_tables, e->h_tables.data(),
                                             e->h_utables.empty() ? nullptr : e->h_utables.data(), e->h_utables.empty() ? nullptr : e->d_utables, e->n_local,
                                             d_rows + o * row_stride, row_stride, col_offset, pl, e->sc, e->l2_prefetch, s, e->pev)) {
@@ -1115,11 +1103,12 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     if (pipelined) {
         PkPartPlan mx{};
         for (auto &bt : batches) {
-            pk_part_plan(bt.npos ? bt.npos : 1, e->tune, &bt.pl);
+            pk_part_plan(bt.npos ? bt.npos : 1, e->tune, &bt.pl, N, fine_out_ok(e, rs, 0));
             mx.buf1_items = std::max(mx.buf1_items, bt.pl.buf1_items); mx.buf2_items = std::max(mx.buf2_items, bt.pl.buf2_items);
             mx.spill_items = std::max(mx.spill_items, bt.pl.spill_items);
             mx.n_regions1 = std::max(mx.n_regions1, bt.pl.n_regions1); mx.n_regions2 = std::max(mx.n_regions2, bt.pl.n_regions2);
             mx.out_shift = std::max(mx.out_shift, bt.pl.out_shift);
+            mx.out_bytes = std::max(mx.out_bytes, bt.pl.out_bytes);
         }
         rc = ensure_scratch(e, mx); if (rc) return rc;
     }
@@ -1361,9 +1350,10 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     if (n == "k3_window") { e->tune.window = value; return PK_OK; }
     else if (n == "k3w_variant") { if (value >= -1 && value < pk_part_n_wvariants()) e->tune.wvariant = value; return PK_OK; }
     else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } e->tune.wgroup = value; return PK_OK; }
-    else if (n == "k3_rank_atomic") { e->tune.rank_atomic = value ? 1 : 0; return PK_OK; }
+    else if (n == "k3_rank_atomic") { e->tune.rank_atomic = value < 0 ? 0 : value > 2 ? 2 : value; return PK_OK; }   // 2: no output (timing ablation)
     else if (n == "gather_dst_mode") { e->gather_dst_mode = value ? 1 : 0; return PK_OK; }
-    else if (n == "rows_persist") { e->rows_persist = value ? 1 : 0; return PK_OK; }
+    else if (n == "fine_out") { e->tune.fine_out = value ? 1 : 0; return PK_OK; }
+    else if (n == "fine_shift") { e->tune.fine_shift = value < 0 ? 0 : value > 24 ? 24 : value; return PK_OK; }
     else if (n == "k3_variant") { if (value >= -1 && value < pk_part_n_variants()) e->tune.variant = value; return PK_OK; }
     else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
     else if (n == "group_tables") {        // 0: per-genome tables only; takes effect at the next pk_engine_finalize

@@ -101,9 +101,11 @@ void pk_launch_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p
                      uint32_t col_offset, pk_stream_t s);
 void pk_launch_probe_group(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t n, PkKeySpec ks,
                            const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, pk_stream_t s);
+// list4 != NULL (fine un-permute lists, one-byte rows): results are appended as 4-byte items instead of written as rows
 void pk_launch_items_group(const void *d_buf, const uint32_t *d_counts, const unsigned long long *d_flat_total, uint32_t n_regions, uint64_t cap,
                            const uint64_t *d_words, uint64_t p0, PkKeySpec ks, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
-                           uint32_t row_stride, uint32_t col_offset, pk_stream_t s);
+                           uint32_t row_stride, uint32_t col_offset, uint32_t *list4, uint32_t *list_cursor, uint32_t cursor_stride,
+                           uint32_t out_shift, pk_stream_t s);
 void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
                       uint64_t binlen, unsigned long long *d_bin_hist, unsigned long long *d_col_sums,
                       uint8_t *d_rows_low, uint32_t step, pk_stream_t s);
@@ -139,6 +141,9 @@ struct PkPartPlan {
     uint32_t pb1, pb2, cap1, cap2, n_regions1, n_regions2;
     uint64_t buf1_items, buf2_items, spill_items;   // 8-byte (hash, pos) items
     uint32_t out_shift, out_bins;                   // un-permute lists: out_bins bins of 2^out_shift positions
+    uint64_t out_bytes, fine_rows;                  // bytes of the un-permute lists; rows of the launch (fine mode)
+    uint32_t out_fine;                              // 1: one-byte rows — 4-byte (position in bin, bits) items in <= 512 bins, un-permuted
+                                                    //    through shared-memory slices of the bitmap (unpermute_slice_kernel)
 };
 // tuning state of the partitioned probe: per engine (two engines of one process — thread per GPU — do not share it)
 struct PkPartTune {
@@ -146,7 +151,9 @@ struct PkPartTune {
     int window = 1;         // 0: never use the window kernels
     int wvariant = -1;      // window kernel variant, -1 auto
     int wgroup = 0;         // genomes per window group (2 * group stage buffers); 0 = by window size
-    int rank_atomic = 0;    // window kernel: shared-memory-atomic ranking of the results (1) or warp match_any (0)
+    int rank_atomic = 1;    // window kernel: shared-memory-atomic ranking of the results (1) or warp match_any (0)
+    int fine_shift = 0;     // fine mode: log2 of the positions per bin, 0 = the smallest that gives <= 512 bins
+    int fine_out = 1;       // one-byte rows out of group tables: fine position bins + shared-memory-slice un-permute
     int last_window = 0;    // K3 of the last launch: 2 window kernel on group tables, 1 on per-genome tables, 3 L1/L2 on group tables, 0 L1/L2 kernel
 };
 struct PkPartScratch {
@@ -158,13 +165,15 @@ struct PkPartScratch {
     uint32_t *err;
     void *out_list;                                 // NULL: probe_part scatters row bytes itself
     uint32_t *out_cursor;
-    uint64_t out_items;
+    uint64_t out_bytes;
 };
 uint32_t pk_part_obins(void);
 uint32_t pk_part_ocursor_words(void);
 int pk_part_n_variants(void);
 int pk_part_n_wvariants(void);
-void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl);
+// fine_out: 0 no, 1 one-byte rows out of group tables (fine bins + slice un-permute), 2 ... with 32-bit slots (larger K3 blocks)
+void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n_local = 1, int fine_out = 0);
+uint32_t pk_part_max_fine_bins(void);
 void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
 void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t off, uint64_t n, PkKeySpec ks,
                     uint32_t n_local, uint8_t *d_rows, uint32_t row_stride, uint32_t col_offset, const PkPartPlan &pl,

@@ -474,10 +474,18 @@ __global__ void __launch_bounds__(256) items_group_kernel(const uint2 *__restric
                                                           const unsigned long long *__restrict__ flat_total, uint32_t n_regions, uint64_t cap,
                                                           const uint64_t *__restrict__ words, uint64_t p0, PkKeySpec ks,
                                                           const PkTable *__restrict__ utables, uint32_t n_local, uint8_t *__restrict__ rows,
-                                                          uint32_t row_stride, uint32_t col_offset) {
+                                                          uint32_t row_stride, uint32_t col_offset, uint32_t *__restrict__ list4,
+                                                          uint32_t *__restrict__ list_cursor, uint32_t cursor_stride, uint32_t out_shift) {
     const uint32_t n_groups = (n_local + PK_U_GROUP - 1) / PK_U_GROUP;
     auto one = [&](const uint2 it) {
         const uint64_t canon = pk_canon_at(words, p0 + it.y, ks.k);
+        if (list4) {        // one-byte rows, fine un-permute lists: (position in bin) << 8 | bits, one slot per position of the bin
+            const uint32_t m = pk_group_lookup(utables[0], canon, it.x, 0, min(PK_U_GROUP, n_local), ks);
+            const uint32_t bin = it.y >> out_shift;
+            const uint32_t slot = atomicAdd(&list_cursor[bin * cursor_stride], 1u);
+            list4[((uint64_t)bin << out_shift) + slot] = ((it.y & ((1u << out_shift) - 1)) << 8) | (m & 0xffu);
+            return;
+        }
         uint8_t *dst = rows + (uint64_t)it.y * row_stride + col_offset;
         for (uint32_t u = 0; u < n_groups; u++)
             dst[u] = (uint8_t)pk_group_lookup(utables[u], canon, it.x, PK_U_GROUP * u, min(PK_U_GROUP, n_local - PK_U_GROUP * u), ks);
@@ -495,10 +503,11 @@ __global__ void __launch_bounds__(256) items_group_kernel(const uint2 *__restric
 }
 void pk_launch_items_group(const void *d_buf, const uint32_t *d_counts, const unsigned long long *d_flat_total, uint32_t n_regions, uint64_t cap,
                            const uint64_t *d_words, uint64_t p0, PkKeySpec ks, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
-                           uint32_t row_stride, uint32_t col_offset, pk_stream_t s) {
+                           uint32_t row_stride, uint32_t col_offset, uint32_t *list4, uint32_t *list_cursor, uint32_t cursor_stride,
+                           uint32_t out_shift, pk_stream_t s) {
     const unsigned grid = d_counts ? (n_regions < 148u * 8 ? (n_regions ? n_regions : 1) : 148u * 8) : 148u * 2;
     items_group_kernel<<<grid, 256, 0, s>>>((const uint2 *)d_buf, d_counts, d_flat_total, n_regions, cap, d_words, p0, ks, d_utables, n_local, d_rows,
-                                            row_stride, col_offset);
+                                            row_stride, col_offset, list4, list_cursor, cursor_stride, out_shift);
 }
 
 // ------------------------------------------------------------------ reduce

@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs 
 // ------------------------------------------------------------------ K3: probe one partition per block
 #define PP_OBINS 128                      // position bins of the un-permute lists
 #define PP_OCS 32                         // the bins' cursors sit 128 bytes apart: 2^18 blocks add to each of them
+#define PP_FBINS 512                      // fine mode (one-byte rows): up to 512 bins ...
+#define PP_FSLICE_SHIFT 17                // ... un-permuted through 128 KB shared-memory slices of the bitmap
 #define PS_BINS 1024                      // counting-sort bins of the bucket-sorted variant
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
@@ -218,6 +220,7 @@ struct ProbeArgs {
     uint2 *out_list;                  // [(grp * PP_OBINS + bin) << out_shift]
     uint32_t *out_cursor;             // [n_groups * PP_OBINS]
     uint32_t out_shift;
+    uint32_t out_fine;                // one-byte rows: 4-byte items ((position in bin) << 8 | bits), bins indexed without the group factor
     uint32_t rank_atomic;             // window kernel: rank the results inside their position bin by one shared-memory atomicAdd per
                                       // item (1) or by warp match_any + per-warp counters (0)
     PkTable tabs[32];
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
     __shared__ uint32_t q_pos[PW_QCAP], q_h[PW_QCAP], q_meta[PW_QCAP];   //   position, hash, (item << 5 | genome)
     __shared__ uint32_t q_n[2];
     __shared__ uint16_t o_wc[T / 32][PP_OBINS];
-    __shared__ uint32_t o_gb[PP_OBINS], o_cnt[PP_OBINS];
+    __shared__ uint32_t o_gb[PP_FBINS], o_cnt[PP_FBINS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr bool GRP = FMT == PK_FMT_GROUP || FMT == PK_FMT_GROUP32;       // group tables: a probe returns an 8-bit membership mask
     constexpr bool G32 = FMT == PK_FMT_GROUP32;
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
         if (tid == 0) { q_n[0] = 0; q_n[1] = 0; }
         for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
         for (uint32_t i = tid; i < (T / 32) * PP_OBINS / 2; i += T) ((uint32_t *)&o_wc[0][0])[i] = 0;
-        for (uint32_t i = tid; i < PP_OBINS; i += T) o_cnt[i] = 0;
+        for (uint32_t i = tid; i < PP_FBINS; i += T) o_cnt[i] = 0;
         key_t key[IPT];          // S64: the canonical k-mer; S32: the slot value it has in its home bucket
         uint32_t h[IPT], pos[IPT], bits[IPT];
 #pragma unroll
@@ -743,25 +746,37 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < IPT; j++)
             if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
-        if (a.out_list && a.rank_atomic) {
-            // rank inside (block, bin) by one shared-memory atomicAdd per item; one global atomicAdd per (block, bin)
-            // reserves the run in the bin's list
+        if (a.out_list && a.rank_atomic == 2) {
+            // ABLATION (timing experiments only; rows are wrong): no output at all
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < IPT; j++) acc |= bits[j];
+            if (acc == 0xdeadbeefu) a.out_cursor[0] = acc;
+        } else if (a.out_list && (a.out_fine || a.rank_atomic == 1)) {
+            // rank inside (block, bin) by one shared-memory atomicAdd per item, one global atomicAdd per (block, bin)
+            // reserves the run in the bin's list. (Reserving at the top of the block, to overlap the atomics' round trip
+            // with the probes, was slower: 2.43 vs 2.19 ms, profiles/r2k_sweep_early_reservation.json.) Fine mode
+            // (one-byte rows): (position in bin) << 8 | bits in 4 bytes, <= 512 bins; else (position, bits) in 8 bytes
             uint32_t rk[IPT];
 #pragma unroll
             for (int j = 0; j < IPT; j++)
                 rk[j] = tid + j * T < cnt ? atomicAdd(&o_cnt[pos[j] >> a.out_shift], 1u) : 0u;
             __syncthreads();
-            for (uint32_t b = tid; b < PP_OBINS; b += T) {
+            const uint32_t nbins = a.out_fine ? PP_FBINS : PP_OBINS;
+            for (uint32_t b = tid; b < nbins; b += T) {
                 const uint32_t c = o_cnt[b];
-                if (c) o_gb[b] = atomicAdd(&a.out_cursor[(a.grp * PP_OBINS + b) * PP_OCS], c);
+                if (c) o_gb[b] = atomicAdd(&a.out_cursor[(a.out_fine ? b : a.grp * PP_OBINS + b) * PP_OCS], c);
             }
             __syncthreads();
+            uint32_t *list4 = (uint32_t *)a.out_list;
 #pragma unroll
             for (int j = 0; j < IPT; j++) {
                 if (tid + j * T < cnt) {
                     const uint32_t bin = pos[j] >> a.out_shift;
-                    const uint64_t slot = (((uint64_t)a.grp * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + rk[j];
-                    a.out_list[slot] = make_uint2(pos[j], bits[j]);
+                    if (a.out_fine)
+                        list4[((uint64_t)bin << a.out_shift) + o_gb[bin] + rk[j]] = ((pos[j] & ((1u << a.out_shift) - 1)) << 8) | (bits[j] & 0xffu);
+                    else
+                        a.out_list[(((uint64_t)a.grp * PP_OBINS + bin) << a.out_shift) + o_gb[bin] + rk[j]] = make_uint2(pos[j], bits[j]);
                 }
             }
         } else if (a.out_list) {
@@ -855,6 +870,8 @@ static const K3WinVariant k3w_variants[] = {
     K3W(256, 3, 8),      // 4: <= 32 registers
     K3W(128, 6, 12),     // 5: 128-thread blocks
     K3W(128, 6, 16),     // 6
+    K3W(512, 3, 2),      // 7: 512-thread blocks, capacity 1536 (2^17 partitions; pairs with k3_variant 6)
+    K3W(512, 3, 3),      // 8
 };
 #define PW_MAX_GROUP_STAGE_BYTES 32768u
 #define PW_GROUP_STAGE_TARGET 24576u          // pieces of a group-table window are at most this large
@@ -862,9 +879,10 @@ int pk_part_n_wvariants(void) { return (int)(sizeof k3w_variants / sizeof k3w_va
 // auto: per-genome tables 6 blocks/SM (profiles/r1e_sweep.json: 5.14 vs 5.32 ms), group tables 4 blocks/SM with up to
 // 64 registers (profiles/r1l_sweep.json: 2.29 vs 3.62 ms — one 20 KB window per block, the probe loop is short and
 // the item registers matter more than occupancy)
-static const K3WinVariant &k3w_pick(const PkPartTune &tu, uint32_t n_genomes_in_launch, bool group_tables = false) {
+// ... group tables with 32-bit slots (10 KB windows): 6 blocks/SM again (profiles/r2d_sweep_k3_variants_g32.json: 1.84 vs 1.95 ms)
+static const K3WinVariant &k3w_pick(const PkPartTune &tu, uint32_t n_genomes_in_launch, bool group_tables = false, bool g32 = false) {
     (void)n_genomes_in_launch;
-    return k3w_variants[tu.wvariant >= 0 && tu.wvariant < pk_part_n_wvariants() ? tu.wvariant : (group_tables ? 0 : 3)];
+    return k3w_variants[tu.wvariant >= 0 && tu.wvariant < pk_part_n_wvariants() ? tu.wvariant : (group_tables && !g32 ? 0 : 3)];
 }
 // bytes one stage must hold for every table of the launch, or 0 when some window does not fit a stage
 static uint32_t k3w_stage_bytes(const PkTable *tabs, uint32_t ng, uint32_t pb, uint32_t limit) {
@@ -899,12 +917,68 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const uint2 *__restrict_
     }
 }
 
+// K4, one-byte rows: the 4-byte (position in bin, bits) lists -> rows through SHARED-MEMORY SLICES of the bitmap. A block
+// owns 2^PP_FSLICE_SHIFT consecutive rows (128 KB of shared memory, zero-filled: rows of invalid windows are zero),
+// scans its bin's whole list (L2-resident: the 2^(out_shift - 17) blocks of a bin run side by side), keeps the items of
+// its slice with byte stores into shared memory, and writes the slice out with 16-byte stores. The scattered byte
+// stores — 135 M of them on configs[1], each its own 32-byte sector through L1TEX in unpermute_kernel (1.05 ms) — stay
+// on chip; the price is reading a bin's list once per slice.
+__global__ void __launch_bounds__(1024, 1) unpermute_slice_kernel(const uint32_t *__restrict__ list, const uint32_t *__restrict__ cursor,
+                                                                  uint32_t out_shift, uint32_t bin0, uint64_t n_rows, uint8_t *__restrict__ rows) {
+    extern __shared__ __align__(16) uint8_t s_slice[];          // [1 << PP_FSLICE_SHIFT]
+    constexpr uint32_t S = 1u << PP_FSLICE_SHIFT;
+    const uint32_t sub_shift = out_shift > PP_FSLICE_SHIFT ? out_shift - PP_FSLICE_SHIFT : 0;
+    const uint32_t bin = bin0 + (blockIdx.x >> sub_shift), sub = blockIdx.x & ((1u << sub_shift) - 1);
+    const uint32_t slice = out_shift > PP_FSLICE_SHIFT ? S : 1u << out_shift;       // rows of this block
+    const uint64_t row0 = ((uint64_t)bin << out_shift) + (uint64_t)sub * S;
+    if (row0 >= n_rows) return;
+    for (uint32_t i = threadIdx.x * 16; i < slice; i += blockDim.x * 16) *(uint4 *)(s_slice + i) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t cnt = min(cursor[bin * PP_OCS], 1u << out_shift);
+    const uint32_t *src = list + ((uint64_t)bin << out_shift);
+    const uint32_t n4 = cnt & ~3u;
+    // four 16-byte loads in flight per thread: one block per SM has to cover the L2 latency on its own
+    for (uint32_t i0 = threadIdx.x * 4; i0 < n4; i0 += blockDim.x * 16) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = i0 + u * blockDim.x * 4;
+            v[u] = i < n4 ? *(const uint4 *)(src + i) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t it[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t p = it[q] >> 8;          // 0xffffff (padding): never inside a bin of <= 2^24 positions' slice range
+                if ((p >> PP_FSLICE_SHIFT) == sub && i0 + u * blockDim.x * 4 < n4) s_slice[p & (S - 1)] = (uint8_t)it[q];
+            }
+        }
+    }
+    for (uint32_t i = n4 + threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t v = src[i], p = v >> 8;
+        if ((p >> PP_FSLICE_SHIFT) == sub) s_slice[p & (S - 1)] = (uint8_t)v;
+    }
+    __syncthreads();
+    const uint32_t nout = (uint32_t)min((uint64_t)slice, n_rows - row0);
+    uint8_t *dst = rows + row0;
+    if ((((uintptr_t)dst) & 15) == 0) {
+        for (uint32_t i = threadIdx.x * 16; i + 16 <= nout; i += blockDim.x * 16) *(uint4 *)(dst + i) = *(const uint4 *)(s_slice + i);
+        for (uint32_t i = (nout & ~15u) + threadIdx.x; i < nout; i += blockDim.x) dst[i] = s_slice[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < nout; i += blockDim.x) dst[i] = s_slice[i];
+    }
+}
+
 // ------------------------------------------------------------------ host orchestration
 static uint32_t ceil_log2(uint64_t v) { uint32_t b = 0; while ((1ull << b) < v) b++; return b; }
 
-void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl) {
-    // mean fill <= 5/6 of the K3 block capacity (>= 20% head-room for the Poisson spread)
-    const uint32_t cap = (uint32_t)k3_pick(tune, 1).cap;
+uint32_t pk_part_max_fine_bins(void) { return PP_FBINS; }
+void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n_local, int fine_out) {
+    // mean fill <= 5/6 of the K3 block capacity (>= 20% head-room for the Poisson spread). One-byte rows out of 32-bit-slot
+    // group tables (fine_out == 2): 512-thread blocks of capacity 1536 (profiles/r2j_sweep.json: K3 2.01 vs 2.19 ms)
+    const bool big = fine_out == 2 && tune.fine_out && n_local <= 8 && tune.variant < 0 && tune.wvariant < 0;
+    const uint32_t cap = big ? 1536u : (uint32_t)k3_pick(tune, 1).cap;
     const uint64_t fill = (uint64_t)cap * 5 / 6;
     uint32_t pb = ceil_log2((n + fill - 1) / fill);
     if (pb > 18) pb = 18;
@@ -922,9 +996,24 @@ void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl) {
     pl->out_shift = ceil_log2((n + PP_OBINS - 1) / PP_OBINS);
     if (pl->out_shift < 8) pl->out_shift = 8;
     pl->out_bins = (uint32_t)((n + (1ull << pl->out_shift) - 1) >> pl->out_shift);
+    pl->out_fine = 0;
+    pl->fine_rows = n;
+    pl->out_bytes = ((uint64_t)((n_local + 31) / 32) * PP_OBINS << pl->out_shift) * 8;
+    if (fine_out && tune.fine_out && n_local <= 8) {
+        // one-byte rows: <= 512 bins of >= 2^17 positions (a position in its bin + 8 bits fit 32 bits up to bins of 2^24)
+        uint32_t sh = ceil_log2((n + PP_FBINS - 1) / PP_FBINS);
+        if (tune.fine_shift > 0 && (uint32_t)tune.fine_shift > sh) sh = (uint32_t)tune.fine_shift;     // fewer, larger bins
+        if (sh < PP_FSLICE_SHIFT) sh = PP_FSLICE_SHIFT;
+        if (sh <= 24) {
+            pl->out_fine = 1;
+            pl->out_shift = sh;
+            pl->out_bins = (uint32_t)((n + (1ull << sh) - 1) >> sh);
+            pl->out_bytes = ((uint64_t)pl->out_bins << sh) * 4;
+        }
+    }
 }
 uint32_t pk_part_obins(void) { return PP_OBINS; }
-uint32_t pk_part_ocursor_words(void) { return PP_OBINS * PP_OCS; }
+uint32_t pk_part_ocursor_words(void) { return (PP_OBINS > PP_FBINS ? PP_OBINS : PP_FBINS) * PP_OCS; }
 
 // The stages of one partitioned batch. A batch may be fed in pieces (pk_part_append per chromosome, as
 // its bytes arrive) and drained in pieces (pk_part_unpermute per range of position bins).
@@ -945,7 +1034,7 @@ void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &
     cudaMemsetAsync(sc.cursor1, 0, sizeof(uint32_t) * pl.n_regions1, s);
     if (pl.n_regions2) cudaMemsetAsync(sc.cursor2, 0, sizeof(uint32_t) * pl.n_regions2, s);
     cudaMemsetAsync(sc.spill_cursor, 0, sizeof(unsigned long long), s);
-    if (sc.out_list) cudaMemsetAsync(sc.out_cursor, 0, sizeof(uint32_t) * ((n_local + 31) / 32) * PP_OBINS * PP_OCS, s);
+    if (sc.out_list) cudaMemsetAsync(sc.out_cursor, 0, sizeof(uint32_t) * (pl.out_fine ? PP_FBINS : ((n_local + 31) / 32) * PP_OBINS) * PP_OCS, s);
 }
 
 // K1 over positions [p0 + off, p0 + off + n) of the batch that starts at p0 (pos = off + i)
@@ -986,13 +1075,16 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     p.out_cursor = sc.out_cursor;
     p.out_shift = pl.out_shift;
     p.rank_atomic = (uint32_t)tu.rank_atomic;
+    p.out_fine = 0;
     if (evs) cudaEventRecord(evs[2], s);
     bool regions_done = false;         // the regions have been answered for ALL genomes by the L1/L2 group kernel
     for (uint32_t grp = 0; grp < n_groups && !regions_done; grp++) {       // one launch per group of 32 genomes
         const uint32_t ngen = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         p.grp = grp; p.g_first = 32 * grp; p.n_genomes = ngen;
         last_window = 0;
-        if (tu.window && h_utables && k3_pick(tu, ngen).cap == k3w_pick(tu, ngen).cap) {
+        const K3WinVariant &wv_group = (tu.wvariant < 0 && pl.cap2 == 1536) ? k3w_variants[8]
+                                                                            : k3w_pick(tu, ngen, true, h_utables && h_utables[4 * grp].fmt == PK_TFMT_G32);
+        if (tu.window && h_utables && (uint32_t)wv_group.cap == pl.cap2) {
             // group tables: one probe per 8 genomes; the launch walks the (<= 4) group tables of its 32 genomes. A
             // window larger than PW_GROUP_STAGE_TARGET is cut into equal pieces that pass through the stages one
             // after the other (every item probes the piece its home bucket lies in).
@@ -1014,7 +1106,8 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
                     p.t_of[np] = (uint8_t)u; p.c_of[np] = (uint8_t)c; np++;
                 }
             if (ok && np) {
-                const K3WinVariant &wv = k3w_pick(tu, ngen, true);
+                p.out_fine = pl.out_fine;
+                const K3WinVariant &wv = wv_group;
                 const uint32_t stage_bytes = (uint32_t)cb * 32, n_stages = np == 1 ? 1 : 2;
                 p.ng = np; p.tbits = PK_U_GROUP; p.chunk_buckets = nch > 1 ? (uint32_t)cb : 0;
                 const int fk = (nch > 1 ? 3 : 2) + (p.tabs[0].fmt == PK_TFMT_G32 ? 2 : 0);
@@ -1027,11 +1120,14 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
         if (h_utables && d_utables) {
             // group tables, but this launch's windows cannot be staged (more than 32 pieces: a short batch against
             // large tables) or the window kernels are switched off: probe the regions through L1/L2, all genomes at once
-            pk_launch_items_group(p.buf, p.counts, nullptr, p.n_regions, p.cap, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset, s);
+            const bool fine = pl.out_fine && sc.out_list;
+            pk_launch_items_group(p.buf, p.counts, nullptr, p.n_regions, p.cap, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset,
+                                  fine ? (uint32_t *)sc.out_list : nullptr, sc.out_cursor, PP_OCS, pl.out_shift, s);
             last_window = 3;
             regions_done = true;
             continue;
         }
+        if (pl.out_fine) { last_window = -1; regions_done = true; continue; }     // unreachable: a fine plan needs group tables (handled above)
         p.chunk_buckets = 0;
         for (uint32_t g = 0; g < 32; g++) { p.t_of[g] = (uint8_t)g; p.c_of[g] = 0; }
         p.ng = ngen; p.tbits = 1;
@@ -1053,7 +1149,9 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     }
     if (evs) cudaEventRecord(evs[3], s);
     if (h_utables && d_utables) {      // drain the spill list (normally empty) out of the group tables
-        pk_launch_items_group(sc.spill, nullptr, sc.spill_cursor, 0, pl.spill_items, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset, s);
+        const bool fine = pl.out_fine && sc.out_list;
+        pk_launch_items_group(sc.spill, nullptr, sc.spill_cursor, 0, pl.spill_items, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset,
+                              fine ? (uint32_t *)sc.out_list : nullptr, sc.out_cursor, PP_OCS, pl.out_shift, s);
         if (evs) cudaEventRecord(evs[4], s);
         return;
     }
@@ -1073,6 +1171,15 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
 void pk_part_unpermute(uint32_t bin0, uint32_t bin1, uint32_t n_local, uint8_t *d_rows, uint32_t row_stride,
                        uint32_t col_offset, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s) {
     if (!sc.out_list || bin1 <= bin0) return;
+    if (pl.out_fine) {
+        const uint32_t sub_shift = pl.out_shift > PP_FSLICE_SHIFT ? pl.out_shift - PP_FSLICE_SHIFT : 0;
+        const size_t smem = (size_t)1 << (pl.out_shift > PP_FSLICE_SHIFT ? PP_FSLICE_SHIFT : pl.out_shift);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(unpermute_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << PP_FSLICE_SHIFT); attr_set = true; }
+        unpermute_slice_kernel<<<(bin1 - bin0) << sub_shift, 1024, smem, s>>>((const uint32_t *)sc.out_list, sc.out_cursor, pl.out_shift, bin0,
+                                                                              pl.fine_rows, d_rows + col_offset);
+        return;
+    }
     dim3 grid((unsigned)(((1ull << pl.out_shift) + UP_TILE - 1) / UP_TILE), bin1 - bin0, (n_local + 31) / 32);
     unpermute_kernel<<<grid, 256, 0, s>>>((const uint2 *)sc.out_list, sc.out_cursor, pl.out_shift, bin0, d_rows, row_stride,
                                           col_offset, (n_local + 7) / 8);

@@ -264,6 +264,31 @@ class ShardedAnchorer:
         eng.interleave_device(d_planes.data_ptr(), self.rg, npos, self.w, d_rows.data_ptr(), self.rg * self.w, st)
         return d_rows
 
+    def _load_anchor_shared(self, arrs, cat_off, ltot: int):
+        """The packed anchor (2-bit words + invalid-base mask, concatenated numbering of pk_anchor_layout) on every rank
+        of the genome group, each rank having copied and packed only its 1/Rg share. Call on self.stream."""
+        import torch
+        import torch.distributed as dist
+        eng, rg, gi = self.engine, self.rg, self.gi
+        words32 = (ltot + 31) // 32
+        cw = ((words32 + rg - 1) // rg + 1) & ~1                      # packed words per rank, even (the mask is read as uint64)
+        a0, a1 = gi * cw * 32, min(ltot, (gi + 1) * cw * 32)          # this rank's bases
+        share = torch.full((cw * 32 + 64,), ord("N"), dtype=torch.uint8, device=self.dev)
+        for off, a in zip(cat_off, arrs):
+            lo, hi = max(a0, off), min(a1, off + a.size)
+            if hi > lo:
+                share[lo - a0:hi - a0].copy_(torch.from_numpy(a[lo - off:hi - off]), non_blocking=True)
+        nwt = eng.packed_words(cw * 32)
+        tw = torch.empty(nwt, dtype=torch.int64, device=self.dev)
+        tm = torch.empty(nwt, dtype=torch.int32, device=self.dev)
+        eng.pack_device(share.data_ptr(), cw * 32, tw.data_ptr(), tm.data_ptr(), self.stream.cuda_stream)
+        total = max(rg * cw, eng.packed_words(ltot)) + 8
+        d_words = torch.zeros(total, dtype=torch.int64, device=self.dev)
+        d_mask = torch.full((total,), -1, dtype=torch.int32, device=self.dev)      # beyond the anchor: invalid bases
+        dist.all_gather_into_tensor(d_words[: rg * cw], tw[:cw], group=self.group)
+        dist.all_gather_into_tensor(d_mask[: rg * cw], tm[:cw], group=self.group)
+        return d_words, d_mask
+
     # ---- the product call: one anchor genome -> this rank's share of its results ----
     def anchor_genome(self, seqs, bgzf: bool = True, rows_to_host: bool = False) -> dict:
         """All chromosomes of one anchor. Collective over the genome group. Every rank returns
@@ -288,8 +313,15 @@ class ShardedAnchorer:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         with torch.cuda.stream(self.stream):
             ev[0].record(self.stream)
-            # H2D + pack + probe, pipelined inside the library on its own streams; complete on return
-            eng.anchor_genome_plane(arrs, pl["own"], pl["rows"], self.w)
+            if self.rg == 1:
+                # H2D + pack + probe, pipelined inside the library on its own streams; complete on return
+                eng.anchor_genome_plane(arrs, pl["own"], pl["rows"], self.w)
+            else:
+                # every rank needs the whole anchor, but not over its own PCIe link: rank g copies and packs 1/Rg of
+                # it, an all-gather over NVLink hands everyone the packed sequence (0.375 byte per base)
+                d_words, d_mask = self._load_anchor_shared(arrs, cat_off, plane_rows)
+                eng.probe_device(d_words.data_ptr(), d_mask.data_ptr(), 0, max(plane_rows - k + 1, 0), pl["own"], self.w, 0,
+                                 self.stream.cuda_stream)
             ev[1].record(self.stream)
             self.barrier()
             rows = torch.empty((max(s1 - s0, 1), rb), dtype=torch.uint8, device=self.dev)
