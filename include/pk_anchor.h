@@ -68,7 +68,8 @@ void pk_kmcdb_close(pk_kmcdb *db);
  * applies what `kmc -fm` / Biopython see instead: a trailing '\r' is cut from every line, bytes < 32 are dropped
  * from the sequence, the name is the header's first whitespace-separated token. Sequences live in page-locked
  * memory (plain memory when no CUDA driver is present) owned by the handle; pointers stay valid until
- * pk_fasta_close. Plain-text files only (gzip: PK_EUNSUPPORTED). */
+ * pk_fasta_close. gzip / bgzip files (recognised by their magic, as Genome.iter_fasta recognises them by suffix,
+ * index.py:922-930) are inflated with zlib, every member of the file. */
 typedef struct pk_fasta pk_fasta;
 int pk_fasta_open(const char *path, int strip_cr, pk_fasta **out);
 uint32_t pk_fasta_n_records(const pk_fasta *fa);

@@ -19,19 +19,16 @@ from .engine import Engine
 
 
 def parse_fasta(path, strip_cr: bool = False) -> list[tuple[str, np.ndarray]]:
-    """[(name, uint8 sequence)]: the native reader (pk_fasta_open: one memchr pass into page-locked memory) for
-    plain files, `parse_fasta_numpy` for gzip input. Same rules, same result (tests/test_host.py)."""
+    """[(name, uint8 sequence)] through the native reader (pk_fasta_open: one memchr pass into page-locked memory;
+    gzip / bgzip input inflated with zlib first). `parse_fasta_numpy` restates the same rules in numpy for the tests
+    (tests/test_host.py compares the two)."""
     import ctypes as C
     import weakref
     from . import _lib
     path = str(path)
-    if path.endswith(".gz") or path.endswith(".bgz"):
-        return parse_fasta_numpy(path, strip_cr)
     L = _lib.lib()
     h = C.c_void_p()
     rc = L.pk_fasta_open(path.encode(), int(bool(strip_cr)), C.byref(h))
-    if rc == -5:                                    # PK_EUNSUPPORTED: gzip magic without a .gz suffix
-        return parse_fasta_numpy(path, strip_cr)
     _lib.check(rc)
     n = L.pk_fasta_n_records(h)
     recs, base, total = [], None, 0

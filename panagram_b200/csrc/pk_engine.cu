@@ -1355,7 +1355,7 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     else if (n == "fine_out") { e->tune.fine_out = value ? 1 : 0; return PK_OK; }
     else if (n == "fine_shift") { e->tune.fine_shift = value < 0 ? 0 : value > 24 ? 24 : value; return PK_OK; }
     else if (n == "k3_variant") { if (value >= -1 && value < pk_part_n_variants()) e->tune.variant = value; return PK_OK; }
-    else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
+    else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }     // > 1: the window kernel prefetches items + window of the partition `value` ahead into L2
     else if (n == "group_tables") {        // 0: per-genome tables only; takes effect at the next pk_engine_finalize
         if (!value)
             for (auto &t : e->tabs)

@@ -9,8 +9,10 @@
 //   * sequence = the following lines concatenated verbatim, '\n' removed — a '\r' stays, as it does with getline
 //   * strip_cr (what `kmc -fm` and Biopython see): a trailing '\r' is cut from every line, every byte < 32 is
 //     dropped from the sequence (kmc_core/splitter.cpp), the name ends at the first whitespace
-// Plain files only; the Python host keeps its gzip path.
+// gzip / bgzip input (Genome.iter_fasta is gzip-aware, index.py:922-930) is inflated with zlib first, member after
+// member (a .bgz file is a chain of gzip members), then parsed by the same pass.
 #include <cuda_runtime.h>
+#include <zlib.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -18,6 +20,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -56,11 +59,43 @@ extern "C" int pk_fasta_open(const char *path, int strip_cr, pk_fasta **out) {
     }
     close(fd);
     struct Unmap { const uint8_t *p; size_t n; ~Unmap() { if (p) munmap((void *)p, n); } } unmap{raw, size};
-    if (size >= 2 && raw[0] == 0x1F && raw[1] == 0x8B) { pk_set_error("%s: gzip input is not handled by pk_fasta_open", path); return PK_EUNSUPPORTED; }
+    std::vector<uint8_t> inflated;
+    const uint8_t *text = raw;
+    size_t text_size = size;
+    if (size >= 2 && raw[0] == 0x1F && raw[1] == 0x8B) {
+        // every gzip member of the file, back to back (zlib stops at a member's end: reset and go on)
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, 15 + 16) != Z_OK) { pk_set_error("%s: zlib initialisation failed", path); return PK_EIO; }
+        inflated.resize(std::max<size_t>(size * 4, 1 << 20));
+        zs.next_in = const_cast<Bytef *>(raw);
+        size_t in_left = size, out_pos = 0;
+        int zr = Z_OK;
+        while (in_left || zs.avail_in) {
+            if (!zs.avail_in) { const size_t n = std::min<size_t>(in_left, 1u << 30); zs.avail_in = (uInt)n; in_left -= n; }
+            if (out_pos == inflated.size()) inflated.resize(inflated.size() * 2);
+            const size_t room = std::min<size_t>(inflated.size() - out_pos, 1u << 30);
+            zs.next_out = inflated.data() + out_pos;
+            zs.avail_out = (uInt)room;
+            zr = inflate(&zs, Z_NO_FLUSH);
+            out_pos += room - zs.avail_out;
+            if (zr == Z_STREAM_END) {
+                if (!zs.avail_in && !in_left) break;
+                if (inflateReset(&zs) != Z_OK) { zr = Z_DATA_ERROR; break; }
+            } else if (zr != Z_OK && zr != Z_BUF_ERROR) {
+                break;
+            }
+        }
+        inflateEnd(&zs);
+        if (zr != Z_STREAM_END && zr != Z_OK) { pk_set_error("%s: corrupt gzip stream (zlib %d)", path, zr); return PK_EIO; }
+        inflated.resize(out_pos);
+        text = inflated.data();
+        text_size = out_pos;
+    }
     pk_fasta *fa = new pk_fasta();
-    fa->seq = alloc_host((uint64_t)size, &fa->pinned);
+    fa->seq = alloc_host((uint64_t)text_size, &fa->pinned);
     if (!fa->seq) { delete fa; pk_set_error("out of host memory"); return PK_ENOMEM; }
-    const uint8_t *p = raw, *end = p + size;
+    const uint8_t *p = text, *end = p + text_size;
     uint64_t w = 0;
     bool in_record = false;
     while (p < end) {

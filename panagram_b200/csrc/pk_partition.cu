@@ -599,6 +599,20 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
             }
         };
         if (tid < n_stages && tid < a.ng) issue(tid);
+        // L2 prefetch for the block that will run `a.prefetch` partitions from now in this SM slot's future: its item
+        // list and (first) window then come out of L2 instead of DRAM when it starts (one warp-uniform branch per block)
+        if (a.prefetch > 1 && q + a.prefetch < a.n_regions) {
+            const uint64_t qf = q + a.prefetch;
+            if (tid == 64) {
+                const uint32_t cf = min(a.counts[qf], a.cap);
+                if (cf) l2_prefetch_bulk(a.buf + qf * (uint64_t)a.cap, (cf * 8 + 15) & ~15u);
+            } else if (tid == 96 && !CHUNKED) {
+                const PkTable t = a.tabs[GRP ? a.t_of[0] : 0];
+                const uint32_t f_lo = (uint32_t)(qf << (32 - a.pb)), f_hi = (uint32_t)(((qf + 1) << (32 - a.pb)) - 1);
+                const uint32_t b0 = __umulhi(f_lo, t.n_buckets), b1 = __umulhi(f_hi, t.n_buckets);
+                l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
+            }
+        }
         const uint2 *src = a.buf + q * (uint64_t)a.cap;
         uint2 it[IPT];
 #pragma unroll
