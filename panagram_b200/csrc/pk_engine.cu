@@ -867,7 +867,7 @@ static int probe_any(pk_engine *e, const uint64_t *d_words, const uint32_t *d_ma
         const bool part = mode == 2 || (mode == 0 && m >= (1ull << 20));
         if (part) {
             PkPartPlan pl;
-            pk_part_plan(m, e->tune, &pl, e->n_local, fine_out_ok(e, row_stride, col_offset));
+            pk_part_plan(m, e->tune, &pl, e->n_local, fine_out_ok(e, row_stride, col_offset), e->cfg.k);
             int rc = ensure_scratch(e, pl); if (rc) return rc;
             if (pk_launch_probe_partitioned(d_words, d_mask, p0 + o, m, probe_ks(e), e->d_tables, e->h_tables.data(),
                                             e->h_utables.empty() ? nullptr : e->h_utables.data(), e->h_utables.empty() ? nullptr : e->d_utables, e->n_local,
@@ -1103,7 +1103,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
     if (pipelined) {
         PkPartPlan mx{};
         for (auto &bt : batches) {
-            pk_part_plan(bt.npos ? bt.npos : 1, e->tune, &bt.pl, N, fine_out_ok(e, rs, 0));
+            pk_part_plan(bt.npos ? bt.npos : 1, e->tune, &bt.pl, N, fine_out_ok(e, rs, 0), k);
             mx.buf1_items = std::max(mx.buf1_items, bt.pl.buf1_items); mx.buf2_items = std::max(mx.buf2_items, bt.pl.buf2_items);
             mx.spill_items = std::max(mx.spill_items, bt.pl.spill_items);
             mx.n_regions1 = std::max(mx.n_regions1, bt.pl.n_regions1); mx.n_regions2 = std::max(mx.n_regions2, bt.pl.n_regions2);
@@ -1352,10 +1352,13 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     else if (n == "k3w_group") { if (value != 0 && value != 1 && value != 2 && value != 4) { pk_set_error("k3w_group %d: must be 0 (auto), 1, 2 or 4", value); return PK_EINVAL; } e->tune.wgroup = value; return PK_OK; }
     else if (n == "k3_rank_atomic") { e->tune.rank_atomic = value < 0 ? 0 : value > 2 ? 2 : value; return PK_OK; }   // 2: no output (timing ablation)
     else if (n == "gather_dst_mode") { e->gather_dst_mode = value ? 1 : 0; return PK_OK; }
+    else if (n == "k3w_big") { e->tune.wbig = value; return PK_OK; }
+    else if (n == "compact_items") { e->tune.compact = value ? 1 : 0; return PK_OK; }
+    else if (n == "k1_roll") { e->tune.k1_roll = value < 0 ? 0 : value > 2 ? 2 : value; return PK_OK; }     // 2: three blocks per SM (<= 80 registers)
     else if (n == "fine_out") { e->tune.fine_out = value ? 1 : 0; return PK_OK; }
     else if (n == "fine_shift") { e->tune.fine_shift = value < 0 ? 0 : value > 24 ? 24 : value; return PK_OK; }
     else if (n == "k3_variant") { if (value >= -1 && value < pk_part_n_variants()) e->tune.variant = value; return PK_OK; }
-    else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }     // > 1: the window kernel prefetches items + window of the partition `value` ahead into L2
+    else if (n == "l2_prefetch") { e->l2_prefetch = value; return PK_OK; }
     else if (n == "group_tables") {        // 0: per-genome tables only; takes effect at the next pk_engine_finalize
         if (!value)
             for (auto &t : e->tabs)

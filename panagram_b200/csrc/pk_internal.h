@@ -105,7 +105,7 @@ void pk_launch_probe_group(const uint64_t *d_words, const uint32_t *d_mask, uint
 void pk_launch_items_group(const void *d_buf, const uint32_t *d_counts, const unsigned long long *d_flat_total, uint32_t n_regions, uint64_t cap,
                            const uint64_t *d_words, uint64_t p0, PkKeySpec ks, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
                            uint32_t row_stride, uint32_t col_offset, uint32_t *list4, uint32_t *list_cursor, uint32_t cursor_stride,
-                           uint32_t out_shift, pk_stream_t s);
+                           uint32_t out_shift, int compact, pk_stream_t s);
 void pk_launch_reduce(const uint8_t *d_rows, uint32_t row_stride, uint32_t n_cols, uint64_t p_first, uint64_t n,
                       uint64_t binlen, unsigned long long *d_bin_hist, unsigned long long *d_col_sums,
                       uint8_t *d_rows_low, uint32_t step, pk_stream_t s);
@@ -142,6 +142,8 @@ struct PkPartPlan {
     uint64_t buf1_items, buf2_items, spill_items;   // 8-byte (hash, pos) items
     uint32_t out_shift, out_bins;                   // un-permute lists: out_bins bins of 2^out_shift positions
     uint64_t out_bytes, fine_rows;                  // bytes of the un-permute lists; rows of the launch (fine mode)
+    uint32_t compact;                               // 1: K1/K2 emit compact items that carry hash + key remainder (pk_partition.cu)
+    int wbig;                                       // >= 0: the window-kernel variant (large blocks) this plan's capacity belongs to
     uint32_t out_fine;                              // 1: one-byte rows — 4-byte (position in bin, bits) items in <= 512 bins, un-permuted
                                                     //    through shared-memory slices of the bitmap (unpermute_slice_kernel)
 };
@@ -152,6 +154,9 @@ struct PkPartTune {
     int wvariant = -1;      // window kernel variant, -1 auto
     int wgroup = 0;         // genomes per window group (2 * group stage buffers); 0 = by window size
     int rank_atomic = 1;    // window kernel: shared-memory-atomic ranking of the results (1) or warp match_any (0)
+    int wbig = 11;          // window-kernel variant for one-byte rows out of 32-bit-slot group tables (>= 7: the large-block variants)
+    int compact = 1;        // compact items on the one-byte-row / 32-bit-slot path (K3 does not read the sequence)
+    int k1_roll = 1;        // K1: rolling k-mers over 16 consecutive positions per thread (0: re-extract every window)
     int fine_shift = 0;     // fine mode: log2 of the positions per bin, 0 = the smallest that gives <= 512 bins
     int fine_out = 1;       // one-byte rows out of group tables: fine position bins + shared-memory-slice un-permute
     int last_window = 0;    // K3 of the last launch: 2 window kernel on group tables, 1 on per-genome tables, 3 L1/L2 on group tables, 0 L1/L2 kernel
@@ -172,7 +177,7 @@ uint32_t pk_part_ocursor_words(void);
 int pk_part_n_variants(void);
 int pk_part_n_wvariants(void);
 // fine_out: 0 no, 1 one-byte rows out of group tables (fine bins + slice un-permute), 2 ... with 32-bit slots (larger K3 blocks)
-void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n_local = 1, int fine_out = 0);
+void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n_local = 1, int fine_out = 0, uint32_t k = 0);
 uint32_t pk_part_max_fine_bins(void);
 void pk_part_begin(uint32_t n_local, const PkPartPlan &pl, const PkPartScratch &sc, pk_stream_t s);
 void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0, uint64_t off, uint64_t n, PkKeySpec ks,

@@ -475,10 +475,13 @@ __global__ void __launch_bounds__(256) items_group_kernel(const uint2 *__restric
                                                           const uint64_t *__restrict__ words, uint64_t p0, PkKeySpec ks,
                                                           const PkTable *__restrict__ utables, uint32_t n_local, uint8_t *__restrict__ rows,
                                                           uint32_t row_stride, uint32_t col_offset, uint32_t *__restrict__ list4,
-                                                          uint32_t *__restrict__ list_cursor, uint32_t cursor_stride, uint32_t out_shift) {
+                                                          uint32_t *__restrict__ list_cursor, uint32_t cursor_stride, uint32_t out_shift,
+                                                          int compact) {
     const uint32_t n_groups = (n_local + PK_U_GROUP - 1) / PK_U_GROUP;
-    auto one = [&](const uint2 it) {
+    auto one = [&](uint2 it) {
+        if (compact) it.y &= 0x0FFFFFFFu;        // compact item (pk_partition.cu): 28-bit position; the hash is re-derived
         const uint64_t canon = pk_canon_at(words, p0 + it.y, ks.k);
+        if (compact) it.x = pk_probe_hash(canon, ks);
         if (list4) {        // one-byte rows, fine un-permute lists: (position in bin) << 8 | bits, one slot per position of the bin
             const uint32_t m = pk_group_lookup(utables[0], canon, it.x, 0, min(PK_U_GROUP, n_local), ks);
             const uint32_t bin = it.y >> out_shift;
@@ -504,10 +507,10 @@ __global__ void __launch_bounds__(256) items_group_kernel(const uint2 *__restric
 void pk_launch_items_group(const void *d_buf, const uint32_t *d_counts, const unsigned long long *d_flat_total, uint32_t n_regions, uint64_t cap,
                            const uint64_t *d_words, uint64_t p0, PkKeySpec ks, const PkTable *d_utables, uint32_t n_local, uint8_t *d_rows,
                            uint32_t row_stride, uint32_t col_offset, uint32_t *list4, uint32_t *list_cursor, uint32_t cursor_stride,
-                           uint32_t out_shift, pk_stream_t s) {
+                           uint32_t out_shift, int compact, pk_stream_t s) {
     const unsigned grid = d_counts ? (n_regions < 148u * 8 ? (n_regions ? n_regions : 1) : 148u * 8) : 148u * 2;
     items_group_kernel<<<grid, 256, 0, s>>>((const uint2 *)d_buf, d_counts, d_flat_total, n_regions, cap, d_words, p0, ks, d_utables, n_local, d_rows,
-                                            row_stride, col_offset, list4, list_cursor, cursor_stride, out_shift);
+                                            row_stride, col_offset, list4, list_cursor, cursor_stride, out_shift, compact);
 }
 
 // ------------------------------------------------------------------ reduce

@@ -37,15 +37,33 @@ struct PartSmem {
     uint32_t warp_sums[PT_WARPS];
     uint32_t tile_total;
     uint2 stage[PT_TILE];
+    uint16_t dig[PT_TILE];                  // compact K1 items do not carry their digit any more: kept beside them
 };
+
+// COMPACT ITEMS (one-byte rows out of 32-bit-slot group tables, k = 19..22, launches of >= 2^9 coarse regions and
+// < 2^28 positions). K3 spent most of its L1TEX time re-deriving every k-mer from the packed sequence — two random
+// 8-byte loads per item, 270 M sector requests on configs[1] — only to get the 20 key-remainder bits its 32-bit-slot
+// probe compares. A G32 probe needs exactly: the hash (bucket index) and those 20 bits; and of the hash, the low
+// 32 - eb bits are a function of the remainder (pk_g32_hash), the top 9 bits are the coarse region the item sits in.
+// So K1 emits 8-byte items that carry everything K3 needs:
+//     x = [ M : eb - 9 hash bits below the coarse digit ][ R20 >> 4 : 16 bits ]      y = [ R20 & 15 : 4 bits ][ pos : 28 bits ]
+// K2 takes its digit from the top pb2 bits of M (a plain shift of x), K3 rebuilds h = coarse << 23 | M << (32 - eb) |
+// mix32(R20) >> eb and never touches the sequence (only the rare walk-on fallback does).
+#define PT_CI_POS_BITS 28
+#define PT_CI_POS_MASK 0x0FFFFFFFu
+__device__ __forceinline__ uint2 pt_compact_item(uint32_t h, uint32_t r20, uint32_t pos, uint32_t eb) {
+    const uint32_t M = (h >> (32 - eb)) & ((1u << (eb - 9)) - 1);
+    return make_uint2((M << 16) | (r20 >> 4), ((r20 & 15u) << PT_CI_POS_BITS) | pos);
+}
 
 // Scatter a tile of items (h, pos) into fixed-capacity regions by digit = (h >> shift) & (nb-1).
 // Region r = region0 + digit holds items dst[r * cap .. r * cap + min(cursor[r], cap)).
 // Rank inside (tile, digit): one shared-memory atomicAdd per item (measured 2x faster than warp
 // match_any ranking with per-warp counters: K1 1.32 -> 0.98 ms, K2 1.20 -> 0.64 ms). POS_STRIDE > 0:
 // the item positions are pos0 + j * POS_STRIDE and are not kept in registers.
-template <int POS_STRIDE>
+template <int POS_STRIDE, int CK1 = 0>
 __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)[PT_IPT], const uint32_t (&pos)[POS_STRIDE ? 1 : PT_IPT],
+                                                const uint32_t (&r20)[CK1 ? PT_IPT : 1], uint32_t eb,
                                                 uint32_t pos0, uint32_t validmask, uint32_t shift, uint32_t nb,
                                                 uint2 *__restrict__ dst, uint64_t region0, uint32_t cap,
                                                 uint32_t *__restrict__ cursor, uint2 *__restrict__ spill,
@@ -89,7 +107,13 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
     for (int j = 0; j < PT_IPT; j++) {
         if ((validmask >> j) & 1) {
             const uint32_t d = (h[j] >> shift) & (nb - 1);
-            S.stage[S.dstart[d] + rank[j]] = make_uint2(h[j], POS_STRIDE ? pos0 + j * POS_STRIDE : pos[POS_STRIDE ? 0 : j]);
+            const uint32_t pp = POS_STRIDE ? pos0 + j * POS_STRIDE : pos[POS_STRIDE ? 0 : j];
+            if (CK1) {
+                S.stage[S.dstart[d] + rank[j]] = pt_compact_item(h[j], r20[CK1 ? j : 0], pp, eb);
+                S.dig[S.dstart[d] + rank[j]] = (uint16_t)d;
+            } else {
+                S.stage[S.dstart[d] + rank[j]] = make_uint2(h[j], pp);
+            }
         }
     }
 #pragma unroll
@@ -101,7 +125,7 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
     const uint32_t total = S.tile_total;
     for (uint32_t i = tid; i < total; i += PT_THREADS) {
         const uint2 it = S.stage[i];
-        const uint32_t d = (it.x >> shift) & (nb - 1);
+        const uint32_t d = CK1 ? (uint32_t)S.dig[i] : (it.x >> shift) & (nb - 1);
         const uint64_t off = (uint64_t)S.gbase[d] + (i - S.dstart[d]);
         if (off < cap) {
             dst[(region0 + d) * cap + off] = it;
@@ -127,6 +151,7 @@ struct PartArgs {
     uint32_t *err;
     uint8_t *rows;
     uint32_t row_stride, col_offset, nbl;
+    uint32_t compact, eb;           // compact items (see PartSmem): on/off, hash bits that carry key bits (2k - 20)
 };
 
 // K1: positions [p0 + off, p0 + off + n) -> (hash, i) pairs (i = position - p0), partitioned by the top pb1 bits.
@@ -152,8 +177,67 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_seq_kernel(PartArgs a
             }
         }
     }
-    block_partition<32>(S, h, nopos, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
+    block_partition<32>(S, h, nopos, nopos, 0, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
                         a.spill_cursor, a.spill_cap, a.err);
+}
+
+// K1, rolling form: a thread takes PT_IPT CONSECUTIVE positions, extracts the first k-mer and its reverse complement
+// once (three packed words, two mask words) and then slides: one base in at the low end of the forward k-mer, its
+// complement in at the high end of the reverse one — the SHL_insert2bits / SHR_insert2bits pair of
+// kmer_api.h:54-81 — instead of re-extracting and re-reversing every window. Same items, same order of positions
+// inside a thread's run (the rank inside a (tile, digit) run differs, which no consumer depends on).
+template <int MINB>
+__global__ void __launch_bounds__(PT_THREADS, MINB) partition_seq_roll_kernel(PartArgs a) {
+    __shared__ PartSmem S;
+    const uint64_t base = a.off + blockIdx.x * (uint64_t)PT_TILE + (uint64_t)threadIdx.x * PT_IPT;
+    const uint64_t end = a.off + a.n;
+    uint32_t h[PT_IPT], r20[PT_IPT], valid = 0;
+    const uint32_t nopos[1] = {0};
+#pragma unroll
+    for (int j = 0; j < PT_IPT; j++) { h[j] = 0; r20[j] = 0; }
+    if (base < end) {
+        const uint32_t k = a.ks.k;
+        const uint64_t P = a.p0 + base;
+        const uint64_t wi = P >> 5;
+        const uint32_t s = 2 * ((uint32_t)P & 31);
+        const uint64_t w0 = a.words[wi], w1 = a.words[wi + 1], w2 = a.words[wi + 2];
+        const uint64_t hi = s ? (w0 << s) | (w1 >> (64 - s)) : w0;          // bases P .. P+31
+        const uint64_t lo = s ? (w1 << s) | (w2 >> (64 - s)) : w1;          // bases P+32 .. P+63
+        uint64_t fwd = hi >> (64 - 2 * k);
+        uint64_t rc = pk_revcomp(fwd, k);
+        uint64_t up = k < 32 ? (hi << (2 * k)) | (lo >> (64 - 2 * k)) : lo;   // the bases that slide in, first one on top
+        const uint64_t mi = P >> 6;
+        const uint32_t t = (uint32_t)P & 63;
+        const uint64_t m0 = a.mask64[mi], m1 = a.mask64[mi + 1];
+        const uint64_t M = t ? (m0 >> t) | (m1 << (64 - t)) : m0;           // bit i: base P+i is not ACGT
+        const uint64_t wmask = (1ull << k) - 1;                             // k <= 32
+        const uint64_t kk = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+        const uint32_t topsh = 2 * (k - 1);
+#pragma unroll
+        for (int j = 0; j < PT_IPT; j++) {
+            if (base + j < end) {
+                if (((M >> j) & wmask) == 0) {
+                    const uint64_t canon = fwd < rc ? fwd : rc;
+                    h[j] = pk_probe_hash(canon, a.ks);
+                    r20[j] = (uint32_t)canon & PK_G32_REM_MASK;
+                    valid |= 1u << j;
+                } else {
+                    uint8_t *dst = a.rows + (base + j) * a.row_stride + a.col_offset;
+                    for (uint32_t q = 0; q < a.nbl; q++) dst[q] = 0;
+                }
+            }
+            const uint64_t b = up >> 62;
+            up <<= 2;
+            fwd = ((fwd << 2) | b) & kk;
+            rc = (rc >> 2) | ((3 - b) << topsh);
+        }
+    }
+    if (a.compact)
+        block_partition<1, 1>(S, h, nopos, r20, a.eb, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
+                              a.spill_cursor, a.spill_cap, a.err);
+    else
+        block_partition<1>(S, h, nopos, nopos, 0, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
+                           a.spill_cursor, a.spill_cap, a.err);
 }
 
 // K2: coarse region c = blockIdx.y, tile blockIdx.x of it -> fine regions c * 2^pb2 + next pb2 bits.
@@ -176,7 +260,10 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs 
             valid |= 1u << j;
         }
     }
-    block_partition<0>(S, h, pos, 0, valid, 32 - a.pb1 - a.pb2, 1u << a.pb2, a.buf2, (uint64_t)c << a.pb2, a.cap2, a.cursor2,
+    // compact items: the fine digit is the top pb2 bits of M, which sits above the 16 remainder bits of x
+    const uint32_t nopos[1] = {0};
+    const uint32_t shift = a.compact ? 16 + (a.eb - 9) - a.pb2 : 32 - a.pb1 - a.pb2;
+    block_partition<0>(S, h, pos, nopos, 0, 0, valid, shift, 1u << a.pb2, a.buf2, (uint64_t)c << a.pb2, a.cap2, a.cursor2,
                        a.spill, a.spill_cursor, a.spill_cap, a.err);
 }
 
@@ -220,6 +307,8 @@ struct ProbeArgs {
     uint2 *out_list;                  // [(grp * PP_OBINS + bin) << out_shift]
     uint32_t *out_cursor;             // [n_groups * PP_OBINS]
     uint32_t out_shift;
+    uint32_t compact, eb, pb2;        // compact items (PartSmem): on/off, 2k - 20, fine partition bits
+    uint32_t n_bins;                  // position bins of this launch (<= PP_OBINS, fine mode <= PP_FBINS)
     uint32_t out_fine;                // one-byte rows: 4-byte items ((position in bin) << 8 | bits), bins indexed without the group factor
     uint32_t rank_atomic;             // window kernel: rank the results inside their position bin by one shared-memory atomicAdd per
                                       // item (1) or by warp match_any + per-warp counters (0)
@@ -599,38 +688,36 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
             }
         };
         if (tid < n_stages && tid < a.ng) issue(tid);
-        // L2 prefetch for the block that will run `a.prefetch` partitions from now in this SM slot's future: its item
-        // list and (first) window then come out of L2 instead of DRAM when it starts (one warp-uniform branch per block)
-        if (a.prefetch > 1 && q + a.prefetch < a.n_regions) {
-            const uint64_t qf = q + a.prefetch;
-            if (tid == 64) {
-                const uint32_t cf = min(a.counts[qf], a.cap);
-                if (cf) l2_prefetch_bulk(a.buf + qf * (uint64_t)a.cap, (cf * 8 + 15) & ~15u);
-            } else if (tid == 96 && !CHUNKED) {
-                const PkTable t = a.tabs[GRP ? a.t_of[0] : 0];
-                const uint32_t f_lo = (uint32_t)(qf << (32 - a.pb)), f_hi = (uint32_t)(((qf + 1) << (32 - a.pb)) - 1);
-                const uint32_t b0 = __umulhi(f_lo, t.n_buckets), b1 = __umulhi(f_hi, t.n_buckets);
-                l2_prefetch_bulk(t.slots + 4ull * b0, (b1 - b0 + 1) * 32);
-            }
-        }
         const uint2 *src = a.buf + q * (uint64_t)a.cap;
         uint2 it[IPT];
 #pragma unroll
         for (int j = 0; j < IPT; j++) it[j] = tid + j * T < cnt ? src[tid + j * T] : make_uint2(0, 0);
         if (tid == 0) { q_n[0] = 0; q_n[1] = 0; }
-        for (uint32_t i = tid; i < (uint32_t)CAP; i += T) s_bits[i] = 0;
-        for (uint32_t i = tid; i < (T / 32) * PP_OBINS / 2; i += T) ((uint32_t *)&o_wc[0][0])[i] = 0;
-        for (uint32_t i = tid; i < PP_FBINS; i += T) o_cnt[i] = 0;
+        // s_bits (results of deferred walk-ons) is zeroed per item by the thread that defers it, not in bulk; the warp-ranking
+        // counters only when that ranking is in use; the bin counters only as far as this launch has bins
+        const bool atomic_rank = a.out_fine || a.rank_atomic == 1;
+        if (a.out_list && !atomic_rank)
+            for (uint32_t i = tid; i < (T / 32) * PP_OBINS / 2; i += T) ((uint32_t *)&o_wc[0][0])[i] = 0;
+        for (uint32_t i = tid; i < a.n_bins; i += T) o_cnt[i] = 0;
+        uint32_t dmask = 0;      // bit j: item j of this thread was deferred (its s_bits entry is live)
         key_t key[IPT];          // S64: the canonical k-mer; S32: the slot value it has in its home bucket
         uint32_t h[IPT], pos[IPT], bits[IPT];
 #pragma unroll
         for (int j = 0; j < IPT; j++) {
             key[j] = 0; h[j] = it[j].x; pos[j] = it[j].y; bits[j] = 0;
             if (tid + j * T < cnt) {
-                const uint64_t canon = pk_canon_at(a.words, a.p0 + it[j].y, a.ks.k);
-                if constexpr (G32) key[j] = pk_g32_key(canon, 0);
-                else if constexpr (GRP) key[j] = pk_u_key(canon, 0);
-                else key[j] = (key_t)pk_target<GRP ? PK_FMT_S64 : FMT>(canon, 0);
+                if (G32 && a.compact) {
+                    // compact item: hash and key remainder travel in the item, the sequence is not read
+                    const uint32_t r20 = ((it[j].x & 0xFFFFu) << 4) | (it[j].y >> PT_CI_POS_BITS);
+                    pos[j] = it[j].y & PT_CI_POS_MASK;
+                    h[j] = ((uint32_t)(q >> a.pb2) << 23) | ((it[j].x >> 16) << (32 - a.eb)) | (pk_mix32(r20) >> a.eb);
+                    key[j] = (key_t)(r20 << PK_S32_DISP_BITS);
+                } else {
+                    const uint64_t canon = pk_canon_at(a.words, a.p0 + it[j].y, a.ks.k);
+                    if constexpr (G32) key[j] = pk_g32_key(canon, 0);
+                    else if constexpr (GRP) key[j] = pk_u_key(canon, 0);
+                    else key[j] = (key_t)pk_target<GRP ? PK_FMT_S64 : FMT>(canon, 0);
+                }
             }
         }
         __syncthreads();
@@ -652,6 +739,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
             auto defer = [&](int j, uint32_t i, uint32_t g, const PkTable &t) {
                 const uint32_t slot = atomicAdd(qn, 1u);
                 if (slot < (uint32_t)PW_QCAP) {
+                    if (!((dmask >> j) & 1)) { s_bits[i] = 0; dmask |= 1u << j; }
                     q_key[slot] = key[j]; q_pos[slot] = pos[j]; q_h[slot] = h[j]; q_meta[slot] = (i << 5) | g;
                 } else {                    // queue full (pathological)
                     bits[j] |= full_lookup(t, pk_canon_at(a.words, a.p0 + pos[j], a.ks.k), h[j], GRP ? a.t_of[g] : g);
@@ -759,7 +847,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
         // (the last group's second barrier also orders s_bits)
 #pragma unroll
         for (int j = 0; j < IPT; j++)
-            if (tid + j * T < cnt) bits[j] |= s_bits[tid + j * T];
+            if ((dmask >> j) & 1) bits[j] |= s_bits[tid + j * T];
         if (a.out_list && a.rank_atomic == 2) {
             // ABLATION (timing experiments only; rows are wrong): no output at all
             uint32_t acc = 0;
@@ -776,8 +864,7 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
             for (int j = 0; j < IPT; j++)
                 rk[j] = tid + j * T < cnt ? atomicAdd(&o_cnt[pos[j] >> a.out_shift], 1u) : 0u;
             __syncthreads();
-            const uint32_t nbins = a.out_fine ? PP_FBINS : PP_OBINS;
-            for (uint32_t b = tid; b < nbins; b += T) {
+            for (uint32_t b = tid; b < a.n_bins; b += T) {
                 const uint32_t c = o_cnt[b];
                 if (c) o_gb[b] = atomicAdd(&a.out_cursor[(a.out_fine ? b : a.grp * PP_OBINS + b) * PP_OCS], c);
             }
@@ -886,6 +973,13 @@ static const K3WinVariant k3w_variants[] = {
     K3W(128, 6, 16),     // 6
     K3W(512, 3, 2),      // 7: 512-thread blocks, capacity 1536 (2^17 partitions; pairs with k3_variant 6)
     K3W(512, 3, 3),      // 8
+    K3W(448, 3, 4),      // 9: capacity 1344: configs[1]'s 1030 items per partition fill 77 % of the block instead of 67 %
+    K3W(448, 3, 3),      // 10
+    K3W(384, 4, 4),      // 11: capacity 1536 with 4 items per thread
+    K3W(640, 2, 3),      // 12: capacity 1280
+    K3W(384, 4, 3),      // 13
+    K3W(320, 4, 5),      // 14: capacity 1280
+    K3W(256, 5, 6),      // 15: capacity 1280
 };
 #define PW_MAX_GROUP_STAGE_BYTES 32768u
 #define PW_GROUP_STAGE_TARGET 24576u          // pieces of a group-table window are at most this large
@@ -988,11 +1082,15 @@ __global__ void __launch_bounds__(1024, 1) unpermute_slice_kernel(const uint32_t
 static uint32_t ceil_log2(uint64_t v) { uint32_t b = 0; while ((1ull << b) < v) b++; return b; }
 
 uint32_t pk_part_max_fine_bins(void) { return PP_FBINS; }
-void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n_local, int fine_out) {
+void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n_local, int fine_out, uint32_t k) {
+    const uint32_t eb_g32 = 2 * k > 20 ? 2 * k - 20 : 0;
     // mean fill <= 5/6 of the K3 block capacity (>= 20% head-room for the Poisson spread). One-byte rows out of 32-bit-slot
     // group tables (fine_out == 2): 512-thread blocks of capacity 1536 (profiles/r2j_sweep.json: K3 2.01 vs 2.19 ms)
     const bool big = fine_out == 2 && tune.fine_out && n_local <= 8 && tune.variant < 0 && tune.wvariant < 0;
-    const uint32_t cap = big ? 1536u : (uint32_t)k3_pick(tune, 1).cap;
+    const int wbig = tune.wbig >= 7 && tune.wbig < pk_part_n_wvariants() ? tune.wbig : 8;
+    const uint32_t cap = big ? (uint32_t)k3w_variants[wbig].cap : (uint32_t)k3_pick(tune, 1).cap;
+    pl->wbig = big ? wbig : -1;
+    pl->compact = 0;
     const uint64_t fill = (uint64_t)cap * 5 / 6;
     uint32_t pb = ceil_log2((n + fill - 1) / fill);
     if (pb > 18) pb = 18;
@@ -1023,6 +1121,8 @@ void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n
             pl->out_shift = sh;
             pl->out_bins = (uint32_t)((n + (1ull << sh) - 1) >> sh);
             pl->out_bytes = ((uint64_t)pl->out_bins << sh) * 4;
+            // compact items: see PartSmem. 9 coarse bits, the fine digit inside the eb - 9 stored hash bits, 28-bit positions
+            pl->compact = (big && tune.compact && pl->pb1 == 9 && eb_g32 >= 18 && eb_g32 <= 25 && n <= (1ull << PT_CI_POS_BITS)) ? 1 : 0;
         }
     }
 }
@@ -1041,6 +1141,7 @@ static PartArgs make_part_args(const uint64_t *d_words, const uint32_t *d_mask, 
     a.cursor1 = sc.cursor1; a.cursor2 = sc.cursor2; a.spill_cursor = sc.spill_cursor; a.spill_cap = pl.spill_items;
     a.err = sc.err;
     a.rows = d_rows; a.row_stride = row_stride; a.col_offset = col_offset; a.nbl = (n_local + 7) / 8;
+    a.compact = pl.compact && ks.ghash; a.eb = 2 * ks.k > 20 ? 2 * ks.k - 20 : 0;
     return a;
 }
 
@@ -1059,7 +1160,11 @@ void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0
     PartArgs a = make_part_args(d_words, d_mask, p0, ks, n_local, d_rows, row_stride, col_offset, pl, sc);
     a.off = off; a.n = n;
     const unsigned grid = (unsigned)((n + PT_TILE - 1) / PT_TILE);
-    partition_seq_kernel<<<grid, PT_THREADS, 0, s>>>(a);
+    if (a.compact || (sc.tune && sc.tune->k1_roll)) {        // compact items: only the rolling K1 emits them
+        if (sc.tune && sc.tune->k1_roll == 2) partition_seq_roll_kernel<3><<<grid, PT_THREADS, 0, s>>>(a);      // <= 80 registers
+        else partition_seq_roll_kernel<4><<<grid, PT_THREADS, 0, s>>>(a);
+    }
+    else partition_seq_kernel<<<grid, PT_THREADS, 0, s>>>(a);
 }
 
 // K2 + K3 (+ spill drain) over everything appended so far
@@ -1088,6 +1193,8 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     p.out_list = (uint2 *)sc.out_list;
     p.out_cursor = sc.out_cursor;
     p.out_shift = pl.out_shift;
+    p.n_bins = pl.out_bins;
+    p.compact = a.compact; p.eb = a.eb; p.pb2 = pl.pb2;
     p.rank_atomic = (uint32_t)tu.rank_atomic;
     p.out_fine = 0;
     if (evs) cudaEventRecord(evs[2], s);
@@ -1096,7 +1203,7 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
         const uint32_t ngen = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         p.grp = grp; p.g_first = 32 * grp; p.n_genomes = ngen;
         last_window = 0;
-        const K3WinVariant &wv_group = (tu.wvariant < 0 && pl.cap2 == 1536) ? k3w_variants[8]
+        const K3WinVariant &wv_group = (tu.wvariant < 0 && pl.wbig >= 0) ? k3w_variants[pl.wbig]
                                                                             : k3w_pick(tu, ngen, true, h_utables && h_utables[4 * grp].fmt == PK_TFMT_G32);
         if (tu.window && h_utables && (uint32_t)wv_group.cap == pl.cap2) {
             // group tables: one probe per 8 genomes; the launch walks the (<= 4) group tables of its 32 genomes. A
@@ -1136,7 +1243,7 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
             // large tables) or the window kernels are switched off: probe the regions through L1/L2, all genomes at once
             const bool fine = pl.out_fine && sc.out_list;
             pk_launch_items_group(p.buf, p.counts, nullptr, p.n_regions, p.cap, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset,
-                                  fine ? (uint32_t *)sc.out_list : nullptr, sc.out_cursor, PP_OCS, pl.out_shift, s);
+                                  fine ? (uint32_t *)sc.out_list : nullptr, sc.out_cursor, PP_OCS, pl.out_shift, (int)a.compact, s);
             last_window = 3;
             regions_done = true;
             continue;
@@ -1165,7 +1272,7 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     if (h_utables && d_utables) {      // drain the spill list (normally empty) out of the group tables
         const bool fine = pl.out_fine && sc.out_list;
         pk_launch_items_group(sc.spill, nullptr, sc.spill_cursor, 0, pl.spill_items, d_words, p0, ks, d_utables, n_local, d_rows, row_stride, col_offset,
-                              fine ? (uint32_t *)sc.out_list : nullptr, sc.out_cursor, PP_OCS, pl.out_shift, s);
+                              fine ? (uint32_t *)sc.out_list : nullptr, sc.out_cursor, PP_OCS, pl.out_shift, (int)a.compact, s);
         if (evs) cudaEventRecord(evs[4], s);
         return;
     }
