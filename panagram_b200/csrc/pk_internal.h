@@ -154,7 +154,7 @@ struct PkPartTune {
     int wvariant = -1;      // window kernel variant, -1 auto
     int wgroup = 0;         // genomes per window group (2 * group stage buffers); 0 = by window size
     int rank_atomic = 1;    // window kernel: shared-memory-atomic ranking of the results (1) or warp match_any (0)
-    int wbig = 11;          // window-kernel variant for one-byte rows out of 32-bit-slot group tables (>= 7: the large-block variants)
+    int wbig = 6;           // window-kernel variant for one-byte rows out of 32-bit-slot group tables (>= 4: the large-block variants)
     int compact = 1;        // compact items on the one-byte-row / 32-bit-slot path (K3 does not read the sequence)
     int k1_roll = 1;        // K1: rolling k-mers over 16 consecutive positions per thread (0: re-extract every window)
     int fine_shift = 0;     // fine mode: log2 of the positions per bin, 0 = the smallest that gives <= 512 bins

@@ -51,19 +51,15 @@ struct PartSmem {
 // mix32(R20) >> eb and never touches the sequence (only the rare walk-on fallback does).
 #define PT_CI_POS_BITS 28
 #define PT_CI_POS_MASK 0x0FFFFFFFu
-__device__ __forceinline__ uint2 pt_compact_item(uint32_t h, uint32_t r20, uint32_t pos, uint32_t eb) {
-    const uint32_t M = (h >> (32 - eb)) & ((1u << (eb - 9)) - 1);
-    return make_uint2((M << 16) | (r20 >> 4), ((r20 & 15u) << PT_CI_POS_BITS) | pos);
-}
+
 
 // Scatter a tile of items (h, pos) into fixed-capacity regions by digit = (h >> shift) & (nb-1).
 // Region r = region0 + digit holds items dst[r * cap .. r * cap + min(cursor[r], cap)).
 // Rank inside (tile, digit): one shared-memory atomicAdd per item (measured 2x faster than warp
 // match_any ranking with per-warp counters: K1 1.32 -> 0.98 ms, K2 1.20 -> 0.64 ms). POS_STRIDE > 0:
 // the item positions are pos0 + j * POS_STRIDE and are not kept in registers.
-template <int POS_STRIDE, int CK1 = 0>
+template <int POS_STRIDE>
 __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)[PT_IPT], const uint32_t (&pos)[POS_STRIDE ? 1 : PT_IPT],
-                                                const uint32_t (&r20)[CK1 ? PT_IPT : 1], uint32_t eb,
                                                 uint32_t pos0, uint32_t validmask, uint32_t shift, uint32_t nb,
                                                 uint2 *__restrict__ dst, uint64_t region0, uint32_t cap,
                                                 uint32_t *__restrict__ cursor, uint2 *__restrict__ spill,
@@ -107,13 +103,7 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
     for (int j = 0; j < PT_IPT; j++) {
         if ((validmask >> j) & 1) {
             const uint32_t d = (h[j] >> shift) & (nb - 1);
-            const uint32_t pp = POS_STRIDE ? pos0 + j * POS_STRIDE : pos[POS_STRIDE ? 0 : j];
-            if (CK1) {
-                S.stage[S.dstart[d] + rank[j]] = pt_compact_item(h[j], r20[CK1 ? j : 0], pp, eb);
-                S.dig[S.dstart[d] + rank[j]] = (uint16_t)d;
-            } else {
-                S.stage[S.dstart[d] + rank[j]] = make_uint2(h[j], pp);
-            }
+            S.stage[S.dstart[d] + rank[j]] = make_uint2(h[j], POS_STRIDE ? pos0 + j * POS_STRIDE : pos[POS_STRIDE ? 0 : j]);
         }
     }
 #pragma unroll
@@ -125,10 +115,77 @@ __device__ __forceinline__ void block_partition(PartSmem &S, const uint32_t (&h)
     const uint32_t total = S.tile_total;
     for (uint32_t i = tid; i < total; i += PT_THREADS) {
         const uint2 it = S.stage[i];
-        const uint32_t d = CK1 ? (uint32_t)S.dig[i] : (it.x >> shift) & (nb - 1);
+        const uint32_t d = (it.x >> shift) & (nb - 1);
         const uint64_t off = (uint64_t)S.gbase[d] + (i - S.dstart[d]);
         if (off < cap) {
             dst[(region0 + d) * cap + off] = it;
+        } else {
+            const unsigned long long s = atomicAdd(spill_cursor, 1ull);
+            if (s < spill_cap) spill[s] = it; else *err = 1;
+        }
+    }
+    __syncthreads();
+}
+
+// The K1 form for compact items: per item ONE register holds the finished x word and one more the 9-bit coarse digit,
+// the 4 remainder bits of the y word and, once known, the rank inside the (tile, digit) run — 32 registers for the
+// 16 items of a thread instead of hash + remainder + rank (40; the rolling K1 spilled with those). Positions are
+// pos0 + j; 512 coarse regions.
+__device__ __forceinline__ void block_partition_ck1(PartSmem &S, const uint32_t (&xp)[PT_IPT], uint32_t (&aux)[PT_IPT], uint32_t pos0,
+                                                    uint32_t validmask, uint2 *__restrict__ dst, uint32_t cap, uint32_t *__restrict__ cursor,
+                                                    uint2 *__restrict__ spill, unsigned long long *__restrict__ spill_cursor,
+                                                    uint64_t spill_cap, uint32_t *__restrict__ err) {
+    constexpr uint32_t nb = 512;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (uint32_t d = tid; d < nb; d += PT_THREADS) S.tot[d] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PT_IPT; j++)
+        if ((validmask >> j) & 1) aux[j] |= atomicAdd(&S.tot[aux[j] & 511u], 1u) << 13;
+    __syncthreads();
+    {
+        const uint32_t a = S.tot[2 * tid], b = S.tot[2 * tid + 1];
+        uint32_t s = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (uint32_t)o) s += y;
+        }
+        if (lane == 31) S.warp_sums[w] = s;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int ww = 0; ww < PT_WARPS; ww++) woff += ww < (int)w ? S.warp_sums[ww] : 0;
+        const uint32_t excl = woff + s - (a + b);
+        S.dstart[2 * tid] = excl;
+        S.dstart[2 * tid + 1] = excl + a;
+        if (tid == PT_THREADS - 1) S.tile_total = woff + s;
+    }
+    uint32_t gb[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const uint32_t d = tid + q * PT_THREADS;
+        gb[q] = S.tot[d] ? atomicAdd(&cursor[d], S.tot[d]) : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PT_IPT; j++) {
+        if ((validmask >> j) & 1) {
+            const uint32_t d = aux[j] & 511u, slot = S.dstart[d] + (aux[j] >> 13);
+            S.stage[slot] = make_uint2(xp[j], (((aux[j] >> 9) & 15u) << PT_CI_POS_BITS) | (pos0 + j));
+            S.dig[slot] = (uint16_t)d;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) S.gbase[tid + q * PT_THREADS] = gb[q];
+    __syncthreads();
+    const uint32_t total = S.tile_total;
+    for (uint32_t i = tid; i < total; i += PT_THREADS) {
+        const uint2 it = S.stage[i];
+        const uint32_t d = S.dig[i];
+        const uint64_t off = (uint64_t)S.gbase[d] + (i - S.dstart[d]);
+        if (off < cap) {
+            dst[(uint64_t)d * cap + off] = it;
         } else {
             const unsigned long long s = atomicAdd(spill_cursor, 1ull);
             if (s < spill_cap) spill[s] = it; else *err = 1;
@@ -177,7 +234,7 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_seq_kernel(PartArgs a
             }
         }
     }
-    block_partition<32>(S, h, nopos, nopos, 0, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
+    block_partition<32>(S, h, nopos, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
                         a.spill_cursor, a.spill_cap, a.err);
 }
 
@@ -186,15 +243,15 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_seq_kernel(PartArgs a
 // complement in at the high end of the reverse one — the SHL_insert2bits / SHR_insert2bits pair of
 // kmer_api.h:54-81 — instead of re-extracting and re-reversing every window. Same items, same order of positions
 // inside a thread's run (the rank inside a (tile, digit) run differs, which no consumer depends on).
-template <int MINB>
+template <int MINB, int COMPACT>
 __global__ void __launch_bounds__(PT_THREADS, MINB) partition_seq_roll_kernel(PartArgs a) {
     __shared__ PartSmem S;
     const uint64_t base = a.off + blockIdx.x * (uint64_t)PT_TILE + (uint64_t)threadIdx.x * PT_IPT;
     const uint64_t end = a.off + a.n;
-    uint32_t h[PT_IPT], r20[PT_IPT], valid = 0;
+    uint32_t h[PT_IPT], aux[COMPACT ? PT_IPT : 1], valid = 0;        // compact: h holds the item's x word, aux digit | y bits
     const uint32_t nopos[1] = {0};
 #pragma unroll
-    for (int j = 0; j < PT_IPT; j++) { h[j] = 0; r20[j] = 0; }
+    for (int j = 0; j < PT_IPT; j++) { h[j] = 0; if (COMPACT) aux[COMPACT ? j : 0] = 0; }
     if (base < end) {
         const uint32_t k = a.ks.k;
         const uint64_t P = a.p0 + base;
@@ -213,13 +270,20 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) partition_seq_roll_kernel(Pa
         const uint64_t wmask = (1ull << k) - 1;                             // k <= 32
         const uint64_t kk = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
         const uint32_t topsh = 2 * (k - 1);
+        const uint32_t mmask = COMPACT ? (1u << (a.eb - 9)) - 1 : 0, msh = COMPACT ? 32 - a.eb : 0;
 #pragma unroll
         for (int j = 0; j < PT_IPT; j++) {
             if (base + j < end) {
                 if (((M >> j) & wmask) == 0) {
                     const uint64_t canon = fwd < rc ? fwd : rc;
-                    h[j] = pk_probe_hash(canon, a.ks);
-                    r20[j] = (uint32_t)canon & PK_G32_REM_MASK;
+                    const uint32_t hh = pk_probe_hash(canon, a.ks);
+                    if (COMPACT) {
+                        const uint32_t r20 = (uint32_t)canon & PK_G32_REM_MASK;
+                        h[j] = (((hh >> msh) & mmask) << 16) | (r20 >> 4);
+                        aux[COMPACT ? j : 0] = (hh >> 23) | ((r20 & 15u) << 9);
+                    } else {
+                        h[j] = hh;
+                    }
                     valid |= 1u << j;
                 } else {
                     uint8_t *dst = a.rows + (base + j) * a.row_stride + a.col_offset;
@@ -232,11 +296,10 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) partition_seq_roll_kernel(Pa
             rc = (rc >> 2) | ((3 - b) << topsh);
         }
     }
-    if (a.compact)
-        block_partition<1, 1>(S, h, nopos, r20, a.eb, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
-                              a.spill_cursor, a.spill_cap, a.err);
+    if constexpr (COMPACT)
+        block_partition_ck1(S, h, aux, (uint32_t)base, valid, a.buf1, a.cap1, a.cursor1, a.spill, a.spill_cursor, a.spill_cap, a.err);
     else
-        block_partition<1>(S, h, nopos, nopos, 0, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
+        block_partition<1>(S, h, nopos, (uint32_t)base, valid, 32 - a.pb1, 1u << a.pb1, a.buf1, 0, a.cap1, a.cursor1, a.spill,
                            a.spill_cursor, a.spill_cap, a.err);
 }
 
@@ -261,9 +324,8 @@ __global__ void __launch_bounds__(PT_THREADS, 4) partition_fine_kernel(PartArgs 
         }
     }
     // compact items: the fine digit is the top pb2 bits of M, which sits above the 16 remainder bits of x
-    const uint32_t nopos[1] = {0};
     const uint32_t shift = a.compact ? 16 + (a.eb - 9) - a.pb2 : 32 - a.pb1 - a.pb2;
-    block_partition<0>(S, h, pos, nopos, 0, 0, valid, shift, 1u << a.pb2, a.buf2, (uint64_t)c << a.pb2, a.cap2, a.cursor2,
+    block_partition<0>(S, h, pos, 0, valid, shift, 1u << a.pb2, a.buf2, (uint64_t)c << a.pb2, a.cap2, a.cursor2,
                        a.spill, a.spill_cursor, a.spill_cap, a.err);
 }
 
@@ -968,18 +1030,11 @@ static const K3WinVariant k3w_variants[] = {
     K3W(256, 3, 5),      // 1: <= 48 registers
     K3W(256, 3, 3),      // 2: <= 80 registers
     K3W(256, 3, 6),      // 3: <= 40 registers
-    K3W(256, 3, 8),      // 4: <= 32 registers
-    K3W(128, 6, 12),     // 5: 128-thread blocks
-    K3W(128, 6, 16),     // 6
-    K3W(512, 3, 2),      // 7: 512-thread blocks, capacity 1536 (2^17 partitions; pairs with k3_variant 6)
-    K3W(512, 3, 3),      // 8
-    K3W(448, 3, 4),      // 9: capacity 1344: configs[1]'s 1030 items per partition fill 77 % of the block instead of 67 %
-    K3W(448, 3, 3),      // 10
-    K3W(384, 4, 4),      // 11: capacity 1536 with 4 items per thread
-    K3W(640, 2, 3),      // 12: capacity 1280
-    K3W(384, 4, 3),      // 13
-    K3W(320, 4, 5),      // 14: capacity 1280
-    K3W(256, 5, 6),      // 15: capacity 1280
+    // large blocks for one-byte rows out of 32-bit-slot group tables (k3w_big; profiles/r2j..r2q_sweep_*.json: 128-thread
+    // blocks, 8 blocks/SM of 256 threads and capacities 1280 / 1344 were all slower)
+    K3W(512, 3, 2),      // 4: capacity 1536 (2^17 partitions on configs[1]; pairs with k3_variant 6)
+    K3W(512, 3, 3),      // 5
+    K3W(384, 4, 4),      // 6: capacity 1536 with 4 items per thread — the default (K3 1.39 vs 1.51 ms for 5)
 };
 #define PW_MAX_GROUP_STAGE_BYTES 32768u
 #define PW_GROUP_STAGE_TARGET 24576u          // pieces of a group-table window are at most this large
@@ -1087,7 +1142,7 @@ void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n
     // mean fill <= 5/6 of the K3 block capacity (>= 20% head-room for the Poisson spread). One-byte rows out of 32-bit-slot
     // group tables (fine_out == 2): 512-thread blocks of capacity 1536 (profiles/r2j_sweep.json: K3 2.01 vs 2.19 ms)
     const bool big = fine_out == 2 && tune.fine_out && n_local <= 8 && tune.variant < 0 && tune.wvariant < 0;
-    const int wbig = tune.wbig >= 7 && tune.wbig < pk_part_n_wvariants() ? tune.wbig : 8;
+    const int wbig = tune.wbig >= 4 && tune.wbig < pk_part_n_wvariants() ? tune.wbig : 6;
     const uint32_t cap = big ? (uint32_t)k3w_variants[wbig].cap : (uint32_t)k3_pick(tune, 1).cap;
     pl->wbig = big ? wbig : -1;
     pl->compact = 0;
@@ -1161,8 +1216,8 @@ void pk_part_append(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0
     a.off = off; a.n = n;
     const unsigned grid = (unsigned)((n + PT_TILE - 1) / PT_TILE);
     if (a.compact || (sc.tune && sc.tune->k1_roll)) {        // compact items: only the rolling K1 emits them
-        if (sc.tune && sc.tune->k1_roll == 2) partition_seq_roll_kernel<3><<<grid, PT_THREADS, 0, s>>>(a);      // <= 80 registers
-        else partition_seq_roll_kernel<4><<<grid, PT_THREADS, 0, s>>>(a);
+        if (a.compact) partition_seq_roll_kernel<4, 1><<<grid, PT_THREADS, 0, s>>>(a);
+        else partition_seq_roll_kernel<4, 0><<<grid, PT_THREADS, 0, s>>>(a);
     }
     else partition_seq_kernel<<<grid, PT_THREADS, 0, s>>>(a);
 }

@@ -161,7 +161,7 @@ class Index:
         log(f"genome_dist.tsv: Jaccard / Mash distances of {len(names)} genomes from {int(np.trace(inter))} sampled k-mer "
             f"memberships (sampling fraction {frac:.3g}) ({time.perf_counter() - t0:.2f}s)")
 
-    DIST_SAMPLE_TARGET = 4_000_000       # distinct k-mers aimed for in the sample behind genome_dist.tsv (mash: 10000 per genome)
+    DIST_SAMPLE_TARGET = 1_000_000       # distinct k-mers aimed for in the sample behind genome_dist.tsv (mash: 10000 per genome)
 
     def run(self, log=print, genome_ranks: int | None = None) -> dict:
         """Index.run (index.py:172-191): config, then — unless --prepare — the anchor rule for every

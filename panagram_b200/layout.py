@@ -220,32 +220,55 @@ def kmer_sample_hash(keys: np.ndarray) -> np.ndarray:
     return (x >> np.uint64(32)).astype(np.uint32)
 
 
+_BITS8 = ((np.arange(256)[:, None] >> np.arange(8)[None, :]) & 1).astype(np.float64)       # [mask value, bit]
+
+
 def pair_counts(records: list[tuple[np.ndarray, np.ndarray, int]], n_genomes: int) -> np.ndarray:
     """[N, N] intersection sizes (diagonal: set sizes) of the genomes' k-mer samples. records = one
     (keys uint64 [n], tags uint32 [n], genome_begin) per engine as pk_engine_sample_kmers returns them: tag =
-    (local group << 8) | membership mask of genomes genome_begin + 8 * group + 0..7."""
-    keys = np.concatenate([r[0] for r in records]) if records else np.zeros(0, np.uint64)
-    tags = np.concatenate([r[1] for r in records]) if records else np.zeros(0, np.uint32)
-    base = np.concatenate([np.full(r[0].size, r[2], dtype=np.int64) for r in records]) if records else np.zeros(0, np.int64)
+    (local group << 8) | membership mask of genomes genome_begin + 8 * group + 0..7.
+    Per group of 8 genomes the keys are sorted once and equal keys merged (a k-mer can sit in the table and in the
+    stash); pairs inside a group then come from the histogram of the 256 mask values, pairs across two groups from
+    the 256 x 256 histogram of the mask pairs of their common keys (a sorted-merge join)."""
+    groups = {}
+    for keys, tags, base in records:
+        keys = np.asarray(keys, dtype=np.uint64)
+        tags = np.asarray(tags, dtype=np.uint32)
+        for grp in np.unique(tags >> 8) if tags.size else []:
+            sel = (tags >> 8) == grp
+            g0 = int(base) + 8 * int(grp)
+            k, m = keys[sel], (tags[sel] & 0xFF).astype(np.uint8)
+            if g0 in groups:
+                k, m = np.concatenate([groups[g0][0], k]), np.concatenate([groups[g0][1], m])
+            groups[g0] = (k, m)
     inter = np.zeros((n_genomes, n_genomes), dtype=np.float64)
-    if keys.size == 0:
-        return inter
-    order = np.argsort(keys, kind="stable")
-    ks = keys[order]
-    row = np.cumsum(np.r_[True, ks[1:] != ks[:-1]]) - 1            # index of the distinct k-mer of every record
-    n_rows = int(row[-1]) + 1
-    col0 = base[order] + 8 * (tags[order] >> 8).astype(np.int64)
-    mask = (tags[order] & 0xFF).astype(np.uint32)
-    chunk = 1 << 20
-    for r0 in range(0, n_rows, chunk):
-        lo, hi = np.searchsorted(row, [r0, r0 + chunk])
-        b = np.zeros((min(chunk, n_rows - r0), n_genomes), dtype=np.float32)
-        for bit in range(8):
-            sel = ((mask[lo:hi] >> bit) & 1).astype(bool)
-            cols = col0[lo:hi][sel] + bit
-            ok = cols < n_genomes
-            b[row[lo:hi][sel][ok] - r0, cols[ok]] = 1.0
-        inter += (b.T @ b).astype(np.float64)
+    merged = {}
+    for g0, (k, m) in groups.items():
+        order = np.argsort(k, kind="stable")
+        k, m = k[order], m[order]
+        if k.size:
+            first = np.flatnonzero(np.r_[True, k[1:] != k[:-1]])
+            if first.size != k.size:
+                m = np.bitwise_or.reduceat(m, first)
+                k = k[first]
+        merged[g0] = (k, m)
+        ng = min(8, n_genomes - g0)
+        if ng <= 0:
+            continue
+        hist = np.bincount(m, minlength=256).astype(np.float64)
+        inter[g0:g0 + ng, g0:g0 + ng] = ((_BITS8 * hist[:, None]).T @ _BITS8)[:ng, :ng]
+    starts = sorted(merged)
+    for ia, ga in enumerate(starts):
+        for gb in starts[ia + 1:]:
+            na, nb = min(8, n_genomes - ga), min(8, n_genomes - gb)
+            if na <= 0 or nb <= 0:
+                continue
+            (ka, ma), (kb, mb) = merged[ga], merged[gb]
+            _, ja, jb = np.intersect1d(ka, kb, assume_unique=True, return_indices=True)
+            h2 = np.bincount(ma[ja].astype(np.int64) * 256 + mb[jb], minlength=65536).astype(np.float64).reshape(256, 256)
+            blk = (_BITS8.T @ h2 @ _BITS8)[:na, :nb]
+            inter[ga:ga + na, gb:gb + nb] = blk
+            inter[gb:gb + nb, ga:ga + na] = blk.T
     return inter
 
 
@@ -264,12 +287,8 @@ def genome_dist_tsv(names: list[str], inter: np.ndarray, k: int) -> str:
     (figs.py:50-59: f, t, d, p, x per line; only d is used): for every pair i > j one line
     name_i, name_j, Mash distance, p-value, shared/total — here from the intersection / union sizes of the genomes'
     k-mer samples instead of 10000-hash MinHash sketches. p-value: the probability of >= `shared` common k-mers among
-    `total` by chance, P[Binomial(total, r) >= shared] with r the expected Jaccard of two random k-mer sets of these
-    sizes (mash's own significance test); it is 0 for any pair of related genomes."""
-    try:
-        from scipy.stats import binom
-    except Exception:       # noqa: BLE001
-        binom = None
+    `total` by chance — mash tests P[Binomial(total, r) >= shared] with r the expected Jaccard of two random k-mer sets
+    of these sizes; here its Chernoff bound exp(-total * KL(shared/total || r)) — 0 for any pair of related genomes."""
     n = len(names)
     size = np.diag(inter)
     space = 4.0 ** k
@@ -282,11 +301,14 @@ def genome_dist_tsv(names: list[str], inter: np.ndarray, k: int) -> str:
             d = mash_distance(jac, k)
             px, py = 1.0 / (1.0 + space / max(size[i], 1.0)), 1.0 / (1.0 + space / max(size[j], 1.0))
             r = px * py / (px + py - px * py)
-            if shared <= 0:
+            # Chernoff bound of the binomial tail: exp(-total * KL(shared/total || r)); 1 when the overlap is at chance level
+            a = shared / total if total > 0 else 0.0
+            if shared <= 0 or a <= r:
                 p = 1.0
-            elif binom is not None:
-                p = float(binom.sf(shared - 1, max(total, 1), r))
+            elif a >= 1.0:
+                p = float(r ** total) if total < 1e4 else 0.0
             else:
-                p = 0.0
+                kl = a * np.log(a / r) + (1.0 - a) * np.log((1.0 - a) / (1.0 - r))
+                p = float(np.exp(-min(total * kl, 745.0))) if total * kl < 745.0 else 0.0
             lines.append(f"{names[i]}\t{names[j]}\t{d:.6g}\t{p:.6g}\t{int(shared)}/{int(total)}\n")
     return "".join(lines)

@@ -567,7 +567,7 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
                       dict(k3w_variant=1, k3w_group=2), dict(k3w_variant=2, k3w_group=4), dict(k3w_variant=3),
                       dict(k3_window=0), dict(k3_window=1, k3w_variant=-1, k3w_group=4, unpermute=0),
                       dict(unpermute=1, fine_out=0), dict(fine_out=0, k3_rank_atomic=0), dict(fine_out=1, k3_rank_atomic=1, k3w_variant=3),
-                      dict(k3_variant=6, k3w_variant=7), dict(k3_variant=-1, k3w_variant=-1), dict(k1_roll=0), dict(k1_roll=1), dict(compact_items=0), dict(compact_items=1, k3w_big=11)):
+                      dict(k3_variant=6, k3w_variant=4), dict(k3_variant=-1, k3w_variant=-1), dict(k1_roll=0), dict(k1_roll=1), dict(compact_items=0), dict(compact_items=1, k3w_big=5)):
             eng.tune(**knobs)
             got = eng.anchor_genome(seqs)
             assert (got["col_sums"] == want["col_sums"]).all(), knobs
