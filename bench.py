@@ -129,9 +129,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_genome(anc, g, seed):
+def mu_period_of(wl):
+    """Weak workloads: genome g of shard r diverges from the ancestor like genome g of shard 0 (independent
+    mutations), so every GPU's shard is a pan-genome with the statistics of the named configuration — the same
+    number of distinct k-mers, the same table size, the same work: weak scaling in the strict sense. Strong
+    workloads keep the generator's default ladder of 16 rates."""
+    return min(16, wl["n_per_gpu"]) if "n_per_gpu" in wl else 16
+
+
+def make_genome(anc, g, seed, mu_period=16):
     from panagram_b200 import synth
-    return [s for _, s in synth.genome_chroms(anc, g, seed)]
+    return [s for _, s in synth.genome_chroms(anc, g, seed, mu_period=mu_period)]
 
 
 REF_MAX_BASES = 1_100_000_000      # the reference arm builds KMC databases for at most this many bases in total
@@ -153,7 +161,8 @@ def workload_config(wl, args, world):
     """The `config` object of the JSON line: what was run, identical in both arms."""
     n = n_genomes_of(wl, world)
     strong = "n_total" in wl
-    return {"workload": wl["name"] + (f" x{world} genome shards ({n} genomes)" if world > 1 and not strong else ""),
+    return {"workload": wl["name"] + (f" x{world} genome shards ({n} genomes; genome g of every shard has the divergence rate of genome g of "
+                                        f"shard 0, so every shard has configs-sized tables)" if world > 1 and not strong else ""),
             "k": wl["k"], "n_genomes": n, "anchors": len(wl["anchors"]), "genome_length": wl["length"],
             "positions_per_step": None}
 
@@ -167,7 +176,7 @@ def reference_setup(wl, n, cores, log=lambda m: None):
     from oracle import refpipe
     from panagram_b200 import synth
     k = wl["k"]
-    root = Path(tempfile.gettempdir()) / f"pk_refcache_n{n}_L{wl['length']}_s{wl['seed']}_k{k}_a{'-'.join(map(str, wl['anchors']))}_c{min(cores, n)}"
+    root = Path(tempfile.gettempdir()) / f"pk_refcache_n{n}_m{mu_period_of(wl)}_L{wl['length']}_s{wl['seed']}_k{k}_a{'-'.join(map(str, wl['anchors']))}_c{min(cores, n)}"
     meta_p = root / "meta.json"
     if meta_p.exists():
         m = json.loads(meta_p.read_text())
@@ -182,7 +191,7 @@ def reference_setup(wl, n, cores, log=lambda m: None):
     # run_anchor takes at most N anchors (cpp/anchor.cpp:208-211) and runs one thread per anchor
     per_anchor = max(1, min(cores, n) // len(wl["anchors"]))
     for g in range(n):
-        chroms = synth.genome_chroms(anc, g, wl["seed"])
+        chroms = synth.genome_chroms(anc, g, wl["seed"], mu_period=mu_period_of(wl))
         fa = root / "fa" / f"g{g}.fa"
         synth.write_fasta(fa, chroms)
         refpipe.kmc_count(root, names[g], str(fa), g, k, threads=cores, timings=timings)
@@ -450,7 +459,7 @@ def main():
     my_anchors = [a for j, a in enumerate(wl["anchors"]) if j % rp == sh.pi]
     anchor_chroms = {}
     for g in range(g_begin, g_end):
-        chroms = make_genome(anc, g, wl["seed"])
+        chroms = make_genome(anc, g, wl["seed"], mu_period_of(wl))
         if g in my_anchors:
             anchor_chroms[g] = chroms
         eng.reserve(g, sum(c.size for c in chroms))
@@ -460,7 +469,7 @@ def main():
             eng.seal_group((g - g_begin) // 8)       # per-genome tables of the finished group are freed here
     for a in my_anchors:
         if a not in anchor_chroms:
-            anchor_chroms[a] = make_genome(anc, a, wl["seed"])
+            anchor_chroms[a] = make_genome(anc, a, wl["seed"], mu_period_of(wl))
     del anc
     eng.finalize()
     if args.e2e_batches:
@@ -665,11 +674,12 @@ def main():
         pos1 = sum(packed[-1]["nks"]) if packed else 0
         n_group_tabs = (npg + 7) // 8
         win = int(ks.get("k_probe_window", 0))
-        alg_design = pos1 * ((n_group_tabs if win in (2, 3) else npg) * 32 + 0.375 + rb_local * 1.01)
+        alg_design = pos1 * ((n_group_tabs if win in (2, 3, 4) else npg) * 32 + 0.375 + rb_local * 1.01)
         alg_survey = pos1 * (npg * 32 + 0.375 + rb_local * 1.01)
         k3_ms = ks["k_probe_ms"] if ks["k_probe_ms"] > 0 else None
         stage1_ms = sum(ks[x] for x in ("k_partition_ms", "k_fine_ms", "k_probe_ms", "k_spill_ms", "k_unpermute_ms"))
-        kernel_name = {2: "probe_win_kernel<group tables>", 1: "probe_win_kernel", 3: "items_group_kernel"}.get(win, "probe_part_kernel") \
+        kernel_name = {2: "probe_win_kernel<group tables>", 1: "probe_win_kernel", 3: "items_group_kernel",
+                       4: "probe_g32c_kernel (lean window kernel, one 32-bit-slot group table)"}.get(win, "probe_part_kernel") \
             if k3_ms else "probe_kernel (direct)"
         traffic, traffic_src, ncu_ms = None, "not measured (--no-ncu)", None
         if world == 1 and k3_ms and not args.no_ncu:
@@ -679,7 +689,7 @@ def main():
             # capture is the probe kernel of the second (the spill drain reuses probe_part / items_group: skipped)
             free_b, total_b = torch.cuda.mem_get_info()
             if free_b > (total_b - free_b) + (16 << 30):
-                rx, skip = {2: ("probe_win_kernel", 1), 1: ("probe_win_kernel", 1), 3: ("items_group_kernel", 2)}.get(win, ("probe_part_kernel", 2))
+                rx, skip = {2: ("probe_win_kernel", 1), 1: ("probe_win_kernel", 1), 3: ("items_group_kernel", 2), 4: ("probe_g32c_kernel", 1)}.get(win, ("probe_part_kernel", 2))
                 m, traffic_src = ncu_traffic(child, rx, skip)
             else:
                 m, traffic_src = None, "not measured: no room for the ncu child's tables beside ours"
@@ -690,7 +700,7 @@ def main():
         roof = {"bound": "hbm", "kernel": kernel_name, "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src,
                 "kernel_ms": k3_ms, "launch": f"one anchor ({pos1} positions) against {npg} genomes' tables on one GPU",
                 "algorithmic": "design: one 32 B sector per position and 8-genome group table + 0.375 B/position of packed "
-                               "sequence + 1.01 x row bytes written" if win in (2, 3) else
+                               "sequence + 1.01 x row bytes written" if win in (2, 3, 4) else
                                "SURVEY §8d: one 32 B sector per (position, genome) + 0.375 B/position + 1.01 x row bytes",
                 "algorithmic_bytes_per_launch": alg_design, "achieved": alg_design / t_k3 / 1e9,
                 "frac": alg_design / t_k3 / 1e9 / hbm_peak,

@@ -119,7 +119,7 @@ _LIB = None
 
 def build(verbose: bool = False) -> Path:
     """Compile libpkanchor.so in-tree with nvcc for sm_100a."""
-    r = subprocess.run(["make", "-C", str(PKG_DIR / "csrc")], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j6", "-C", str(PKG_DIR / "csrc")], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"building libpkanchor.so failed:\n{r.stdout}\n{r.stderr}")
     if verbose:

@@ -995,6 +995,153 @@ __global__ void __launch_bounds__(T, MINB) probe_win_kernel(const __grid_constan
     }
 }
 
+// K3, lean form for the configuration the metric is quoted on: ONE 32-bit-slot group table (<= 8 genomes, one-byte
+// rows), compact items, fine position bins, the partition's whole window in one stage. Same results as
+// probe_win_kernel<.., PK_FMT_GROUP32, .., 0> on such a launch; what it drops is that kernel's generality, which the
+// ncu source view showed to cost half its instructions and its worst stalls (profiles/r2r: 1.04 G warp instructions,
+// the row bits in LOCAL memory because a lambda indexed them, per-group window geometry re-read from the constant
+// bank, a deferred-walk-on queue with two more barriers, and the reservation atomics' round trip exposed between two
+// barriers):
+//   * a key missing from a full home bucket walks on INLINE through the staged window (rare: keys are displaced
+//     from their home bucket in < 1 % of the cases), leaving the window or reaching the maximal displacement (the
+//     stash) through the global lookup;
+//   * a slot matches when (slot ^ key24) has no low 24 bits: one LOP3 that sets a predicate + one predicated OR per
+//     slot, the mask shifted out once per bucket;
+//   * ranks inside the position bins are taken BEFORE the probe (they depend on the positions only) and with EARLY
+//     the per-bin reservations (one global atomicAdd per bin the block touches) are issued before the wait on the
+//     window, so their round trip runs under the TMA copy and the probes; their results are first needed after.
+template <int T, int IPT, int MINB, int EARLY>
+__global__ void __launch_bounds__(T, MINB) probe_g32c_kernel(const __grid_constant__ ProbeArgs a, const uint32_t stage_bytes) {
+    static_assert(2 * T >= PP_FBINS, "two rounds of the block cover the fine bins");
+    extern __shared__ __align__(128) uint8_t s_win[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t o_cnt[PP_FBINS], o_gb[PP_FBINS];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t win0 = pw_smem(s_win), bar = pw_smem(&s_bar);
+    const uint32_t xoff = (tid & 1) * 16;           // odd lanes read the bucket halves in the other order: spreads the banks
+    const PkTable t = a.tabs[0];
+    const uint32_t nb = t.n_buckets, sh = a.out_shift, lowmask = (1u << sh) - 1;
+    const uint32_t ngg = min(PK_U_GROUP, a.n_genomes);
+    uint32_t *list4 = (uint32_t *)a.out_list;
+    if (tid == 0) { pw_mbar_init(bar, 1); pw_mbar_fence_init(); }
+    uint32_t par = 0;
+    for (uint64_t q = blockIdx.x; q < a.n_regions; q += gridDim.x) {
+        // the region's fill, the window copy and the first half of the item loads are issued together: none of them
+        // depends on another (item slots beyond the fill hold stale items of the same buffer: loaded, never used)
+        const uint32_t craw = a.counts[q];
+        const uint32_t b0 = __umulhi((uint32_t)(q << (32 - a.pb)), nb);
+        const uint32_t nbk = __umulhi((uint32_t)(((q + 1) << (32 - a.pb)) - 1), nb) - b0 + 1;
+        const bool staged = nbk * 32 <= stage_bytes;            // the host sizes the stage for every window; kept as a guard
+        if (tid == 0 && staged) {
+            pw_mbar_expect_tx(bar, nbk * 32);
+            pw_bulk_g2s(win0, t.slots + 4ull * b0, nbk * 32, bar);
+        }
+        const uint2 *src = a.buf + q * (uint64_t)a.cap;
+        uint2 it[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT / 2; j++) it[j] = src[tid + j * T];
+        const uint32_t cnt = min(craw, a.cap);
+        if (cnt == 0) {                                         // (uniform) nothing to probe: let the copy land, then move on
+            __syncthreads();                                    // (first trip: the mbarrier's initialisation becomes visible)
+            if (staged) { pw_mbar_wait(bar, par); par ^= 1; }
+            __syncthreads();
+            continue;
+        }
+#pragma unroll
+        for (int j = IPT / 2; j < IPT; j++) it[j] = tid + j * T < cnt ? src[tid + j * T] : make_uint2(0, 0);
+        for (uint32_t i = tid; i < a.n_bins; i += T) o_cnt[i] = 0;
+        __syncthreads();                                        // bin counters zeroed, mbarrier initialised
+        uint32_t rk[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++)
+            rk[j] = tid + j * T < cnt ? atomicAdd(&o_cnt[(it[j].y & PT_CI_POS_MASK) >> sh], 1u) : 0u;
+        uint32_t gb0 = 0, gb1 = 0;
+        if (EARLY) {
+            __syncthreads();
+            if (tid < a.n_bins) { const uint32_t c = o_cnt[tid]; if (c) gb0 = atomicAdd(&a.out_cursor[tid * PP_OCS], c); }
+            if (tid + T < a.n_bins) { const uint32_t c = o_cnt[tid + T]; if (c) gb1 = atomicAdd(&a.out_cursor[(tid + T) * PP_OCS], c); }
+        }
+        // the hash of a compact item (PartSmem): top 9 bits = its coarse region, then the stored bits, then mix32(R20) >> eb
+        const uint32_t h_top = (uint32_t)(q >> a.pb2) << 23;
+        if (staged) { pw_mbar_wait(bar, par); par ^= 1; }
+        uint32_t wbase = win0 + xoff - b0 * 32;                 // + 32 * bucket = first (even lanes) / second (odd lanes) half
+        asm volatile("" : "+r"(wbase));
+        uint32_t bits[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            bits[j] = 0;
+            if (tid + j * T < cnt) {
+                const uint32_t r20 = ((it[j].x & 0xFFFFu) << 4) | (it[j].y >> PT_CI_POS_BITS);
+                const uint32_t h = h_top | ((it[j].x >> 16) << (32 - a.eb)) | (pk_mix32(r20) >> a.eb);
+                const uint32_t key = r20 << PK_S32_DISP_BITS;
+                const uint32_t b = __umulhi(h, nb);
+                uint32_t acc = 0, last;
+                if (staged) {
+                    const uint32_t wa = wbase + b * 32;
+                    const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
+                    if (((A.x ^ key) & PK_G32_KEY_MASK) == 0) acc |= A.x;
+                    if (((A.y ^ key) & PK_G32_KEY_MASK) == 0) acc |= A.y;
+                    if (((A.z ^ key) & PK_G32_KEY_MASK) == 0) acc |= A.z;
+                    if (((A.w ^ key) & PK_G32_KEY_MASK) == 0) acc |= A.w;
+                    if (((B.x ^ key) & PK_G32_KEY_MASK) == 0) acc |= B.x;
+                    if (((B.y ^ key) & PK_G32_KEY_MASK) == 0) acc |= B.y;
+                    if (((B.z ^ key) & PK_G32_KEY_MASK) == 0) acc |= B.z;
+                    if (((B.w ^ key) & PK_G32_KEY_MASK) == 0) acc |= B.w;
+                    last = xoff ? A.w : B.w;
+                } else {
+                    const u64x4 v = pk_ld_bucket_ca(t.slots + 4ull * b);
+                    acc = pk_g32_bucket_mask(v, key) << PK_G32_MASK_SHIFT;
+                    last = (uint32_t)(v.d >> 32);
+                }
+                if (acc == 0 && last != PK_EMPTY32) {
+                    // full home bucket without the key: the slot at displacement r holds key + r
+                    const uint32_t maxd = pk_u_max_disp(nb);
+                    bool decided = false;
+                    if (staged)
+                        for (uint32_t r = 1; r <= maxd && b - b0 + r < nbk; r++) {
+                            const uint32_t wa = wbase + (b + r) * 32;
+                            const uint4 A = pw_lds128(wa), B = pw_lds128(wa ^ 16);
+                            const uint32_t m = pw_umask32(A, B, key + r);
+                            if (m) { acc = m << PK_G32_MASK_SHIFT; decided = true; break; }
+                            if ((xoff ? A.w : B.w) == PK_EMPTY32) { decided = true; break; }
+                        }
+                    if (!decided)       // past the window's end, or 14 full buckets in a row (stash)
+                        acc = pk_group_lookup(t, pk_canon_at(a.words, a.p0 + (it[j].y & PT_CI_POS_MASK), a.ks.k), h, a.g_first, ngg, a.ks)
+                              << PK_G32_MASK_SHIFT;
+                }
+                bits[j] = acc >> PK_G32_MASK_SHIFT;
+            }
+        }
+        if (!EARLY) {
+            __syncthreads();
+            if (tid < a.n_bins) { const uint32_t c = o_cnt[tid]; if (c) gb0 = atomicAdd(&a.out_cursor[tid * PP_OCS], c); }
+            if (tid + T < a.n_bins) { const uint32_t c = o_cnt[tid + T]; if (c) gb1 = atomicAdd(&a.out_cursor[(tid + T) * PP_OCS], c); }
+        }
+        if (tid < a.n_bins) o_gb[tid] = gb0;
+        if (tid + T < a.n_bins) o_gb[tid + T] = gb1;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < IPT; j++)
+            if (tid + j * T < cnt) {
+                const uint32_t pos = it[j].y & PT_CI_POS_MASK;
+                // slot = start of the bin (pos with its low bits cleared) + the block's run in the bin + the rank in the run
+                list4[(pos & ~lowmask) + o_gb[pos >> sh] + rk[j]] = ((pos & lowmask) << 8) | (bits[j] & 0xffu);
+            }
+        __syncthreads();            // the window, the counters and o_gb are free again
+    }
+}
+struct K3LeanVariant { int threads, cap; void (*fn)(ProbeArgs, uint32_t); };
+#define K3L(T, IPT, MINB, EARLY) {T, T * IPT, probe_g32c_kernel<T, IPT, MINB, EARLY>}
+static const K3LeanVariant k3l_variants[] = {
+    K3L(384, 4, 4, 1),      // 1 (tune.lean = index + 1): capacity 1536, reservations before the probes
+    K3L(384, 4, 4, 0),      // 2: ... after the probes
+    K3L(384, 4, 5, 1),      // 3: <= 32 registers, 5 blocks/SM
+    K3L(512, 3, 3, 1),      // 4
+    K3L(512, 3, 4, 1),      // 5: <= 32 registers
+    K3L(256, 6, 6, 1),      // 6
+};
+int pk_part_n_lvariants(void) { return (int)(sizeof k3l_variants / sizeof k3l_variants[0]); }
+
 // variants of K3 selectable at run time (PK_K3_VARIANT) while the design is being tuned
 struct K3Variant { int threads, cap; void (*fn[2])(ProbeArgs); };   // fn[fmt]
 #define K3V(T, IPT, SORT, MINB, GU) {T, T * IPT, {probe_part_kernel<T, IPT, PK_FMT_S64, SORT, MINB, GU>, probe_part_kernel<T, IPT, PK_FMT_S32, SORT, MINB, GU>}}
@@ -1287,6 +1434,14 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
                 const uint32_t stage_bytes = (uint32_t)cb * 32, n_stages = np == 1 ? 1 : 2;
                 p.ng = np; p.tbits = PK_U_GROUP; p.chunk_buckets = nch > 1 ? (uint32_t)cb : 0;
                 const int fk = (nch > 1 ? 3 : 2) + (p.tabs[0].fmt == PK_TFMT_G32 ? 2 : 0);
+                if (fk == 4 && np == 1 && nt == 1 && p.compact && p.out_fine && sc.out_list && p.counts && tu.lean > 0 &&
+                    tu.lean <= pk_part_n_lvariants() && (uint32_t)k3l_variants[tu.lean - 1].cap == pl.cap2 && tu.rank_atomic == 1) {
+                    const K3LeanVariant &lv = k3l_variants[tu.lean - 1];
+                    cudaFuncSetAttribute(lv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PW_MAX_GROUP_STAGE_BYTES);
+                    lv.fn<<<p.n_regions, lv.threads, stage_bytes, s>>>(p, stage_bytes);
+                    last_window = 4;
+                    continue;
+                }
                 cudaFuncSetAttribute(wv.fn[fk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
                 wv.fn[fk]<<<p.n_regions, wv.threads, (size_t)n_stages * stage_bytes, s>>>(p, stage_bytes, 1, n_stages);
                 last_window = 2;

@@ -2,7 +2,9 @@
 
 Ancestor: iid uniform ACGT of length L (seed = 20260000 + config index). Genome g
 is the ancestor with independent per-base substitutions at rate
-mu_g = 0.002 * (1 + g mod 16) (stream seed + 1 + g), split into C equal
+mu_g = 0.002 * (1 + g mod mu_period) (stream seed + 1 + g; mu_period = 16 unless a
+caller says otherwise: bench.py's weak-scaling series uses the shard width, so that every GPU's shard has the
+divergence ladder — hence the table size and the work — of configs[1] itself), split into C equal
 chromosomes chr1..chrC. Every genome carries one N-run of 1000 at offset
 L/(2C) of chr1 and a lowercase stretch of 10000 at the start of chr2, so the
 non-ACGT and case-folding paths are exercised (kmer_api.h:264-275 semantics).
@@ -21,9 +23,9 @@ def ancestor_codes(length: int, seed: int) -> np.ndarray:
     return np.random.default_rng(seed).integers(0, 4, size=length, dtype=np.uint8)
 
 
-def genome_codes(anc: np.ndarray, g: int, seed: int) -> np.ndarray:
+def genome_codes(anc: np.ndarray, g: int, seed: int, mu_period: int = 16) -> np.ndarray:
     """Genome g's 2-bit codes: ancestor + substitutions at rate mu_g."""
-    mu = 0.002 * (1 + g % 16)
+    mu = 0.002 * (1 + g % mu_period)
     rng = np.random.default_rng(seed + 1 + g)
     n = anc.shape[0]
     nsub = rng.binomial(n, mu)
@@ -35,9 +37,9 @@ def genome_codes(anc: np.ndarray, g: int, seed: int) -> np.ndarray:
 
 
 def genome_chroms(anc: np.ndarray, g: int, seed: int, n_chroms: int = 5,
-                  n_run: int = 1000, lower_run: int = 10000) -> list[tuple[str, np.ndarray]]:
+                  n_run: int = 1000, lower_run: int = 10000, mu_period: int = 16) -> list[tuple[str, np.ndarray]]:
     """[(name, ASCII uint8 array)] for genome g."""
-    codes = genome_codes(anc, g, seed)
+    codes = genome_codes(anc, g, seed, mu_period)
     asc = _ACGT[codes]
     L = asc.shape[0]
     clen = L // n_chroms

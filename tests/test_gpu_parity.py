@@ -551,7 +551,9 @@ def test_partitioned_path_large_vs_oracle_and_direct(n_genomes, k, repeats, load
 def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
     """The TMA-staged window kernel (every variant / stage count), the L1/L2 kernel and the direct kernel
     give identical rows; so does a batch whose table windows are too large for a shared-memory stage."""
-    genomes = big_case(n_genomes, k, 1_400_000, 77 + n_genomes)
+    # k = 21: 6 M positions = 2^13 partitions, so that a partition's window of the (forced, 2^22-bucket) 32-bit-slot
+    # group table fits one shared-memory stage and the lean window kernel takes the launch
+    genomes = big_case(n_genomes, k, 6_000_000 if k == 21 else 1_400_000, 77 + n_genomes)
     eng = Engine(k, n_genomes, load_factor=load, probe_mode="partitioned")
     engd = Engine(k, n_genomes, load_factor=load, probe_mode="direct")
     for g, chroms in enumerate(genomes):
@@ -597,9 +599,14 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
             assert eng.group_stats(0)["n_buckets"] >= 1 << (2 * k - 20)
         else:
             assert eng.group_stats(0)["bytes"] == bytes64
-        for knobs in (dict(k3_window=1), dict(k3_window=0)):
+        # k3_lean: the lean K3 (one 32-bit-slot group table, compact items, fine bins), every variant, and the general
+        # window kernel (0) on the same launch; on other launches (k = 31: 64-bit slots) the knob changes nothing
+        for knobs in (dict(k3_window=1), dict(k3_window=0), dict(k3_window=1, k3_lean=0), dict(k3_lean=2), dict(k3_lean=3),
+                      dict(k3_lean=4), dict(k3_lean=5), dict(k3_lean=6), dict(k3_lean=1)):
             eng.tune(**knobs)
             got = eng.anchor_genome(seqs)
+            if k == 21 and knobs.get("k3_window", 1):
+                assert int(eng.stats()["k_probe_window"]) == (2 if knobs.get("k3_lean") == 0 else 4), knobs
             gz = eng.anchor_genome_bgzf(seqs)
             assert (got["col_sums"] == want["col_sums"]).all() and (gz["col_sums"] == want["col_sums"]).all(), knobs
             for a, b in zip(got["chroms"], want["chroms"]):
