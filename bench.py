@@ -655,7 +655,8 @@ def main():
                     d2h = e2e_pass(bgzf)
                 barrier()
                 ms = (time.perf_counter() - t1) * 1e3 / args.steps
-                t = torch.tensor([ms, float(d2h), float(sum(c.size for hs in h_sets for c in hs))], device=dev, dtype=torch.float64)
+                # host -> device: every rank copies its 1/Rg share of its group's anchors (the rest arrives over NVLink)
+                t = torch.tensor([ms, float(d2h), float(sum(c.size for hs in h_sets for c in hs)) / rg], device=dev, dtype=torch.float64)
                 tmax = t.clone()
                 if world > 1:
                     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -3,8 +3,8 @@
 // (Python path: bgzip.BGZipWriter + `bgzip -rI`, panagram/index.py:1035-1037,1089-1094). See
 // pk_deflate.cuh for the format; three kernels:
 //
-//   bgzf_encode   one 128-thread block per BGZF block (0xff00 payload bytes): every thread deflates its
-//                 510-byte sub-chunk into a staging slot and CRCs it; the block combines sizes and CRCs
+//   bgzf_encode   one 256-thread block per BGZF block (0xff00 payload bytes): every thread deflates its
+//                 255-byte sub-chunk into a staging slot and CRCs it; the block combines sizes and CRCs
 //   bgzf_scan     one block: exclusive scan of the member sizes -> member offsets, the .gzi image, totals
 //   bgzf_assemble one block per member: header + pieces (or one stored block) + trailer, contiguous
 #include <cuda_runtime.h>
@@ -15,20 +15,21 @@
 struct PkzMeta { uint32_t cdata, crc, isize, stored; };
 
 // one block (PKZ_LANES threads) per BGZF member; thread l deflates and CRCs piece l. The member's payload is
-// staged in shared memory first: every thread walks its own 510 bytes one at a time, and out of global memory
+// staged in shared memory first: every thread walks its own 255 bytes (matches four at a time), and out of global memory
 // those byte loads missed L1 (16 resident blocks x 64 KB of payload per SM) and cost an L2 round trip each:
 // 1.07 ms for 135 MB, ~1100 cycles per byte per thread (profiles/r1h_launches.csv).
 __global__ void __launch_bounds__(PKZ_LANES) bgzf_encode_kernel(const uint8_t *__restrict__ in, uint64_t n, uint32_t dist,
                                                                 uint8_t *__restrict__ stage, uint16_t *__restrict__ piece_sizes,
                                                                 PkzMeta *__restrict__ meta, const uint32_t *__restrict__ g_tables) {
-    extern __shared__ __align__(16) uint8_t s_blk[];           // [PKZ_PAYLOAD]
-    __shared__ uint32_t s_tab[256 + PKZ_CRC_MATS * 32];
+    extern __shared__ __align__(16) uint8_t s_blk[];           // [PKZ_PAYLOAD + PKZ_PAD]
+    __shared__ uint32_t s_tab[PKZ_CRC_TAB_WORDS + PKZ_CRC_MATS * 32 + 256];
     __shared__ uint32_t s_crc[PKZ_LANES / 32], s_size[PKZ_LANES / 32];
     const uint32_t l = threadIdx.x;
     const uint64_t b = blockIdx.x;
     const uint8_t *blk = in + b * PKZ_PAYLOAD;
     const uint32_t blen = (uint32_t)(n - b * PKZ_PAYLOAD < PKZ_PAYLOAD ? n - b * PKZ_PAYLOAD : PKZ_PAYLOAD);
-    for (uint32_t i = l; i < 256 + PKZ_CRC_MATS * 32; i += PKZ_LANES) s_tab[i] = g_tables[i];
+    for (uint32_t i = l; i < PKZ_CRC_TAB_WORDS + PKZ_CRC_MATS * 32 + 256; i += PKZ_LANES) s_tab[i] = g_tables[i];
+    if (l < PKZ_PAD) s_blk[blen + l] = 0;
     if ((((uintptr_t)blk) & 15) == 0) {
         for (uint32_t i = l * 16; i + 16 <= blen; i += PKZ_LANES * 16) *(uint4 *)(s_blk + i) = *(const uint4 *)(blk + i);
         for (uint32_t i = (blen & ~15u) + l; i < blen; i += PKZ_LANES) s_blk[i] = blk[i];
@@ -39,10 +40,11 @@ __global__ void __launch_bounds__(PKZ_LANES) bgzf_encode_kernel(const uint8_t *_
     const uint32_t s = l * PKZ_SUB < blen ? l * PKZ_SUB : blen;
     const uint32_t e = (l + 1) * PKZ_SUB < blen ? (l + 1) * PKZ_SUB : blen;
     uint32_t size = 0;
-    if (e > s) size = pkz_encode_piece(s_blk, s, e, dist, e == blen, stage + (b * PKZ_LANES + l) * PKZ_STAGE);
+    if (e > s) size = pkz_encode_piece(s_blk, s, e, dist, e == blen, stage + (b * PKZ_LANES + l) * PKZ_STAGE,
+                                       s_tab + PKZ_CRC_TAB_WORDS + PKZ_CRC_MATS * 32);
     piece_sizes[b * PKZ_LANES + l] = (uint16_t)size;
     uint32_t crc = pkz_crc_update(s_tab, l == 0 ? 0xFFFFFFFFu : 0u, s_blk + s, e - s);
-    crc = pkz_crc_shift(s_tab + 256, crc, blen - e);           // bytes that follow this piece
+    crc = pkz_crc_shift(s_tab + PKZ_CRC_TAB_WORDS, crc, blen - e);           // bytes that follow this piece
     crc = __reduce_xor_sync(0xffffffffu, crc);
     const uint32_t total = __reduce_add_sync(0xffffffffu, size);
     if ((l & 31) == 0) { s_crc[l >> 5] = crc; s_size[l >> 5] = total; }
@@ -160,9 +162,11 @@ uint64_t pk_bgzf_scratch_bytes(uint64_t n) {
     return ((nb * PKZ_LANES * PKZ_STAGE + 255) & ~255ull) + ((nb * 8 + 255) & ~255ull) + ((nb * sizeof(PkzMeta) + 255) & ~255ull) +
            ((nb * PKZ_LANES * 2 + 255) & ~255ull) + 256;
 }
-void pk_bgzf_tables_host(uint32_t *dst /*[256 + 17*32]*/) { pkz_make_tables(dst, dst + 256); }
+void pk_bgzf_tables_host(uint32_t *dst /*[PK_BGZF_TABLE_WORDS]*/) {
+    pkz_make_tables(dst, dst + PKZ_CRC_TAB_WORDS, dst + PKZ_CRC_TAB_WORDS + PKZ_CRC_MATS * 32);
+}
 
-// d_tables: 256 + PKZ_CRC_MATS*32 uint32 on the device; d_scratch: pk_bgzf_scratch_bytes(n) bytes.
+// d_tables: PK_BGZF_TABLE_WORDS uint32 on the device; d_scratch: pk_bgzf_scratch_bytes(n) bytes.
 void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_out, unsigned long long *d_gzi,
                     unsigned long long *d_totals, uint8_t *d_scratch, const uint32_t *d_tables, pk_stream_t s) {
     const uint64_t nb = pk_bgzf_blocks_impl(n);
@@ -174,8 +178,8 @@ void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_o
     if (dist < 1) dist = 1;
     if (dist > 32768) dist = 32768;
     if (nb) {
-        cudaFuncSetAttribute(bgzf_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PKZ_PAYLOAD);
-        bgzf_encode_kernel<<<(unsigned)nb, PKZ_LANES, PKZ_PAYLOAD, s>>>(d_in, n, dist, stage, piece_sizes, meta, d_tables);
+        cudaFuncSetAttribute(bgzf_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PKZ_PAYLOAD + PKZ_PAD));
+        bgzf_encode_kernel<<<(unsigned)nb, PKZ_LANES, PKZ_PAYLOAD + PKZ_PAD, s>>>(d_in, n, dist, stage, piece_sizes, meta, d_tables);
     }
     bgzf_scan_kernel<<<1, 1024, 0, s>>>(meta, nb, coff, d_gzi, d_totals, d_out);
     if (nb) bgzf_assemble_kernel<<<(unsigned)nb, 256, 0, s>>>(d_in, n, stage, piece_sizes, meta, coff, d_out);

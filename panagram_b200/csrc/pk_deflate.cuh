@@ -5,13 +5,13 @@
 // sequence of independent gzip members of <= 64 KiB, each holding <= 0xff00 payload bytes; the reader
 // side (index.py:793-845) only needs (a) valid gzip members and (b) the .gzi table of block starts.
 // Parity with the reference is defined on the DECOMPRESSED bytes, so the encoder is free to be
-// GPU-shaped: one 128-thread block per BGZF block, each thread deflates its own 510-byte sub-chunk into a
+// GPU-shaped: one 256-thread block per BGZF block, each thread deflates its own 255-byte sub-chunk into a
 // byte-aligned piece of the member's deflate stream:
 //
 //     lane piece = fixed-Huffman block (BFINAL only on the last piece) [+ empty stored block = sync marker]
 //
 // The empty stored block (00 00 FF FF after bit padding, the Z_SYNC_FLUSH marker) re-aligns the stream to
-// a byte boundary, so the 128 pieces concatenate byte-wise (5 marker bytes per 510 payload bytes at worst).
+// a byte boundary, so the 256 pieces concatenate byte-wise (5 marker bytes per 255 payload bytes at worst).
 // LZ77 matches use ONE distance: the row width (`dist` bytes) — consecutive bitmap rows repeat for as long as no genome's k-mer membership changes, so
 // "same as the previous row" is where the redundancy of this data is; a member whose pieces do not beat
 // the raw size is emitted as a single stored block instead.
@@ -29,11 +29,12 @@
 #endif
 
 #define PKZ_PAYLOAD 0xFF00u                   // payload bytes per BGZF block (htslib BGZF_BLOCK_SIZE)
-#define PKZ_LANES 128u                        // pieces (threads) per BGZF block: the encoder is a sequential loop per
+#define PKZ_LANES 256u                        // pieces (threads) per BGZF block: the encoder is a sequential loop per
                                               // piece, so its run time is the latency of ONE piece (32 pieces of 2040
-                                              // bytes: 2.0 ms for 135 MB on B200, measured; profiles/r1e_launches.csv)
-#define PKZ_SUB (PKZ_PAYLOAD / PKZ_LANES)     // 510 bytes per piece
-#define PKZ_STAGE 592u                        // staging bytes per piece: 510 * 9/8 + 10 bits + 5 + slack; multiple of 16
+                                              // bytes: 2.0 ms for 135 MB on B200, 128 of 510: 1.37 ms; profiles/)
+#define PKZ_SUB (PKZ_PAYLOAD / PKZ_LANES)     // 255 bytes per piece
+#define PKZ_STAGE 304u                        // staging bytes per piece: 255 * 9/8 + 10 bits + 5 + slack; multiple of 16
+#define PKZ_PAD 16u                           // bytes readable past a payload (word-wise match compares over-read <= 3)
 #define PKZ_MAX_MATCH 258u
 #define PKZ_MIN_MATCH 3u
 #define PKZ_HDR 18u                           // gzip header with the BC extra field
@@ -113,29 +114,66 @@ PKZ_FN PkzDist pkz_dist(uint32_t d) {
     return r;
 }
 
-// Deflate bytes [s, e) of the member payload `blk` (history = blk[0, s)) into `out` as one byte-aligned
-// piece. Returns the piece length (<= PKZ_STAGE for e - s <= PKZ_SUB).
-PKZ_FN uint32_t pkz_encode_piece(const uint8_t *blk, uint32_t s, uint32_t e, uint32_t dist, bool final, uint8_t *out) {
+// bytes p[0..3] as a little-endian word, p unaligned (device: two aligned loads + a funnel shift; at most 3 bytes
+// past p + 3 are touched, never used)
+PKZ_FN uint32_t pkz_ld32u(const uint8_t *p) {
+#ifdef __CUDA_ARCH__
+    const uint32_t sh = ((uint32_t)(uintptr_t)p & 3u) * 8u;
+    const uint32_t *q = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    return sh ? __funnelshift_r(q[0], q[1], sh) : q[0];
+#else
+    uint32_t v;
+    __builtin_memcpy(&v, p, 4);
+    return v;
+#endif
+}
+PKZ_FN uint32_t pkz_ctz(uint32_t v) {         // v != 0
+#ifdef __CUDA_ARCH__
+    return __ffs((int)v) - 1;
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+// number of positions j < maxl with blk[i + j] == blk[i + j - dist], counted from j = 0 up to the first mismatch:
+// bytes until i + j is word-aligned, then four at a time
+PKZ_FN uint32_t pkz_match_len(const uint8_t *blk, uint32_t i, uint32_t dist, uint32_t maxl) {
+    uint32_t len = 0;
+    while (len < maxl && ((i + len) & 3u)) {
+        if (blk[i + len] != blk[i + len - dist]) return len;
+        len++;
+    }
+    while (len + 4 <= maxl) {
+        const uint32_t x = pkz_ld32u(blk + i + len) ^ pkz_ld32u(blk + i + len - dist);
+        if (x) return len + (pkz_ctz(x) >> 3);
+        len += 4;
+    }
+    while (len < maxl && blk[i + len] == blk[i + len - dist]) len++;
+    return len;
+}
+
+// Deflate bytes [s, e) of the member payload `blk` (history = blk[0, s); blk 4-byte aligned, PKZ_PAD bytes readable
+// past e) into `out` as one byte-aligned piece. lit[b] = fixed-Huffman code of literal b, bit-reversed, | length << 16.
+// Returns the piece length (<= PKZ_STAGE for e - s <= PKZ_SUB).
+PKZ_FN uint32_t pkz_encode_piece(const uint8_t *blk, uint32_t s, uint32_t e, uint32_t dist, bool final, uint8_t *out,
+                                 const uint32_t *lit) {
     PkzBits w;
     w.acc = 0; w.nbits = 0; w.pos = 0; w.out = out;
     const PkzDist dc = pkz_dist(dist);
-    const uint32_t dcode = pkz_rev(dc.code, 5);
+    // the distance code and its extra bits follow every length code: one put
+    const uint32_t dbits = pkz_rev(dc.code, 5) | (dc.eval << 5), dn = 5 + dc.ebits;
     pkz_put(w, final ? 1u : 0u, 1);
     pkz_put(w, 1, 2);                                        // BTYPE = 01: fixed Huffman
     uint32_t i = s;
     while (i < e) {
         uint32_t len = 0;
-        if (i >= dist) {
-            const uint32_t maxl = e - i < PKZ_MAX_MATCH ? e - i : PKZ_MAX_MATCH;
-            while (len < maxl && blk[i + len] == blk[i + len - dist]) len++;
-        }
+        if (i >= dist) len = pkz_match_len(blk, i, dist, e - i < PKZ_MAX_MATCH ? e - i : PKZ_MAX_MATCH);
         if (len >= PKZ_MIN_MATCH) {
             pkz_put_length(w, len);
-            pkz_put(w, dcode, 5);
-            if (dc.ebits) pkz_put(w, dc.eval, dc.ebits);
+            pkz_put(w, dbits, dn);
             i += len;
         } else {
-            pkz_put_litlen(w, blk[i]);
+            const uint32_t c = lit[blk[i]];
+            pkz_put(w, c & 0xffffu, c >> 16);
             i++;
         }
     }
@@ -152,12 +190,26 @@ PKZ_FN uint32_t pkz_encode_piece(const uint8_t *blk, uint32_t s, uint32_t e, uin
 }
 
 // ---- CRC-32 (gzip polynomial, reflected) -------------------------------------------------------------
-// tab: the 256-entry byte table. The update is linear in the state, so lane 0 starts from the CRC preset
-// (0xFFFFFFFF) and the others from 0; pkz_crc_shift moves a state over n following zero bytes with the
-// operators "append 2^j zero bytes" (32 x 32 bit matrices over GF(2), mats[j][bit]), and the XOR of the
-// shifted lane states, complemented, is the member's CRC.
+// tab: four 256-entry tables (slicing-by-4: tab[256 * j + b] = CRC state of byte b followed by j zero bytes), so four
+// input bytes cost four INDEPENDENT lookups instead of a chain of four dependent ones. The update is linear in the
+// state, so lane 0 starts from the CRC preset (0xFFFFFFFF) and the others from 0; pkz_crc_shift moves a state over
+// n following zero bytes with the operators "append 2^j zero bytes" (32 x 32 bit matrices over GF(2),
+// mats[j][bit]), and the XOR of the shifted lane states, complemented, is the member's CRC.
+#define PKZ_CRC_TAB_WORDS 1024
 PKZ_FN uint32_t pkz_crc_update(const uint32_t *tab, uint32_t crc, const uint8_t *p, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) crc = tab[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    uint32_t i = 0;
+    for (; i < n && ((uintptr_t)(p + i) & 3u); i++) crc = tab[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    for (; i + 4 <= n; i += 4) {
+        uint32_t wv;
+#ifdef __CUDA_ARCH__
+        wv = *(const uint32_t *)(p + i);
+#else
+        __builtin_memcpy(&wv, p + i, 4);
+#endif
+        crc ^= wv;
+        crc = tab[768 + (crc & 0xff)] ^ tab[512 + ((crc >> 8) & 0xff)] ^ tab[256 + ((crc >> 16) & 0xff)] ^ tab[crc >> 24];
+    }
+    for (; i < n; i++) crc = tab[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
     return crc;
 }
 PKZ_FN uint32_t pkz_gf2_times(const uint32_t *mat, uint32_t vec) {
@@ -172,12 +224,19 @@ PKZ_FN uint32_t pkz_crc_shift(const uint32_t *mats /*[PKZ_CRC_MATS][32]*/, uint3
     return crc;
 }
 
-// host-side construction of the two tables (uploaded once by pk_bgzf.cu)
-static inline void pkz_make_tables(uint32_t tab[256], uint32_t mats[PKZ_CRC_MATS * 32]) {
+// host-side construction of the tables (uploaded once by pk_bgzf.cu): tab[PKZ_CRC_TAB_WORDS], mats, lit[256]
+static inline void pkz_make_tables(uint32_t *tab, uint32_t mats[PKZ_CRC_MATS * 32], uint32_t lit[256]) {
     for (uint32_t n = 0; n < 256; n++) {
         uint32_t c = n;
         for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
         tab[n] = c;
+    }
+    for (uint32_t n = 0; n < 256; n++)
+        for (int j = 1; j < 4; j++) tab[256 * j + n] = tab[tab[256 * (j - 1) + n] & 0xff] ^ (tab[256 * (j - 1) + n] >> 8);
+    for (uint32_t b = 0; b < 256; b++) {
+        uint32_t code = b < 144 ? 0x30 + b : 0x190 + (b - 144), nb = b < 144 ? 8 : 9, r = 0;
+        for (uint32_t i = 0; i < nb; i++) r |= ((code >> i) & 1u) << (nb - 1 - i);
+        lit[b] = r | (nb << 16);
     }
     uint32_t a[32], b[32];
     a[0] = 0xEDB88320u;                                      // operator for one zero BIT

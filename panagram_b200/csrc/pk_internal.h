@@ -123,7 +123,7 @@ void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t 
                            uint32_t bit_mask, uint64_t n, uint32_t *d_out, pk_stream_t s);
 
 // ---- on-GPU BGZF writer (pk_bgzf.cu) ----
-#define PK_BGZF_TABLE_WORDS (256 + 17 * 32)      // CRC byte table + "append 2^j zero bytes" operators
+#define PK_BGZF_TABLE_WORDS (1024 + 17 * 32 + 256)      // CRC slicing-by-4 tables + "append 2^j zero bytes" operators + literal codes
 uint64_t pk_bgzf_blocks_impl(uint64_t n);
 uint64_t pk_bgzf_bound_impl(uint64_t n);
 uint64_t pk_bgzf_gzi_bound_impl(uint64_t n);

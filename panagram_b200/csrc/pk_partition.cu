@@ -1185,6 +1185,7 @@ static const K3WinVariant k3w_variants[] = {
 };
 #define PW_MAX_GROUP_STAGE_BYTES 32768u
 #define PW_GROUP_STAGE_TARGET 24576u          // pieces of a group-table window are at most this large
+#define PW_LEAN_MAX_STAGE 65536u              // the lean kernel's single stage: a whole window of up to this size
 int pk_part_n_wvariants(void) { return (int)(sizeof k3w_variants / sizeof k3w_variants[0]); }
 // auto: per-genome tables 6 blocks/SM (profiles/r1e_sweep.json: 5.14 vs 5.32 ms), group tables 4 blocks/SM with up to
 // 64 registers (profiles/r1l_sweep.json: 2.29 vs 3.62 ms — one 20 KB window per block, the probe loop is short and
@@ -1434,14 +1435,20 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
                 const uint32_t stage_bytes = (uint32_t)cb * 32, n_stages = np == 1 ? 1 : 2;
                 p.ng = np; p.tbits = PK_U_GROUP; p.chunk_buckets = nch > 1 ? (uint32_t)cb : 0;
                 const int fk = (nch > 1 ? 3 : 2) + (p.tabs[0].fmt == PK_TFMT_G32 ? 2 : 0);
-                if (fk == 4 && np == 1 && nt == 1 && p.compact && p.out_fine && sc.out_list && p.counts && tu.lean > 0 &&
-                    tu.lean <= pk_part_n_lvariants() && (uint32_t)k3l_variants[tu.lean - 1].cap == pl.cap2 && tu.rank_atomic == 1) {
+                // ONE 32-bit-slot table, compact items, fine bins: the lean kernel, which stages a partition's whole
+                // window at once — up to PW_LEAN_MAX_STAGE bytes (a half-genome batch of the end-to-end call has 2^16
+                // partitions and 40 KB windows: 4-5 blocks/SM still fit), where the general kernel would cut it in pieces
+                const uint64_t lean_stage = (maxw * 32 + 127) & ~127ull;
+                if (p.tabs[0].fmt == PK_TFMT_G32 && nt == 1 && lean_stage <= PW_LEAN_MAX_STAGE && p.compact && p.out_fine && sc.out_list &&
+                    p.counts && tu.lean > 0 && tu.lean <= pk_part_n_lvariants() && (uint32_t)k3l_variants[tu.lean - 1].cap == pl.cap2 &&
+                    tu.rank_atomic == 1) {
                     const K3LeanVariant &lv = k3l_variants[tu.lean - 1];
-                    cudaFuncSetAttribute(lv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PW_MAX_GROUP_STAGE_BYTES);
-                    lv.fn<<<p.n_regions, lv.threads, stage_bytes, s>>>(p, stage_bytes);
+                    cudaFuncSetAttribute(lv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PW_LEAN_MAX_STAGE);
+                    lv.fn<<<p.n_regions, lv.threads, (size_t)lean_stage, s>>>(p, (uint32_t)lean_stage);
                     last_window = 4;
                     continue;
                 }
+                (void)fk;
                 cudaFuncSetAttribute(wv.fn[fk], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PW_MAX_STAGES * PW_MAX_STAGE_BYTES));
                 wv.fn[fk]<<<p.n_regions, wv.threads, (size_t)n_stages * stage_bytes, s>>>(p, stage_bytes, 1, n_stages);
                 last_window = 2;

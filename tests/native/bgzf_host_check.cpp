@@ -19,11 +19,12 @@ int main(int argc, char **argv) {
     while ((r = fread(buf, 1, sizeof buf, f)) > 0) in.insert(in.end(), buf, buf + r);
     fclose(f);
     const uint32_t dist = (uint32_t)atoi(argv[4]);
-    static uint32_t tab[256], mats[PKZ_CRC_MATS * 32];
-    pkz_make_tables(tab, mats);
+    static uint32_t tab[PKZ_CRC_TAB_WORDS], mats[PKZ_CRC_MATS * 32], lit[256];
+    pkz_make_tables(tab, mats, lit);
     std::vector<uint8_t> out;
     std::vector<uint64_t> gzi;
     const uint64_t n = in.size();
+    in.resize(n + PKZ_PAD);              // the encoder's word-wise compares may read (never use) a few bytes past the end
     const uint64_t nblocks = (n + PKZ_PAYLOAD - 1) / PKZ_PAYLOAD;
     std::vector<uint8_t> stage(PKZ_LANES * PKZ_STAGE + 16);
     uint8_t *st = stage.data() + ((16 - ((uintptr_t)stage.data() & 15)) & 15);
@@ -35,7 +36,7 @@ int main(int argc, char **argv) {
             const uint32_t s = l * PKZ_SUB < blen ? l * PKZ_SUB : blen;
             const uint32_t e = (l + 1) * PKZ_SUB < blen ? (l + 1) * PKZ_SUB : blen;
             lens[l] = e - s;
-            sizes[l] = e > s ? pkz_encode_piece(blk, s, e, dist, e == blen, st + l * PKZ_STAGE) : 0;
+            sizes[l] = e > s ? pkz_encode_piece(blk, s, e, dist, e == blen, st + l * PKZ_STAGE, lit) : 0;
             if (sizes[l] > PKZ_STAGE) { fprintf(stderr, "piece overflow %u\n", sizes[l]); return 4; }
             total += sizes[l];
             crcs[l] = pkz_crc_update(tab, l == 0 ? 0xFFFFFFFFu : 0u, blk + s, e - s);

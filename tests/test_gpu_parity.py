@@ -250,6 +250,47 @@ def test_bgzf_compress_device_formats():
             assert len(raw) < n / 5, label
 
 
+@pytest.mark.parametrize("n_cols,row_stride", [(9, 2), (16, 2), (20, 4), (32, 4), (33, 8), (64, 8), (70, 16), (128, 16), (12, 4)])
+def test_reduce_device_wide_rows(n_cols, row_stride):
+    """pk_reduce_device on contiguous rows of 2..16 bytes (the vector kernel; the generic kernel where the bins are
+    short) against numpy: popcount histograms per bin, column sums, low-res rows; aligned and unaligned starts,
+    slices that begin in the middle of a bin, bits beyond n_cols set in the padding (must be ignored)."""
+    import torch
+    eng = Engine(21, 1)
+    eng.add_keys(0, np.array([1], dtype=np.uint64))
+    eng.finalize()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(n_cols * 100 + row_stride)
+    nbytes = (n_cols + 7) // 8
+    n_all = 700_001
+    base = rng.integers(0, 256, (n_all // 5, row_stride), dtype=np.uint8)
+    rows = np.repeat(base, rng.integers(1, 14, base.shape[0]), axis=0)[:n_all].copy()      # runs, like a real bitmap
+    assert rows.shape[0] == n_all
+    d_all = torch.from_numpy(rows).to(dev)
+    bits_all = np.unpackbits(rows, axis=1, bitorder="little")[:, :n_cols]
+    step = eng.lowres_step
+    for first_row, p_first, n, binlen in ((0, 0, n_all, 200_000), (3, 150_003, 400_000, 200_000), (1, 65_537, 250_001, 65_536),
+                                          (16, 1_000, 300_000, 1_000), (5, 7, 50, 200_000), (2, 99_999, 131_072, 100_000)):
+        r = rows[first_row:first_row + n]
+        bits = bits_all[first_row:first_row + n]
+        nb_total = (p_first + n + binlen - 1) // binlen
+        d_hist = torch.zeros(nb_total * (n_cols + 1), dtype=torch.int64, device=dev)
+        d_col = torch.zeros(n_cols, dtype=torch.int64, device=dev)
+        l0, l1 = (p_first + step - 1) // step, (p_first + n + step - 1) // step
+        d_low = torch.zeros((max(l1 - l0, 1), row_stride), dtype=torch.uint8, device=dev)
+        eng.reduce_device(d_all.data_ptr() + first_row * row_stride, row_stride, n_cols, p_first, n, binlen,
+                          d_hist.data_ptr(), d_col.data_ptr(), d_low.data_ptr(), st)
+        torch.cuda.synchronize()
+        pc = bits.sum(axis=1).astype(np.int64)
+        want = np.bincount(((p_first + np.arange(n, dtype=np.int64)) // binlen) * (n_cols + 1) + pc, minlength=nb_total * (n_cols + 1))
+        assert (d_hist.cpu().numpy() == want).all(), (first_row, p_first, n, binlen)
+        assert (d_col.cpu().numpy() == bits.sum(axis=0)).all(), (first_row, p_first, n, binlen)
+        low_idx = np.arange(l0, l1) * step - p_first
+        assert (d_low.cpu().numpy()[: l1 - l0, :nbytes] == r[low_idx][:, :nbytes]).all(), (first_row, p_first, n, binlen)
+    eng.close()
+
+
 def test_device_level_sharded_gather_equals_single_engine():
     """Two genome shards on one GPU stand in for two ranks: per-shard rows, gathered as planes,
     interleaved, reduced == one engine holding all 16 genomes."""
