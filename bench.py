@@ -389,6 +389,7 @@ def main():
     ap.add_argument("--group-tables", type=int, default=1, help="0: per-genome tables only (one probe per genome and position)")
     ap.add_argument("--group-only", type=int, default=1, help="free the per-genome tables once their group table is built")
     ap.add_argument("--e2e-batches", type=int, default=0, help="override the engine's batches per pk_anchor_genome call (0 = default)")
+    ap.add_argument("--tune", default="", help="engine knobs for experiments, e.g. e2e_front_small=1,k3_lean=0")
     ap.add_argument("--genome-ranks", type=int, default=0, help="ranks per genome group (0 = auto)")
     ap.add_argument("--exchange", default="slice", choices=["slice", "nccl"],
                     help="Rg>1: position-split peer-memory exchange (every rank assembles its slice of the rows) or "
@@ -474,6 +475,8 @@ def main():
     eng.finalize()
     if args.e2e_batches:
         eng.tune(e2e_batches=args.e2e_batches)
+    if args.tune:
+        eng.tune(**{kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune.split(",") if kv})
     tstats = [eng.table_stats(g) for g in range(g_begin, g_end)]
     gstats = [eng.group_stats(u) for u in range((npg + 7) // 8)]
     setup_s = time.perf_counter() - t0
@@ -685,7 +688,8 @@ def main():
         traffic, traffic_src, ncu_ms = None, "not measured (--no-ncu)", None
         if world == 1 and k3_ms and not args.no_ncu:
             child = ["--workload", args.workload, "--load-factor", str(args.load_factor), "--probe-mode", args.probe_mode,
-                     "--group-tables", str(args.group_tables), "--group-only", str(args.group_only), "--no-cpu-baseline", "--no-ncu", "--no-e2e"]
+                     "--group-tables", str(args.group_tables), "--group-only", str(args.group_only), "--no-cpu-baseline", "--no-ncu", "--no-e2e"] + \
+                    (["--tune", args.tune] if args.tune else [])
             # the child builds the same tables beside ours: only when this GPU has the room. It runs two steps; the
             # capture is the probe kernel of the second (the spill drain reuses probe_part / items_group: skipped)
             free_b, total_b = torch.cuda.mem_get_info()

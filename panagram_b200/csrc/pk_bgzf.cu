@@ -20,12 +20,13 @@ struct PkzMeta { uint32_t cdata, crc, isize, stored; };
 // 1.07 ms for 135 MB, ~1100 cycles per byte per thread (profiles/r1h_launches.csv).
 __global__ void __launch_bounds__(PKZ_LANES) bgzf_encode_kernel(const uint8_t *__restrict__ in, uint64_t n, uint32_t dist,
                                                                 uint8_t *__restrict__ stage, uint16_t *__restrict__ piece_sizes,
-                                                                PkzMeta *__restrict__ meta, const uint32_t *__restrict__ g_tables) {
+                                                                PkzMeta *__restrict__ meta, const uint32_t *__restrict__ g_tables,
+                                                                const uint64_t m0) {
     extern __shared__ __align__(16) uint8_t s_blk[];           // [PKZ_PAYLOAD + PKZ_PAD]
     __shared__ uint32_t s_tab[PKZ_CRC_TAB_WORDS + PKZ_CRC_MATS * 32 + 256];
     __shared__ uint32_t s_crc[PKZ_LANES / 32], s_size[PKZ_LANES / 32];
     const uint32_t l = threadIdx.x;
-    const uint64_t b = blockIdx.x;
+    const uint64_t b = m0 + blockIdx.x;                        // member of the stream
     const uint8_t *blk = in + b * PKZ_PAYLOAD;
     const uint32_t blen = (uint32_t)(n - b * PKZ_PAYLOAD < PKZ_PAYLOAD ? n - b * PKZ_PAYLOAD : PKZ_PAYLOAD);
     for (uint32_t i = l; i < PKZ_CRC_TAB_WORDS + PKZ_CRC_MATS * 32 + 256; i += PKZ_LANES) s_tab[i] = g_tables[i];
@@ -167,20 +168,40 @@ void pk_bgzf_tables_host(uint32_t *dst /*[PK_BGZF_TABLE_WORDS]*/) {
 }
 
 // d_tables: PK_BGZF_TABLE_WORDS uint32 on the device; d_scratch: pk_bgzf_scratch_bytes(n) bytes.
-void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_out, unsigned long long *d_gzi,
-                    unsigned long long *d_totals, uint8_t *d_scratch, const uint32_t *d_tables, pk_stream_t s) {
-    const uint64_t nb = pk_bgzf_blocks_impl(n);
+struct BgzfScratch { uint8_t *stage; unsigned long long *coff; PkzMeta *meta; uint16_t *piece_sizes; };
+static BgzfScratch bgzf_scratch(uint8_t *d_scratch, uint64_t nb) {
+    BgzfScratch r;
     uint8_t *p = d_scratch;
-    uint8_t *stage = p; p += (nb * PKZ_LANES * PKZ_STAGE + 255) & ~255ull;
-    unsigned long long *coff = (unsigned long long *)p; p += (nb * 8 + 255) & ~255ull;
-    PkzMeta *meta = (PkzMeta *)p; p += (nb * sizeof(PkzMeta) + 255) & ~255ull;
-    uint16_t *piece_sizes = (uint16_t *)p;
+    r.stage = p; p += (nb * PKZ_LANES * PKZ_STAGE + 255) & ~255ull;
+    r.coff = (unsigned long long *)p; p += (nb * 8 + 255) & ~255ull;
+    r.meta = (PkzMeta *)p; p += (nb * sizeof(PkzMeta) + 255) & ~255ull;
+    r.piece_sizes = (uint16_t *)p;
+    return r;
+}
+// members [m0, m1) of the n-byte stream: deflate + CRC into the scratch. The bytes of those members must be final;
+// ranges may be encoded in any order and on any stream, pk_launch_bgzf_finish must be ordered after all of them.
+void pk_launch_bgzf_encode(const uint8_t *d_in, uint64_t n, uint32_t dist, uint64_t m0, uint64_t m1, uint8_t *d_scratch,
+                           const uint32_t *d_tables, pk_stream_t s) {
+    const uint64_t nb = pk_bgzf_blocks_impl(n);
+    if (m1 > nb) m1 = nb;
+    if (m1 <= m0) return;
+    const BgzfScratch sc = bgzf_scratch(d_scratch, nb);
     if (dist < 1) dist = 1;
     if (dist > 32768) dist = 32768;
-    if (nb) {
-        cudaFuncSetAttribute(bgzf_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PKZ_PAYLOAD + PKZ_PAD));
-        bgzf_encode_kernel<<<(unsigned)nb, PKZ_LANES, PKZ_PAYLOAD + PKZ_PAD, s>>>(d_in, n, dist, stage, piece_sizes, meta, d_tables);
-    }
-    bgzf_scan_kernel<<<1, 1024, 0, s>>>(meta, nb, coff, d_gzi, d_totals, d_out);
-    if (nb) bgzf_assemble_kernel<<<(unsigned)nb, 256, 0, s>>>(d_in, n, stage, piece_sizes, meta, coff, d_out);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(bgzf_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PKZ_PAYLOAD + PKZ_PAD)); attr_set = true; }
+    bgzf_encode_kernel<<<(unsigned)(m1 - m0), PKZ_LANES, PKZ_PAYLOAD + PKZ_PAD, s>>>(d_in, n, dist, sc.stage, sc.piece_sizes, sc.meta, d_tables, m0);
+}
+// member offsets, the .gzi image, totals, and the members laid out contiguously in d_out
+void pk_launch_bgzf_finish(const uint8_t *d_in, uint64_t n, uint8_t *d_out, unsigned long long *d_gzi, unsigned long long *d_totals,
+                           uint8_t *d_scratch, pk_stream_t s) {
+    const uint64_t nb = pk_bgzf_blocks_impl(n);
+    const BgzfScratch sc = bgzf_scratch(d_scratch, nb);
+    bgzf_scan_kernel<<<1, 1024, 0, s>>>(sc.meta, nb, sc.coff, d_gzi, d_totals, d_out);
+    if (nb) bgzf_assemble_kernel<<<(unsigned)nb, 256, 0, s>>>(d_in, n, sc.stage, sc.piece_sizes, sc.meta, sc.coff, d_out);
+}
+void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_out, unsigned long long *d_gzi,
+                    unsigned long long *d_totals, uint8_t *d_scratch, const uint32_t *d_tables, pk_stream_t s) {
+    pk_launch_bgzf_encode(d_in, n, dist, 0, pk_bgzf_blocks_impl(n), d_scratch, d_tables, s);
+    pk_launch_bgzf_finish(d_in, n, d_out, d_gzi, d_totals, d_scratch, s);
 }

@@ -78,6 +78,7 @@ struct pk_engine {
     int e2e_batches = 2;                        // batches of whole chromosomes per pk_anchor_genome call (copy/compute overlap)
     uint64_t e2e_batch_min = 32ull << 20;       // ... for genomes of at least this many positions
     int e2e_batch_force = 0;                    // set by an explicit "e2e_batches" knob: skip the table-size rule
+    int e2e_front_small = 0;                    // even splits: the straddling chromosome goes to the later batch
     bool pev_valid = false;
     PkPartTune tune{};                          // tuning state of the partitioned probe (pk_engine_tune / PK_K3* environment)
     PkPartScratch sc{};                         // partitioned-probe scratch (grow-only)
@@ -1086,7 +1087,10 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
             const uint64_t target = ltot * (b + 1) / nb;
             Batch bt{};
             bt.c0 = c;
-            while (c < n_chroms && (b + 1 == nb || c == bt.c0 || off[c] + lens[c] / 2 <= target)) c++;
+            // ... e2e_front_small: a chromosome that straddles the target goes to the LATER batch unless 3/4 of it lie before
+            // the target (the first batch's H2D is exposed in full, the later batches' copies run under kernels)
+            while (c < n_chroms && (b + 1 == nb || c == bt.c0 ||
+                                    off[c] + (e->e2e_front_small ? lens[c] - lens[c] / 4 : lens[c] / 2) <= target)) c++;
             bt.c1 = c;
             bt.base = off[bt.c0];
             const uint64_t end = (bt.c1 < n_chroms ? off[bt.c1] : ltot);
@@ -1113,6 +1117,7 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
         rc = ensure_scratch(e, mx); if (rc) return rc;
     }
     bool first = true;
+    uint64_t z_rows_done = 0, z_members_done = 0;       // BGZF mode: rows in the output stream so far, members deflated so far
     for (const Batch &bt : batches) {
         const PkPartPlan &pl = bt.pl;
         uint8_t *rows_b = rows_all + bt.base * rs;
@@ -1160,32 +1165,41 @@ static int anchor_genome_impl(pk_engine *e, uint32_t n_chroms, const char *const
                                  col_sums ? e->d_colsums : nullptr, want_low ? low_c : nullptr, step, s);
                 e->stats.kernel_launches += 1 + (want_low ? 1 : 0);
             }
+            if (z) {     // one stream per anchor, chromosomes back to back (cpp/anchor.cpp:167: bgzf_write appends chunk after chunk)
+                CU(cudaMemcpyAsync(e->z_cat + z_rows_done * rb, rows_c, nk[c] * rb, cudaMemcpyDeviceToDevice, s));
+                z_rows_done += nk[c];
+            }
             CU(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
             CU(cudaEventRecord(done[c], s));
             CU(cudaStreamWaitEvent(cs, done[c], 0));
             if (bitmap1 && bitmap1[c]) CU(cudaMemcpyAsync(bitmap1[c], rows_c, nk[c] * rb, cudaMemcpyDeviceToHost, cs));
             if (bitmap_low && bitmap_low[c]) CU(cudaMemcpyAsync(bitmap_low[c], low_c, ((nk[c] + step - 1) / step) * rb, cudaMemcpyDeviceToHost, cs));
         }
+        if (z && !plane) {
+            // the BGZF members this batch completed are deflated on the copy stream (idle in this mode: the rows stay on
+            // the device) while the next batch is partitioned and probed on the compute stream
+            const bool last = &bt == &batches.back();
+            const uint64_t m1 = last ? pk_bgzf_blocks_impl(postot * rb) : z_rows_done * rb / PK_BGZF_PAYLOAD;
+            if (m1 > z_members_done) {
+                pk_launch_bgzf_encode(e->z_cat, postot * rb, rb, z_members_done, m1, e->z_scratch, e->z_tables, cs);
+                e->stats.kernel_launches += 1;
+                z_members_done = m1;
+            }
+        }
     }
     if (z) {
-        // one stream per anchor, chromosomes back to back (cpp/anchor.cpp:167: bgzf_write appends chunk after chunk)
-        uint64_t so = 0;
-        for (uint32_t c = 0; c < n_chroms; c++) {
-            if (!nk[c]) continue;
-            CU(cudaMemcpyAsync(e->z_cat + so * rb, e->g_rows + off[c] * rb, nk[c] * rb, cudaMemcpyDeviceToDevice, s));
-            so += nk[c];
-        }
-        pk_launch_bgzf(e->z_cat, postot * rb, rb, e->z_gz[0], e->z_gzi[0], e->z_totals, e->z_scratch, e->z_tables, s);
-        pk_launch_bgzf(e->g_low, lowtot * rb, rb, e->z_gz[1], e->z_gzi[1], e->z_totals + 2, e->z_scratch, e->z_tables, s);
-        e->stats.kernel_launches += 6;
+        // cs is ordered after every chromosome's rows, low-res rows and reductions (done[c])
+        pk_launch_bgzf_finish(e->z_cat, postot * rb, e->z_gz[0], e->z_gzi[0], e->z_totals, e->z_scratch, cs);
+        pk_launch_bgzf(e->g_low, lowtot * rb, rb, e->z_gz[1], e->z_gzi[1], e->z_totals + 2, e->z_scratch, e->z_tables, cs);
+        e->stats.kernel_launches += 5;
         CU(cudaGetLastError());
         unsigned long long tot[4];
-        CU(cudaMemcpyAsync(tot, e->z_totals, sizeof tot, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        CU(cudaMemcpyAsync(tot, e->z_totals, sizeof tot, cudaMemcpyDeviceToHost, cs));
+        CU(cudaStreamSynchronize(cs));
         for (int i = 0; i < 2; i++) {
             if (tot[2 * i] > z->gz_cap[i] || tot[2 * i + 1] > z->gzi_cap[i]) { pk_set_error("BGZF image larger than its bound (internal error)"); return PK_ECUDA; }
-            CU(cudaMemcpyAsync(z->gz[i], e->z_gz[i], tot[2 * i], cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(z->gzi[i], e->z_gzi[i], tot[2 * i + 1], cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(z->gz[i], e->z_gz[i], tot[2 * i], cudaMemcpyDeviceToHost, cs));
+            CU(cudaMemcpyAsync(z->gzi[i], e->z_gzi[i], tot[2 * i + 1], cudaMemcpyDeviceToHost, cs));
             z->sizes[2 * i] = tot[2 * i]; z->sizes[2 * i + 1] = tot[2 * i + 1];
         }
     }
@@ -1376,6 +1390,7 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
         e->group_only = value ? 1 : 0;
         return PK_OK;
     }
+    else if (n == "e2e_front_small") { e->e2e_front_small = value ? 1 : 0; return PK_OK; }
     else if (n == "e2e_batch_min") { e->e2e_batch_min = value < 0 ? 0 : (uint64_t)value; return PK_OK; }
     else if (n == "e2e_batches") { if (value < 1 || value > 8) { pk_set_error("e2e_batches %d out of 1..8", value); return PK_EINVAL; } e->e2e_batches = value; e->e2e_batch_force = 1; return PK_OK; }
     else if (n == "unpermute") {

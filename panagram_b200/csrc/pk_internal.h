@@ -124,11 +124,16 @@ void pk_launch_rows_to_u32(const uint8_t *d_rows, uint32_t row_stride, uint32_t 
 
 // ---- on-GPU BGZF writer (pk_bgzf.cu) ----
 #define PK_BGZF_TABLE_WORDS (1024 + 17 * 32 + 256)      // CRC slicing-by-4 tables + "append 2^j zero bytes" operators + literal codes
+#define PK_BGZF_PAYLOAD 0xFF00ull              // payload bytes per BGZF member (PKZ_PAYLOAD)
 uint64_t pk_bgzf_blocks_impl(uint64_t n);
 uint64_t pk_bgzf_bound_impl(uint64_t n);
 uint64_t pk_bgzf_gzi_bound_impl(uint64_t n);
 uint64_t pk_bgzf_scratch_bytes(uint64_t n);
 void pk_bgzf_tables_host(uint32_t *dst /*[PK_BGZF_TABLE_WORDS]*/);
+void pk_launch_bgzf_encode(const uint8_t *d_in, uint64_t n, uint32_t dist, uint64_t m0, uint64_t m1, uint8_t *d_scratch,
+                           const uint32_t *d_tables, pk_stream_t s);
+void pk_launch_bgzf_finish(const uint8_t *d_in, uint64_t n, uint8_t *d_out, unsigned long long *d_gzi, unsigned long long *d_totals,
+                           uint8_t *d_scratch, pk_stream_t s);
 void pk_launch_bgzf(const uint8_t *d_in, uint64_t n, uint32_t dist, uint8_t *d_out, unsigned long long *d_gzi,
                     unsigned long long *d_totals, uint8_t *d_scratch, const uint32_t *d_tables, pk_stream_t s);
 

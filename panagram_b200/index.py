@@ -139,7 +139,9 @@ class Index:
             u0 = eng.genome_begin + gl // 8 * 8
             if kind != "bitvec" and all(g in filled for g in range(u0, min(u0 + 8, eng.genome_end))):
                 eng.seal_group(gl // 8)
+        t0 = time.perf_counter()
         eng.finalize()
+        log(f"group tables complete ({time.perf_counter() - t0:.2f}s)")
         return eng
 
     def _engine_kw(self) -> dict:
@@ -147,7 +149,9 @@ class Index:
                     min_bin_count=self.cfg.min_bin_count, load_factor=self.load_factor)
 
     def build_engine(self, genome_begin: int = 0, genome_end: int | None = None, log=print) -> Engine:
+        t0 = time.perf_counter()
         eng = Engine(self.cfg.k, len(self.samples), genome_begin, genome_end, device=self.device, **self._engine_kw())
+        log(f"engine on cuda:{self.device} ({time.perf_counter() - t0:.2f}s)")
         return self.populate(eng, log)
 
     def write_genome_dist(self, records, frac: float, log=print):
@@ -191,7 +195,9 @@ class Index:
             eng = self.build_engine(log=log)
             total = sum((eng.group_stats(u) or {"n_keys": 0})["n_keys"] for u in range((eng.n_local + 7) // 8))
             frac = min(1.0, self.DIST_SAMPLE_TARGET / max(total, 1))
+            t0 = time.perf_counter()
             keys, tags = eng.sample_kmers(frac)
+            log(f"k-mer sample for genome_dist.tsv: {keys.size} k-mers ({time.perf_counter() - t0:.2f}s)")
             self.write_genome_dist([(keys, tags, 0)], frac, log)
             for s in anchors:
                 t0 = time.perf_counter()
