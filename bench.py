@@ -678,12 +678,13 @@ def main():
         pos1 = sum(packed[-1]["nks"]) if packed else 0
         n_group_tabs = (npg + 7) // 8
         win = int(ks.get("k_probe_window", 0))
-        alg_design = pos1 * ((n_group_tabs if win in (2, 3, 4) else npg) * 32 + 0.375 + rb_local * 1.01)
+        alg_design = pos1 * ((n_group_tabs if win in (2, 3, 4, 5) else npg) * 32 + 0.375 + rb_local * 1.01)
         alg_survey = pos1 * (npg * 32 + 0.375 + rb_local * 1.01)
         k3_ms = ks["k_probe_ms"] if ks["k_probe_ms"] > 0 else None
         stage1_ms = sum(ks[x] for x in ("k_partition_ms", "k_fine_ms", "k_probe_ms", "k_spill_ms", "k_unpermute_ms"))
         kernel_name = {2: "probe_win_kernel<group tables>", 1: "probe_win_kernel", 3: "items_group_kernel",
-                       4: "probe_g32c_kernel (lean window kernel, one 32-bit-slot group table)"}.get(win, "probe_part_kernel") \
+                       4: "probe_g32c_kernel (lean window kernel, one 32-bit-slot group table)",
+                       5: "probe_g32l2_kernel (coarse regions through L2, no K2)"}.get(win, "probe_part_kernel") \
             if k3_ms else "probe_kernel (direct)"
         traffic, traffic_src, ncu_ms = None, "not measured (--no-ncu)", None
         if world == 1 and k3_ms and not args.no_ncu:
@@ -694,7 +695,7 @@ def main():
             # capture is the probe kernel of the second (the spill drain reuses probe_part / items_group: skipped)
             free_b, total_b = torch.cuda.mem_get_info()
             if free_b > (total_b - free_b) + (16 << 30):
-                rx, skip = {2: ("probe_win_kernel", 1), 1: ("probe_win_kernel", 1), 3: ("items_group_kernel", 2), 4: ("probe_g32c_kernel", 1)}.get(win, ("probe_part_kernel", 2))
+                rx, skip = {2: ("probe_win_kernel", 1), 1: ("probe_win_kernel", 1), 3: ("items_group_kernel", 2), 4: ("probe_g32c_kernel", 1), 5: ("probe_g32l2_kernel", 1)}.get(win, ("probe_part_kernel", 2))
                 m, traffic_src = ncu_traffic(child, rx, skip)
             else:
                 m, traffic_src = None, "not measured: no room for the ncu child's tables beside ours"
@@ -705,7 +706,7 @@ def main():
         roof = {"bound": "hbm", "kernel": kernel_name, "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src,
                 "kernel_ms": k3_ms, "launch": f"one anchor ({pos1} positions) against {npg} genomes' tables on one GPU",
                 "algorithmic": "design: one 32 B sector per position and 8-genome group table + 0.375 B/position of packed "
-                               "sequence + 1.01 x row bytes written" if win in (2, 3, 4) else
+                               "sequence + 1.01 x row bytes written" if win in (2, 3, 4, 5) else
                                "SURVEY §8d: one 32 B sector per (position, genome) + 0.375 B/position + 1.01 x row bytes",
                 "algorithmic_bytes_per_launch": alg_design, "achieved": alg_design / t_k3 / 1e9,
                 "frac": alg_design / t_k3 / 1e9 / hbm_peak,

@@ -1,15 +1,3 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "bgzf or anchor_dir or k3_tuning or pinned or cli or edge_cases or sharded_anchorer_world1" > gpurun_out/r2ac_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2ac_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2ac_smoke.log 2>&1; echo "smoke rc=$?"
-timeout 600 python bench.py --no-cpu-baseline --no-ncu > gpurun_out/r2ac_bench_configs1.json 2> gpurun_out/r2ac_bench_configs1.err
-for i in 1 2; do timeout 600 python bench.py --index-e2e configs1 --no-cpu-baseline > gpurun_out/r2ac_index_configs1_$i.json 2> gpurun_out/r2ac_index_$i.err; done
-python - <<'P'
-import json
-for l in open('gpurun_out/r2ac_bench_configs1.json'):
-    if l.startswith('{'):
-        d=json.loads(l); print('ms',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'],'files',d['e2e_files']['ms_per_step'])
-for i in (1,2):
-    for l in open('gpurun_out/r2ac_index_configs1_%d.json'%i):
-        if l.startswith('{'):
-            d=json.loads(l); print('index',d['total_s'],d['log'])
-P
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "k3_tuning" > gpurun_out/r2af_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2af_pytest.log
+timeout 600 python bench/k3_sweep.py --workload configs1 --steps 5 --out gpurun_out/r2af_sweep_k3_l2_direct.json k3_l2=7 k3_l2=9 k3_l2=10 k3_l2=11 k3_l2=12 k3_l2=13 k3_l2=14 k3_l2=7 > gpurun_out/r2af_sweep.log 2>&1; tail -9 gpurun_out/r2af_sweep.log

@@ -328,7 +328,7 @@ typedef struct pk_stats {
      * they ran on: K1 partition_seq, K2 partition_fine, K3 probe_part, K3 over the spill list,
      * K4 unpermute */
     float k_partition_ms, k_fine_ms, k_probe_ms, k_spill_ms, k_unpermute_ms;
-    float k_probe_window;    /* K3 of the last launch: 4 probe_g32c_kernel (lean form, one 32-bit-slot group table), 2 probe_win_kernel on group tables, 1 on per-genome tables, 3 items_group_kernel, 0 probe_part_kernel */
+    float k_probe_window;    /* K3 of the last launch: 5 probe_g32l2_kernel (coarse regions through L2, no K2), 4 probe_g32c_kernel (lean form, one 32-bit-slot group table), 2 probe_win_kernel on group tables, 1 on per-genome tables, 3 items_group_kernel, 0 probe_part_kernel */
     uint64_t positions, probes, probe_launches, kernel_launches;
 } pk_stats;
 int pk_engine_stats(const pk_engine *e, pk_stats *out);

@@ -1369,6 +1369,7 @@ extern "C" int pk_engine_tune(pk_engine *e, const char *name, int value) {
     else if (n == "k3w_big") { e->tune.wbig = value; return PK_OK; }
     else if (n == "compact_items") { e->tune.compact = value ? 1 : 0; return PK_OK; }
     else if (n == "k3_lean") { if (value >= 0 && value <= pk_part_n_lvariants()) e->tune.lean = value; return PK_OK; }
+    else if (n == "k3_l2") { if (value >= 0 && value <= pk_part_n_gvariants()) e->tune.k3_l2 = value; return PK_OK; }
     else if (n == "k1_roll") { e->tune.k1_roll = value ? 1 : 0; return PK_OK; }
     else if (n == "fine_out") { e->tune.fine_out = value ? 1 : 0; return PK_OK; }
     else if (n == "fine_shift") { e->tune.fine_shift = value < 0 ? 0 : value > 24 ? 24 : value; return PK_OK; }

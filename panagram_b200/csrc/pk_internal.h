@@ -162,10 +162,12 @@ struct PkPartTune {
     int wbig = 6;           // window-kernel variant for one-byte rows out of 32-bit-slot group tables (>= 4: the large-block variants)
     int compact = 1;        // compact items on the one-byte-row / 32-bit-slot path (K3 does not read the sequence)
     int lean = 1;           // K3 on ONE 32-bit-slot group table with compact items and fine bins: the lean kernel, variant lean - 1 (0: the general window kernel)
+    int k3_l2 = 7;          // > 0: no K2; K3 probes the coarse regions through L2 (probe_g32l2_kernel variant k3_l2 - 1) where one
+                            // 32-bit-slot group table, compact items and fine bins allow it; 0: K2 + the window kernels
     int k1_roll = 1;        // K1: rolling k-mers over 16 consecutive positions per thread (0: re-extract every window)
     int fine_shift = 0;     // fine mode: log2 of the positions per bin, 0 = the smallest that gives <= 512 bins
     int fine_out = 1;       // one-byte rows out of group tables: fine position bins + shared-memory-slice un-permute
-    int last_window = 0;    // K3 of the last launch: 2 window kernel on group tables, 1 on per-genome tables, 3 L1/L2 on group tables, 4 lean window kernel on one 32-bit-slot group table, 0 L1/L2 kernel
+    int last_window = 0;    // K3 of the last launch: 2 window kernel on group tables, 1 on per-genome tables, 3 L1/L2 on group tables, 4 lean window kernel on one 32-bit-slot group table, 5 coarse regions through L2 (no K2), 0 L1/L2 kernel
 };
 struct PkPartScratch {
     const PkPartTune *tune;                         // never NULL on the engine's paths
@@ -183,6 +185,7 @@ uint32_t pk_part_ocursor_words(void);
 int pk_part_n_variants(void);
 int pk_part_n_wvariants(void);
 int pk_part_n_lvariants(void);
+int pk_part_n_gvariants(void);
 // fine_out: 0 no, 1 one-byte rows out of group tables (fine bins + slice un-permute), 2 ... with 32-bit slots (larger K3 blocks)
 void pk_part_plan(uint64_t n, const PkPartTune &tune, PkPartPlan *pl, uint32_t n_local = 1, int fine_out = 0, uint32_t k = 0);
 uint32_t pk_part_max_fine_bins(void);

@@ -1130,6 +1130,91 @@ __global__ void __launch_bounds__(T, MINB) probe_g32c_kernel(const __grid_consta
         __syncthreads();            // the window, the counters and o_gb are free again
     }
 }
+// K3 straight out of the COARSE regions — no K2, no shared-memory windows (tune "k3_l2"; the default for one
+// 32-bit-slot group table with compact items and fine bins). The 2^9 coarse regions are processed in order, a few
+// hundred blocks per region, so at any time the blocks in flight probe three or four coarse windows of the table
+// (5 MB each on configs[1]): they stay L2-resident and every probe is one LDG.E.256 that hits L2 (or brings its
+// sector in: the table is read from DRAM once, and only the sectors some probe needs). Same items, ranks, reservations
+// and result lists as probe_g32c_kernel; a block takes T * IPT consecutive items of its region whatever the plan's
+// fine capacity is, so larger blocks mean longer runs per position bin (fewer reservations, fuller store sectors).
+// Measured on configs[1] (profiles/r2ad_sweep_k3_l2_prefetch.json): K2 0.52 + K3 1.18 -> K3 1.14 ms, stage 2.69 ->
+// 2.12 ms; asking the TMA unit to prefetch the window of the region 1..5 ahead into L2 (cp.async.bulk.prefetch.L2)
+// changed nothing (1.15-1.17 ms) and was dropped.
+// Block shape (profiles/r2ae_sweep_k3_l2_variants.json): occupancy beats run length — 256 threads x 4 items at 8 blocks/SM
+// (64 warps, <= 32 registers) 1.04 ms, 384 x 4 at 4 blocks/SM 1.14, 512 x 8 1.30, 1024 x 4 1.59. Taking the slots
+// directly with one global atomicAdd per item instead of ranking inside the block: 3.78 ms (135 M atomics on ~500
+// addresses; profiles/r2af_sweep_k3_l2_direct_atomics.json) — dropped.
+template <int T, int IPT, int MINB>
+__global__ void __launch_bounds__(T, MINB) probe_g32l2_kernel(const __grid_constant__ ProbeArgs a) {
+    static_assert(2 * T >= PP_FBINS, "two rounds of the block cover the fine bins");
+    constexpr uint32_t CAP = T * IPT;
+    __shared__ uint32_t o_cnt[PP_FBINS], o_gb[PP_FBINS];
+    const uint32_t tid = threadIdx.x, r = blockIdx.y;
+    const PkTable t = a.tabs[0];
+    const uint32_t nb = t.n_buckets, sh = a.out_shift, lowmask = (1u << sh) - 1;
+    const uint32_t ngg = min(PK_U_GROUP, a.n_genomes);
+    uint32_t *list4 = (uint32_t *)a.out_list;
+    const uint32_t cnt_r = min(a.counts[r], a.cap);
+    const uint32_t base = blockIdx.x * CAP;
+    if (base >= cnt_r) return;
+    const uint32_t cnt = min(CAP, cnt_r - base);
+    const uint2 *src = a.buf + (uint64_t)r * a.cap + base;
+    uint2 it[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; j++) it[j] = tid + j * T < cnt ? src[tid + j * T] : make_uint2(0, 0);
+    for (uint32_t i = tid; i < a.n_bins; i += T) o_cnt[i] = 0;
+    __syncthreads();
+    uint32_t rk[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+        rk[j] = tid + j * T < cnt ? atomicAdd(&o_cnt[(it[j].y & PT_CI_POS_MASK) >> sh], 1u) : 0u;
+    // the probes' loads are issued before the ranks are complete: nothing below the barrier depends on them
+    const uint32_t h_top = r << (32 - a.pb);
+    uint32_t bits[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        bits[j] = 0;
+        if (tid + j * T < cnt) {
+            const uint32_t r20 = ((it[j].x & 0xFFFFu) << 4) | (it[j].y >> PT_CI_POS_BITS);
+            const uint32_t h = h_top | ((it[j].x >> 16) << (32 - a.eb)) | (pk_mix32(r20) >> a.eb);
+            const uint32_t key = r20 << PK_S32_DISP_BITS;
+            const u64x4 v = pk_ld_bucket(t.slots + 4ull * __umulhi(h, nb));
+            uint32_t m = pk_g32_bucket_mask(v, key);
+            if (m == 0 && (uint32_t)(v.d >> 32) != PK_EMPTY32)       // full home bucket without the key: walk on (rare)
+                m = pk_group_lookup(t, pk_canon_at(a.words, a.p0 + (it[j].y & PT_CI_POS_MASK), a.ks.k), h, a.g_first, ngg, a.ks);
+            bits[j] = m;
+        }
+    }
+    __syncthreads();
+    uint32_t gb0 = 0, gb1 = 0;
+    if (tid < a.n_bins) { const uint32_t c = o_cnt[tid]; if (c) gb0 = atomicAdd(&a.out_cursor[tid * PP_OCS], c); }
+    if (tid + T < a.n_bins) { const uint32_t c = o_cnt[tid + T]; if (c) gb1 = atomicAdd(&a.out_cursor[(tid + T) * PP_OCS], c); }
+    if (tid < a.n_bins) o_gb[tid] = gb0;
+    if (tid + T < a.n_bins) o_gb[tid + T] = gb1;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+        if (tid + j * T < cnt) {
+            const uint32_t pos = it[j].y & PT_CI_POS_MASK;
+            list4[(pos & ~lowmask) + o_gb[pos >> sh] + rk[j]] = ((pos & lowmask) << 8) | (bits[j] & 0xffu);
+        }
+}
+
+struct K3L2Variant { int threads, cap; void (*fn)(ProbeArgs); };
+#define K3G(T, IPT, MINB) {T, T * IPT, probe_g32l2_kernel<T, IPT, MINB>}
+static const K3L2Variant k3g_variants[] = {
+    K3G(384, 4, 4),         // 1 (tune.k3_l2 = index + 1)
+    K3G(512, 4, 3),         // 2: 2048 items per block
+    K3G(512, 8, 2),         // 3: 4096
+    K3G(256, 8, 4),         // 4: 2048, 8 items per thread
+    K3G(1024, 4, 1),        // 5: 4096, one block per SM
+    K3G(1024, 8, 1),        // 6: 8192
+    K3G(256, 4, 8),         // 7: 1024 items, 8 blocks/SM (<= 32 registers) — the default
+    K3G(512, 2, 4),         // 8: 1024 items, 2 per thread
+    K3G(256, 3, 8),         // 9: 768 items
+    K3G(256, 2, 8),         // 10: 512 items
+};
+int pk_part_n_gvariants(void) { return (int)(sizeof k3g_variants / sizeof k3g_variants[0]); }
 struct K3LeanVariant { int threads, cap; void (*fn)(ProbeArgs, uint32_t); };
 #define K3L(T, IPT, MINB, EARLY) {T, T * IPT, probe_g32c_kernel<T, IPT, MINB, EARLY>}
 static const K3LeanVariant k3l_variants[] = {
@@ -1380,7 +1465,10 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     int lw_dummy = 0;
     int &last_window = sc.last_window ? *sc.last_window : lw_dummy;
     PartArgs a = make_part_args(d_words, d_mask, p0, ks, n_local, d_rows, row_stride, col_offset, pl, sc);
-    if (pl.pb2) {
+    // tune "k3_l2" = variant + 1 (0: off): no K2, K3 probes the coarse regions through L2
+    const bool l2_path = tu.k3_l2 > 0 && pl.pb2 && a.compact && pl.out_fine && sc.out_list && h_utables && n_local <= PK_U_GROUP &&
+                         h_utables[0].fmt == PK_TFMT_G32 && tu.rank_atomic == 1;
+    if (pl.pb2 && !l2_path) {
         dim3 grid((pl.cap1 + PT_TILE - 1) / PT_TILE, pl.n_regions1);
         partition_fine_kernel<<<grid, PT_THREADS, 0, s>>>(a);
     }
@@ -1402,6 +1490,17 @@ void pk_part_probe(const uint64_t *d_words, const uint32_t *d_mask, uint64_t p0,
     p.out_fine = 0;
     if (evs) cudaEventRecord(evs[2], s);
     bool regions_done = false;         // the regions have been answered for ALL genomes by the L1/L2 group kernel
+    if (l2_path) {
+        ProbeArgs q = p;
+        q.buf = (const uint2 *)sc.buf1; q.counts = sc.cursor1; q.cap = pl.cap1; q.n_regions = pl.n_regions1; q.pb = pl.pb1; q.pb2 = 0;
+        q.grp = 0; q.g_first = 0; q.n_genomes = n_local; q.ng = 1; q.tbits = PK_U_GROUP; q.out_fine = pl.out_fine;
+        q.tabs[0] = h_utables[0];
+        const K3L2Variant &gv = k3g_variants[tu.k3_l2 <= pk_part_n_gvariants() ? tu.k3_l2 - 1 : 0];
+        dim3 grid((pl.cap1 + gv.cap - 1) / gv.cap, pl.n_regions1);
+        gv.fn<<<grid, gv.threads, 0, s>>>(q);
+        last_window = 5;
+        regions_done = true;
+    }
     for (uint32_t grp = 0; grp < n_groups && !regions_done; grp++) {       // one launch per group of 32 genomes
         const uint32_t ngen = n_local - 32 * grp < 32 ? n_local - 32 * grp : 32;
         p.grp = grp; p.g_first = 32 * grp; p.n_genomes = ngen;

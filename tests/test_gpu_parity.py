@@ -642,12 +642,17 @@ def test_k3_tuning_knobs_do_not_change_results(n_genomes, k, load):
             assert eng.group_stats(0)["bytes"] == bytes64
         # k3_lean: the lean K3 (one 32-bit-slot group table, compact items, fine bins), every variant, and the general
         # window kernel (0) on the same launch; on other launches (k = 31: 64-bit slots) the knob changes nothing
-        for knobs in (dict(k3_window=1), dict(k3_window=0), dict(k3_window=1, k3_lean=0), dict(k3_lean=2), dict(k3_lean=3),
-                      dict(k3_lean=4), dict(k3_lean=5), dict(k3_lean=6), dict(k3_lean=1)):
+        # k3_l2: the form without K2 (coarse regions probed through L2; the default), every block shape; 0: K2 + window kernels
+        state = dict(k3_window=1, k3_lean=1, k3_l2=7)
+        for knobs in (dict(k3_window=1), dict(k3_l2=0), dict(k3_window=0), dict(k3_window=1, k3_lean=0), dict(k3_lean=2), dict(k3_lean=3),
+                      dict(k3_lean=4), dict(k3_lean=5), dict(k3_lean=6), dict(k3_lean=1), dict(k3_l2=1), dict(k3_l2=2), dict(k3_l2=3),
+                      dict(k3_l2=4), dict(k3_l2=5), dict(k3_l2=6), dict(k3_l2=8), dict(k3_l2=9), dict(k3_l2=10), dict(k3_l2=7)):
             eng.tune(**knobs)
+            state.update(knobs)
             got = eng.anchor_genome(seqs)
-            if k == 21 and knobs.get("k3_window", 1):
-                assert int(eng.stats()["k_probe_window"]) == (2 if knobs.get("k3_lean") == 0 else 4), knobs
+            if k == 21:
+                want_kernel = 5 if state["k3_l2"] else 3 if not state["k3_window"] else 2 if state["k3_lean"] == 0 else 4
+                assert int(eng.stats()["k_probe_window"]) == want_kernel, (knobs, state)
             gz = eng.anchor_genome_bgzf(seqs)
             assert (got["col_sums"] == want["col_sums"]).all() and (gz["col_sums"] == want["col_sums"]).all(), knobs
             for a, b in zip(got["chroms"], want["chroms"]):
