@@ -1164,10 +1164,24 @@ __global__ void __launch_bounds__(T, MINB) probe_g32l2_kernel(const __grid_const
     for (int j = 0; j < IPT; j++) it[j] = tid + j * T < cnt ? src[tid + j * T] : make_uint2(0, 0);
     for (uint32_t i = tid; i < a.n_bins; i += T) o_cnt[i] = 0;
     __syncthreads();
+    // Ranks inside the position bins, WARP-AGGREGATED: K1 appends to a coarse region tile after tile, so a region's items
+    // are in position order and the ~1000 consecutive items of a block fall into two or three bins — one shared-memory
+    // atomicAdd per item meant 32 lanes on one address (ncu: 29 wavefronts per ATOMS, 124 M of the kernel's 138 M
+    // shared wavefronts, profiles/r2ag_ncu_k1_k3l2_k4.txt). The lanes that share a bin elect a leader that adds
+    // their number once. (The same order makes a block's result runs hundreds of items long: its stores coalesce.)
+    const uint32_t lane = tid & 31;
     uint32_t rk[IPT];
 #pragma unroll
-    for (int j = 0; j < IPT; j++)
-        rk[j] = tid + j * T < cnt ? atomicAdd(&o_cnt[(it[j].y & PT_CI_POS_MASK) >> sh], 1u) : 0u;
+    for (int j = 0; j < IPT; j++) {
+        const bool valid = tid + j * T < cnt;
+        const uint32_t bin = valid ? (it[j].y & PT_CI_POS_MASK) >> sh : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t first = 0;
+        if (valid && lane == leader) first = atomicAdd(&o_cnt[bin], (uint32_t)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        rk[j] = first + __popc(peers & ((1u << lane) - 1));
+    }
     // the probes' loads are issued before the ranks are complete: nothing below the barrier depends on them
     const uint32_t h_top = r << (32 - a.pb);
     uint32_t bits[IPT];
