@@ -535,7 +535,9 @@ def main():
                 assert p["npos"] == max_npos
                 sh.probe_allgather(p["words"].data_ptr(), p["mask"].data_ptr(), p["npos"], d_local, d_planes, d_rows)
             else:
-                sh.probe_exchange(p["words"].data_ptr(), p["mask"].data_ptr(), p["npos"], p["segs"], d_slice, timing=timing)
+                # the gather of this anchor runs on a side stream under the probe of the next one (the planes alternate)
+                sh.probe_exchange(p["words"].data_ptr(), p["mask"].data_ptr(), p["npos"], p["segs"], d_slice, timing=timing,
+                                  overlap=True)
 
     def barrier():
         if world > 1:
@@ -561,6 +563,8 @@ def main():
         ev[0].record(stream)
         for i in range(args.steps):
             device_step(timing=tev if i == args.steps - 1 else None)
+            if i == args.steps - 1:
+                sh.finish_exchange()             # the last gather belongs to the timed region
             ev[i + 1].record(stream)
         barrier()
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -734,7 +738,7 @@ def main():
                        "ms": r["ms_per_step"]}
             else:
                 cpu = {"value": None, "unit": unit, "cores": 0, "kind": "reference", "sample": r["unavailable"]}
-        per_probe = 3 + (1 if ks["k_fine_ms"] > 0 else 0) + (1 if ks["k_unpermute_ms"] > 0 else 0)
+        per_probe = 3 + (1 if ks["k_fine_ms"] > 0 and win != 5 else 0) + (1 if ks["k_unpermute_ms"] > 0 else 0)      # K1, [K2,] K3, spill drain, [K4]
         launches = (per_probe + (1 if rg > 1 else 0)) * len(packed) * args.steps
         cfg = workload_config(wl, args, world)
         cfg["positions_per_step"] = positions_all
@@ -747,7 +751,7 @@ def main():
                     "parallelism": ("1 GPU" if world == 1 else
                                     f"{rp} genome group(s) x {rg} rank(s); " +
                                     ("no exchange (replica groups take the anchors round-robin)" if rg == 1 else
-                                     ("position-split peer-memory exchange (gather_slice_kernel over NVLink, one barrier per anchor)"
+                                     ("position-split peer-memory exchange (gather_slice_kernel over NVLink on a side stream under the next probe, one barrier per anchor)"
                                       if args.exchange == "slice" else "NCCL all-gather + interleave"))),
                     "setup_s": round(setup_s, 1)})
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,

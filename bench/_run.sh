@@ -1,3 +1,10 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "k3_tuning or partitioned_path_large" > gpurun_out/r2ai_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2ai_pytest.log
-timeout 600 python bench/k3_sweep.py --workload configs1 --steps 5 --out gpurun_out/r2ai_sweep_warp_rank.json k3_l2=7 k3_l2=1 k3_l2=2 k3_l2=4 k3_l2=9 k3_l2=10 k3_l2=5 k3_l2=0 > gpurun_out/r2ai_sweep.log 2>&1; tail -9 gpurun_out/r2ai_sweep.log
+timeout 600 python -m pytest tests/test_multigpu.py -x -q -m gpu > gpurun_out/r2al_pytest_2gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2al_pytest_2gpu.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-e2e > gpurun_out/r2al_configs1_n2.json 2> gpurun_out/r2al_configs1_n2.err; echo "configs1 n2 rc=$?"
+python - <<'P'
+import json
+for l in open('gpurun_out/r2al_configs1_n2.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print('N2 ms',d['ms_per_step'],'G/s',d['value']/1e9,'exch',{k:v for k,v in d['exchange'].items() if k!='what'}, d['step_ms'])
+P
+tail -3 gpurun_out/r2al_configs1_n2.err

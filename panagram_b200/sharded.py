@@ -173,6 +173,8 @@ class ShardedAnchorer:
         self.stream = torch.cuda.Stream(device=self.dev)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._gather_stream = None   # side stream of probe_exchange(overlap=True)
+        self._gather_done = None     # event: the overlapped gather of the previous step
         self._planes = None          # [2] ping-pong: {"rows", "own", "peers"}
         self._host_rows = None       # page-locked staging of anchor_genome(rows_to_host=True), grow-only
         self._host_gz = None         # page-locked staging of the BGZF image of the slice
@@ -227,27 +229,49 @@ class ShardedAnchorer:
             dist.all_reduce(self._flag, group=self.group)
 
     # ---- device-level step (bench.py and the parity tests drive this) ----
-    def probe_exchange(self, d_words: int, d_mask: int, npos: int, segments, d_rows, timing=None):
+    def finish_exchange(self):
+        """After probe_exchange(..., overlap=True): self.stream waits for the gather still running on the side stream."""
+        if self._gather_stream is not None:
+            self.stream.wait_stream(self._gather_stream)
+
+    def probe_exchange(self, d_words: int, d_mask: int, npos: int, segments, d_rows, timing=None, overlap: bool = False):
         """Probe all `npos` positions against the local shard into this rank's plane, barrier, then assemble THIS
         rank's slice (`segments`, from stream_segments) of the full rows into d_rows [(rows of the slice), row_bytes].
         Call under `with torch.cuda.stream(self.stream)`. One barrier per step: planes alternate, and a rank
         reaches the barrier of step i only after its own gather of step i-1, so when the barrier of step i
         releases, nobody still reads the plane that step i+1 overwrites. `timing` = 3 CUDA events recorded
-        before the probe, after the barrier and after the gather."""
+        before the probe, after the barrier and after the gather.
+        overlap=True: the gather runs on a side stream, under the probe of the NEXT step (which writes the other plane;
+        the gather kernel uses no shared memory and few registers, it fits beside the probe kernels). The invariant
+        above is kept by making this stream wait for the rank's own previous gather before it enters the barrier.
+        d_rows is complete after finish_exchange() (or the next step's barrier)."""
+        import torch
         eng, st = self.engine, self.stream.cuda_stream
         pl = self._planes[self._i & 1]
         self._i += 1
         if timing:
             timing[0].record(self.stream)
         eng.probe_device(d_words, d_mask, 0, npos, pl["own"], self.w, 0, st)
+        if self._gather_done is not None:
+            self.stream.wait_event(self._gather_done)       # no-op unless an overlapped gather is still in flight
+            self._gather_done = None
         self.barrier()
         if timing:
             timing[1].record(self.stream)
+        gs = self.stream
+        if overlap:
+            if self._gather_stream is None:
+                self._gather_stream = torch.cuda.Stream(device=self.dev)
+            gs = self._gather_stream
+            gs.wait_stream(self.stream)                     # the barrier (and through it every peer's probe) comes first
         if segments:
             eng.gather_slice_device(pl["peers"], pl["rows"], self.w, segments, d_rows.data_ptr(), d_rows.shape[1],
-                                    self.row_bytes, st)
+                                    self.row_bytes, gs.cuda_stream)
+        if overlap:
+            self._gather_done = torch.cuda.Event()
+            self._gather_done.record(gs)
         if timing:
-            timing[2].record(self.stream)
+            timing[2].record(gs)
         return d_rows
 
     def probe_allgather(self, d_words: int, d_mask: int, npos: int, d_local, d_planes, d_rows):

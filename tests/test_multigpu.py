@@ -91,6 +91,13 @@ def _worker(rank, world, port, tmp, q):
                 sa.probe_exchange(d_words.data_ptr(), d_mask.data_ptr(), npos, [(s0, s1 - s0, 0)], d_slice)
             sa.stream.synchronize()
             ok_slice = bool((d_slice.cpu().numpy() == nccl_rows[s0:s1]).all())
+            # the same with every gather on the side stream, under the next step's probe
+            d_slice.zero_()
+            for _ in range(4):
+                sa.probe_exchange(d_words.data_ptr(), d_mask.data_ptr(), npos, [(s0, s1 - s0, 0)], d_slice, overlap=True)
+            sa.finish_exchange()
+            sa.stream.synchronize()
+            ok_slice = ok_slice and bool((d_slice.cpu().numpy() == nccl_rows[s0:s1]).all())
         # ---- product level: a whole anchor directory written by both ranks
         fa = os.path.join(tmp, "g3.fa")
         if rank == 0:
