@@ -31,8 +31,11 @@ def test_reference_arm_prints_one_contract_line():
 
 
 def test_committed_gpu_line_has_roofline_and_baseline():
-    d = json.loads((ROOT / "profiles" / "r1p_bench_configs1.json").read_text())
+    d = json.loads((ROOT / "profiles" / "r2ak_bench_configs1.json").read_text())
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    assert d["roofline"]["physical"]["dram_bytes_per_launch"] == d["roofline"]["traffic"] > 0      # measured live by the ncu child
+    assert d["roofline"]["stage"]["frac"] < d["roofline"]["frac"] < 1.0
+    assert d["cpu_baseline"]["sample"].startswith("the whole workload")                               # same size as our arm
     assert d["config"]["workload"].startswith("configs[1]") and "model" not in d["config"]
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
