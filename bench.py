@@ -22,7 +22,8 @@ of Rp genome groups x Rg ranks (`--genome-ranks`; default: as few ranks per grou
 replicas of the tables and take the anchors round-robin, ranks of a group shard the genomes and exchange as above.
 
 `value`     device-resident: packed anchor(s) already in HBM, CUDA events around the probe stage
-            (partition + probe + un-permute kernels [+ barrier + exchange kernel at Rg > 1]).
+            (partition + probe + un-permute kernels [+ barrier + exchange kernel at Rg > 1; the exchange of an anchor
+            runs on a side stream under the probe of the next one, the last one inside the timed region]).
 `e2e`       the public call a user makes with HOST buffers (N=1: Engine.anchor_genome -> pk_anchor_genome;
             N>1: ShardedAnchorer.anchor_genome): ASCII in from pinned memory, bitmap rows / low-res rows /
             histograms / column sums out to host memory, all copies inside the timed region.

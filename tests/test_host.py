@@ -84,6 +84,13 @@ def test_synth_is_deterministic_and_shaped():
     assert bytes(a[1][1][:100]).islower()
     g0 = synth.genome_codes(anc, 0, 1)
     assert 0.001 < (g0 != anc).mean() < 0.003
+    # bench.py's weak-scaling shards: with mu_period = shard width, genome g of every shard has the divergence RATE of
+    # genome g of shard 0 (same table size, same work per GPU) but its own mutations
+    big = synth.ancestor_codes(400_000, 7)
+    g8_default, g8_shard = synth.genome_codes(big, 8, 7), synth.genome_codes(big, 8, 7, mu_period=8)
+    assert 0.016 < (g8_default != big).mean() < 0.020 and 0.0015 < (g8_shard != big).mean() < 0.0025
+    assert (g8_shard != synth.genome_codes(big, 0, 7, mu_period=8)).any()
+    assert (synth.genome_codes(big, 3, 7) == synth.genome_codes(big, 3, 7, mu_period=8)).all()
 
 
 def test_index_prepare_writes_reference_config_files(pan3, tmp_path):
