@@ -318,7 +318,12 @@ int pk_anchor_paircount_bins(pk_engine *e, uint32_t n_chroms, const uint64_t *nk
  * padded to that size), "unpermute" (0/1: applies to
  * scratch allocated afterwards), "e2e_batches" (1..8: batches of whole chromosomes per pk_anchor_genome call;
  * copies of one batch overlap the kernels of the other), "e2e_batch_min" (positions from which a genome is
- * split into batches; default 32 Mi). Unknown names return PK_EINVAL. */
+ * split into batches; default 32 Mi), "e2e_front_small" (0/1: which batch an evenly split chromosome joins),
+ * "k3_l2" (one 32-bit-slot group table, one-byte rows: 0 = second partition pass + window kernels, v >= 1 = no second
+ * pass, the coarse regions are probed through L2 by block shape v; default 7 = 256 threads x 4 items), "k3_lean" (the
+ * same launches with k3_l2 = 0: 0 = general window kernel, v >= 1 = lean window kernel variant v), "k3w_big",
+ * "compact_items", "k1_roll", "fine_out", "fine_shift", "k3_rank_atomic" (experiment knobs of those kernels; see
+ * csrc/pk_internal.h). Unknown names return PK_EINVAL. */
 int pk_engine_tune(pk_engine *e, const char *name, int value);
 
 /* timing / accounting of the last pk_anchor_chrom or pk_get_counters_for_read */
