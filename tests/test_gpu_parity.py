@@ -931,8 +931,13 @@ def test_s32_overfull_neighbourhood_goes_to_the_stash():
 
 def test_full_size_configs1_properties():
     """BASELINE configs[1] at full size (8 x 135 Mbp, k=21, anchor = genome 0) through the public call:
-    size-independent properties of the reference's output (SURVEY §4 [probed]) on all 135 M rows, and
-    bit-exact agreement of the partitioned path with the direct kernel and the C oracle on samples."""
+    size-independent properties of the reference's output (SURVEY §4 [probed]) on all 135 M rows — the anchor's own
+    column, zero rows exactly under invalid windows, low-res phase, every bin's popcount histogram, column sums — the
+    BGZF images of the same rows, and bit-exact agreement of the default path (K1 -> probe_g32l2_kernel -> K4) with the
+    direct kernel on a 3 M-position slice. The byte-for-byte comparison of this configuration with the UNMODIFIED
+    reference (all 8 columns, all rows) is `bench.py --index-e2e configs1`
+    (profiles/r2ag_index_configs1_full_vs_reference.json: it needs ~90 s of kmc + run_anchor, too long for this suite);
+    32- and 64-genome cases are compared with the C oracle on every position in test_many_genomes_at_20mbp_vs_c_oracle."""
     from panagram_b200 import synth
     k, n, length, seed = 21, 8, 135_000_000, 20260001
     anc = synth.ancestor_codes(length, seed)
